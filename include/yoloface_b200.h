@@ -1,0 +1,118 @@
+/*
+ * yoloface_b200.h -- B200 extensions next to the X-CUBE-AI style API of network.h.
+ *
+ * The reference API stops at "one int8 image in, one int8 head out" (ai_network_run,
+ * network.h:193-195) with a 16-bit batch field (ai_platform.h:519).  These entry points cover
+ * what a GPU caller needs beyond that, without changing the reference calls:
+ *   - batches above 65,535 and explicit host/device pointers           (yf_b200_run)
+ *   - head decode + NMS on device: yoloface.c:105-152 / tflite_prediction.py:43-57 /
+ *     yoloface_test.py:148-201                                          (yf_b200_detect, yf_b200_decode)
+ *   - camera-side pre-processing on device: yoloface.c:26-93           (yf_b200_preprocess_rgb565)
+ *   - per-operator tensors, the analogue of ST's observer API
+ *     (ai_platform_interface.h:695-731)                                 (yf_b200_set_observer, yf_b200_get_tensor)
+ *   - other input resolutions of the fully-convolutional graph          (yf_b200_set_input_size)
+ * All functions return >= 0 on success and a negative value on failure, latching an ai_error
+ * readable through ai_network_get_error().
+ */
+#ifndef YOLOFACE_B200_H
+#define YOLOFACE_B200_H
+
+#include "ai_platform.h"
+
+AI_API_DECLARE_BEGIN
+
+#define YF_B200_CONFIG_MAGIC 0x32424659u /* "YFB2" */
+
+/* Optional configuration, passed to ai_network_create() as
+ *   ai_buffer cfg = AI_BUFFER_OBJ_INIT(AI_BUFFER_FORMAT_U8, 1, 1, sizeof(yf_b200_config), 1, &config);
+ * NULL keeps the defaults (environment: YF_B200_DEVICE, YF_B200_CHUNK, YF_B200_TFLITE). */
+typedef struct yf_b200_config_ {
+  uint32_t magic;          /* YF_B200_CONFIG_MAGIC */
+  int32_t device;          /* CUDA ordinal; -1 = YF_B200_DEVICE or the current device */
+  uint32_t chunk_images;   /* images processed per pipeline chunk; 0 = default */
+  uint32_t flags;          /* YF_B200_FLAG_* */
+  const char* tflite_path; /* NULL = model embedded in the library */
+} yf_b200_config;
+
+#define YF_B200_FLAG_OBSERVER 0x1u   /* keep every operator's tensor (slower, more memory) */
+
+typedef struct yf_b200_det_ {
+  float x1, y1, x2, y2, conf;        /* corners in input pixels (tflite_prediction.py:5-11), confidence */
+} yf_b200_det;
+
+#define YF_B200_NMS_PLUS_ONE 0x1     /* integer "+1" box area convention of yoloface_test.py:172-186 */
+
+/* Input size of the fully convolutional graph (multiples of 8); default 56x56 (network.h:38-52). */
+AI_API_ENTRY int32_t yf_b200_set_input_size(ai_handle network, int32_t height, int32_t width);
+
+/* n images [n,H,W,3] int8 -> heads [n,H/8,W/8,18] int8.  `in`/`out` may each be host or device
+ * memory (host memory is fastest when page-locked).  Returns n. */
+AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, uint32_t n);
+
+/* Decode + NMS of heads already computed ([n,gh,gw,18] int8, host or device).
+ * conf_thr: keep conf >= conf_thr (0.7 in yoloface.c:123); iou_thr < 0: threshold only (what the
+ * firmware does), else greedy NMS keeping iou <= iou_thr (0.4 in yoloface_test.py:32).
+ * dets: [n, max_det] records, counts: [n] (host memory).  Returns total detections. */
+AI_API_ENTRY int32_t yf_b200_decode(ai_handle network, const void* heads, uint32_t n, float conf_thr, float iou_thr,
+                                    uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det);
+
+/* Inference + decode + NMS in one call; only detections travel back to the host.
+ * heads_out may be NULL. */
+AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t n, float conf_thr, float iou_thr,
+                                    uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det,
+                                    void* heads_out);
+
+/* n RGB565 112x112 frames (big-endian byte pairs, as OV2640 delivers them: yoloface.c:41-47)
+ * -> int8 [n,56,56,3] network inputs.  Host or device pointers. */
+AI_API_ENTRY int32_t yf_b200_preprocess_rgb565(ai_handle network, const void* frames, void* out, uint32_t n);
+
+/* Observer mode: after a run of at most one chunk, every TFLite tensor that is materialised can
+ * be read back densely ([n,H,W,C] int8).  Returns bytes written, or <0 if that tensor is folded
+ * away (PAD outputs) or n exceeds the last run. */
+AI_API_ENTRY int32_t yf_b200_set_observer(ai_handle network, int32_t enable);
+AI_API_ENTRY int64_t yf_b200_get_tensor(ai_handle network, int32_t tflite_tensor, uint32_t n, void* dst, uint64_t dst_bytes);
+/* shape of a TFLite tensor at the current input size: dims[4] = {1,H,W,C}; returns 0 if known */
+AI_API_ENTRY int32_t yf_b200_tensor_shape(ai_handle network, int32_t tflite_tensor, int32_t dims[4]);
+
+typedef struct yf_b200_stats_ {
+  uint64_t kernel_launches;   /* kernels of this library launched since create */
+  uint64_t images;            /* images inferred since create */
+  float last_run_device_ms;   /* CUDA-event time of the last run's kernels (excl. copies) */
+  int32_t device;
+  int32_t sm_count;
+  uint32_t chunk_images;
+  int32_t steps;              /* fused device steps per image batch (26 for yoloface) */
+} yf_b200_stats;
+AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* stats);
+
+/* Per-step description (name, TFLite ops folded, algorithmic bytes/MACs per image) for reports. */
+typedef struct yf_b200_step_info_ {
+  char name[32];
+  int32_t kind;               /* 0 im2col conv, 1 conv1x1, 2 depthwise, 3 maxpool, 4 lut */
+  int32_t first_op, n_ops;
+  int64_t macs;               /* per image */
+  int64_t bytes_read, bytes_written;  /* algorithmic (unpadded) per image, weights excluded */
+  float last_ms;              /* device time of this step in the last profiled run, <0 if none */
+} yf_b200_step_info;
+AI_API_ENTRY int32_t yf_b200_step_count(ai_handle network);
+AI_API_ENTRY int32_t yf_b200_step_info_get(ai_handle network, int32_t step, yf_b200_step_info* info);
+/* time every step of the next run with CUDA events (adds a sync per step) */
+AI_API_ENTRY int32_t yf_b200_set_step_profiling(ai_handle network, int32_t enable);
+
+/* Page-locked host memory for the fast host path. */
+AI_API_ENTRY void* yf_b200_host_alloc(uint64_t bytes);
+AI_API_ENTRY void yf_b200_host_free(void* p);
+
+/* Plan introspection -- pure host code, usable without a GPU (tests validate the lowering on CPU).
+ * yf_b200_plan_json: JSON description of the fused steps / buffers / tensor placement for an HxW
+ * input built from the embedded model (weights from `blob` in ST layout, or the model's own if
+ * NULL).  yf_b200_plan_blob: raw tables, what = 0 EpiCh[], 1 LUTs (n x 256), 2 packed weights.
+ * Both return the number of bytes needed (copying min(cap, needed)), <0 on failure. */
+AI_API_ENTRY int64_t yf_b200_plan_json(int32_t height, int32_t width, const void* blob, char* dst, uint64_t cap);
+AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t height, int32_t width, const void* blob, int32_t what, void* dst, uint64_t cap);
+
+/* Human-readable text of the last failure (CUDA error string, plan error, ...). */
+AI_API_ENTRY const char* yf_b200_last_error_text(void);
+
+AI_API_DECLARE_END
+#endif

@@ -1,0 +1,803 @@
+// yf_api.cu -- the C-ABI of libyoloface_b200.so: X-CUBE-AI style entry points (include/network.h,
+// include/network_data.h) plus the B200 extensions (include/yoloface_b200.h), on top of the plan
+// (yf_plan.cc) and the sm_100a kernels (yf_kernels.cu).  No CPU execution path exists: without a
+// usable CUDA device ai_network_create() fails with AI_ERROR_CREATE_FAILED.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/network.h"
+#include "../../include/network_data.h"
+#include "../../include/yoloface_b200.h"
+#include "yf_kernels.cuh"
+#include "yf_plan.h"
+
+// the .tflite the reference deploys (yoloface/tflite/yoloface_int8.tflite), embedded at build time
+extern "C" const unsigned char yf_embedded_model[];
+extern "C" const unsigned int yf_embedded_model_len;
+
+namespace {
+
+using namespace yf;
+
+thread_local std::string g_text;
+void set_text(const std::string& s) { g_text = s; }
+
+// One compiled resolution: plan + device-side constants + arena.
+struct PlanDev {
+  Plan plan;
+  uint32_t cap = 0;                     // images per chunk the arena holds
+  bool observer = false;
+  uint8_t* d_wblob = nullptr;
+  uint8_t* d_luts = nullptr;
+  uint8_t* d_arena = nullptr;
+  int8_t* d_in = nullptr;               // staging for host inputs [cap,H,W,3]
+  int8_t* d_head = nullptr;             // staging for host outputs [cap,GH,GW,18]
+  std::vector<CUtensorMap> tmaps;       // per step (conv1x1 only)
+  std::vector<float> step_ms;
+  ~PlanDev() {
+    cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head);
+  }
+};
+
+struct Network {
+  bool initialized = false;
+  ai_error err{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+  TflModel model;
+  std::vector<uint8_t> blob;            // weights handed to ai_network_init (ST layout)
+  int device = 0, sm_count = 148;
+  uint32_t chunk = 1024;
+  bool observer = false, step_profiling = false;
+  int H = 56, W = 56;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int* d_err = nullptr;
+  float* d_dets = nullptr; int* d_counts = nullptr; size_t dets_cap = 0; uint32_t dets_max = 0;
+  uint8_t* d_frames = nullptr; size_t frames_cap = 0;
+  std::map<std::pair<int, int>, std::unique_ptr<PlanDev>> plans;
+  PlanDev* active_epi = nullptr;        // whose EpiCh table sits in __constant__ memory
+  uint32_t last_run_n = 0;
+  uint64_t launches = 0, images = 0;
+  float last_ms = 0.f;
+  void latch(int type, int code) { if (err.type == AI_ERROR_NONE) { err.type = type; err.code = code; } }
+};
+
+std::mutex g_mu;
+Network* g_net = nullptr;               // singleton context, like ST's g_network (network.c:36)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool cuda_ok(Network* n, cudaError_t e, const char* what, int type = AI_ERROR_INVALID_STATE, int code = AI_ERROR_CODE_NETWORK) {
+  if (e == cudaSuccess) return true;
+  set_text(std::string(what) + ": " + cudaGetErrorString(e));
+  if (n) n->latch(type, code);
+  return false;
+}
+
+Network* as_net(ai_handle h) {
+  return (h && h == g_net) ? g_net : nullptr;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- plan instantiation ------------------------------------------------------------------
+PlanDev* get_plan(Network* n, int H, int W) {
+  auto key = std::make_pair(H, W);
+  auto it = n->plans.find(key);
+  if (it != n->plans.end() && it->second->observer == n->observer && it->second->cap == n->chunk) return it->second.get();
+  if (it != n->plans.end()) { if (n->active_epi == it->second.get()) n->active_epi = nullptr; n->plans.erase(it); }
+  std::unique_ptr<PlanDev> pd(new PlanDev);
+  std::string perr;
+  if (!build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->plan, &perr)) {
+    set_text("plan: " + perr); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr;
+  }
+  Plan& P = pd->plan;
+  if (P.epi.size() > static_cast<size_t>(kMaxEpiCh)) { set_text("too many output channels for the constant table"); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_LAYER); return nullptr; }
+  pd->cap = n->chunk; pd->observer = n->observer;
+  const size_t per_img = n->observer ? P.arena_bytes_per_image_observer : P.arena_bytes_per_image;
+  const int al = AI_ERROR_ALLOCATION_FAILED, ac = AI_ERROR_CODE_NETWORK_ACTIVATIONS;
+  if (!cuda_ok(n, cudaMalloc(&pd->d_wblob, std::max<size_t>(P.wblob.size(), 16)), "cudaMalloc weights", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+  if (!cuda_ok(n, cudaMalloc(&pd->d_luts, std::max<size_t>(P.luts.size(), 256)), "cudaMalloc luts", al, ac)) return nullptr;
+  if (!cuda_ok(n, cudaMalloc(&pd->d_arena, per_img * pd->cap + 1024), "cudaMalloc arena", al, ac)) return nullptr;
+  if (!cuda_ok(n, cudaMalloc(&pd->d_in, static_cast<size_t>(H) * W * 3 * pd->cap), "cudaMalloc input staging", al, ac)) return nullptr;
+  if (!cuda_ok(n, cudaMalloc(&pd->d_head, static_cast<size_t>(P.GH) * P.GW * 18 * pd->cap), "cudaMalloc head staging", al, ac)) return nullptr;
+  if (!cuda_ok(n, cudaMemcpyAsync(pd->d_wblob, P.wblob.data(), P.wblob.size(), cudaMemcpyHostToDevice, n->stream), "upload weights")) return nullptr;
+  if (!P.luts.empty() && !cuda_ok(n, cudaMemcpyAsync(pd->d_luts, P.luts.data(), P.luts.size(), cudaMemcpyHostToDevice, n->stream), "upload luts")) return nullptr;
+  // pad channels of every buffer must read as defined bytes: clear the arena once
+  if (!cuda_ok(n, cudaMemsetAsync(pd->d_arena, 0, per_img * pd->cap + 1024, n->stream), "clear arena")) return nullptr;
+  // TMA descriptors of the 1x1-conv A operands: 2-D [rows = cap*H*W, CP bytes], box 128 rows x 16 B
+  pd->tmaps.resize(P.steps.size());
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_text("cuTensorMapEncodeTiled entry point unavailable"); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr; }
+  for (size_t i = 0; i < P.steps.size(); ++i) {
+    const Step& s = P.steps[i];
+    if (s.kind != STEP_CONV1X1) continue;
+    const PBuffer& b = P.buffers[s.in_buf];
+    void* base = pd->d_arena + b.offset * pd->cap;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(b.CP), static_cast<cuuint64_t>(pd->cap) * b.H * b.W};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(b.CP)};
+    cuuint32_t box[2] = {16, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pd->tmaps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_text("cuTensorMapEncodeTiled failed for step " + s.name + " (CUresult " + std::to_string(r) + ")");
+      n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_TENSOR); return nullptr; }
+  }
+  pd->step_ms.assign(P.steps.size(), -1.f);
+  PlanDev* raw = pd.get();
+  n->plans[key] = std::move(pd);
+  return raw;
+}
+
+int8_t* buf_ptr(const PlanDev* pd, int buf, const int8_t* in, int8_t* head) {
+  if (buf < 0) return nullptr;
+  const PBuffer& b = pd->plan.buffers[buf];
+  if (b.is_input) return const_cast<int8_t*>(in);
+  if (b.is_output) return head;
+  if (b.observer_only && !pd->observer) return nullptr;
+  return reinterpret_cast<int8_t*>(pd->d_arena + b.offset * pd->cap);
+}
+
+EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* head) {
+  const Plan& P = pd->plan;
+  EpiOut eo{};
+  const PBuffer& ob = P.buffers[s.out_buf];
+  eo.out = buf_ptr(pd, s.out_buf, in, head); eo.out_pitch = ob.CP; eo.out_coff = s.out_coff; eo.cout = s.Cout;
+  // the step owns the pad channels of a buffer it writes from channel 0 alone
+  eo.fill_to = (s.out_coff == 0 && ob.C == s.Cout && !ob.is_output) ? ob.CP : s.Cout;
+  eo.epi_base = s.epi_base;
+  const bool obs = pd->observer;
+  if (obs && s.raw_buf >= 0) { eo.raw = buf_ptr(pd, s.raw_buf, in, head); eo.raw_pitch = P.buffers[s.raw_buf].CP; }
+  if (obs && s.mid_buf >= 0) { eo.mid = buf_ptr(pd, s.mid_buf, in, head); eo.mid_pitch = P.buffers[s.mid_buf].CP; }
+  if (obs && s.pre_add_buf >= 0) { eo.pre_add = buf_ptr(pd, s.pre_add_buf, in, head); eo.pre_add_pitch = P.buffers[s.pre_add_buf].CP; }
+  if (s.add.enabled) {
+    eo.add = s.add; eo.add_in = buf_ptr(pd, s.add_buf, in, head); eo.add_pitch = P.buffers[s.add_buf].CP; eo.add_coff = s.add_coff;
+  }
+  if (obs) {
+    eo.lut1 = s.lut1 >= 0 ? pd->d_luts + static_cast<size_t>(s.lut1) * 256 : nullptr;
+    eo.lut2 = s.lut2 >= 0 ? pd->d_luts + static_cast<size_t>(s.lut2) * 256 : nullptr;
+  } else {
+    eo.lut1 = s.lut_fused >= 0 ? pd->d_luts + static_cast<size_t>(s.lut_fused) * 256 : nullptr;
+    eo.lut2 = nullptr;
+  }
+  return eo;
+}
+
+// run the fused steps for nb images whose input is at d_in (device) writing heads to d_head (device)
+bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb) {
+  const Plan& P = pd->plan;
+  if (n->active_epi != pd) {
+    if (!cuda_ok(n, upload_epi_table(P.epi.data(), static_cast<int>(P.epi.size()), n->stream), "upload epilogue table")) return false;
+    n->active_epi = pd;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (n->step_profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  for (size_t i = 0; i < P.steps.size(); ++i) {
+    const Step& s = P.steps[i];
+    const EpiOut eo = make_epi_out(pd, s, d_in, d_head);
+    cudaError_t e = cudaSuccess;
+    if (n->step_profiling) cudaEventRecord(e0, n->stream);
+    switch (s.kind) {
+      case STEP_CONV1X1: {
+        Conv1x1Args a{};
+        a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
+        a.nchunk = P.buffers[s.in_buf].CP / 16; a.nk = s.Kpad / 32;
+        a.M = static_cast<long long>(nb) * s.Hout * s.Wout; a.num_tiles = static_cast<int>((a.M + 127) / 128);
+        a.eo = eo; a.err = n->d_err;
+        e = launch_conv1x1(pd->tmaps[i], a, s.Npad, n->sm_count, n->stream);
+        break; }
+      case STEP_CONV_IM2COL: {
+        ConvIm2colArgs a{};
+        a.in = d_in; a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
+        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
+        a.band_rows = s.band_rows; a.bands = s.bands; a.in_zp = s.in_zp; a.eo = eo; a.err = n->d_err;
+        e = launch_conv_im2col(a, s.Npad, n->sm_count, n->stream);
+        break; }
+      case STEP_DW: {
+        DwArgs a{};
+        a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP;
+        a.w1h = reinterpret_cast<const uint32_t*>(pd->d_wblob + s.w_off);
+        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
+        a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.in_zp = s.in_zp; a.words = (s.Cout + 3) / 4; a.eo = eo;
+        e = launch_dw(a, n->stream);
+        break; }
+      case STEP_MAXPOOL: {
+        PoolArgs a{};
+        a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP;
+        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
+        a.k = s.kh; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.words = (s.Cout + 3) / 4; a.eo = eo;
+        e = launch_pool(a, n->stream);
+        break; }
+      case STEP_LUT: {
+        LutArgs a{};
+        a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP; a.in_coff = s.in_coff;
+        a.rows = static_cast<long long>(nb) * s.Hout * s.Wout; a.words = (s.Cout + 3) / 4; a.eo = eo;
+        e = launch_lut(a, n->stream);
+        break; }
+    }
+    if (!cuda_ok(n, e, s.name.c_str())) return false;
+    ++n->launches;
+    if (n->step_profiling) {
+      cudaEventRecord(e1, n->stream); cudaEventSynchronize(e1);
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); pd->step_ms[i] = ms;
+    }
+  }
+  if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  return true;
+}
+
+bool check_device_err(Network* n) {
+  int herr = 0;
+  if (!cuda_ok(n, cudaMemcpyAsync(&herr, n->d_err, sizeof(int), cudaMemcpyDeviceToHost, n->stream), "read device status")) return false;
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "synchronize")) return false;
+  if (herr != 0) {
+    set_text("device pipeline watchdog fired (code " + std::to_string(herr) + ")");
+    cudaMemsetAsync(n->d_err, 0, sizeof(int), n->stream);
+    n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_LAYER);
+    return false;
+  }
+  return true;
+}
+
+// inference of n images; in/out host or device
+int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool keep_heads_on_device, int8_t** dev_heads) {
+  PlanDev* pd = get_plan(n, n->H, n->W);
+  if (!pd) return -1;
+  const Plan& P = pd->plan;
+  const size_t in_sz = static_cast<size_t>(P.H) * P.W * 3, out_sz = static_cast<size_t>(P.GH) * P.GW * 18;
+  const bool in_dev = is_device_ptr(in);
+  const bool out_dev = out ? is_device_ptr(out) : true;
+  if (in_dev && (reinterpret_cast<uintptr_t>(in) & 15)) { set_text("device input must be 16-byte aligned"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  cudaEventRecord(n->ev0, n->stream);
+  for (uint32_t done = 0; done < count; done += pd->cap) {
+    const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+    const int8_t* din = in_dev ? static_cast<const int8_t*>(in) + done * in_sz : pd->d_in;
+    if (!in_dev && !cuda_ok(n, cudaMemcpyAsync(pd->d_in, static_cast<const int8_t*>(in) + done * in_sz, nb * in_sz, cudaMemcpyHostToDevice, n->stream), "H2D input", AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR)) return -1;
+    int8_t* dhead = (out && out_dev) ? static_cast<int8_t*>(out) + done * out_sz : pd->d_head;
+    if (!run_steps(n, pd, din, dhead, nb)) return -1;
+    if (out && !out_dev && !cuda_ok(n, cudaMemcpyAsync(static_cast<int8_t*>(out) + done * out_sz, pd->d_head, nb * out_sz, cudaMemcpyDeviceToHost, n->stream), "D2H output", AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR)) return -1;
+    if (keep_heads_on_device && dev_heads) *dev_heads = dhead;
+    n->last_run_n = nb;
+  }
+  cudaEventRecord(n->ev1, n->stream);
+  if (!check_device_err(n)) return -1;
+  cudaEventElapsedTime(&n->last_ms, n->ev0, n->ev1);
+  n->images += count;
+  return static_cast<int32_t>(count);
+}
+
+bool ensure_dets(Network* n, uint32_t count, uint32_t max_det) {
+  const size_t need = static_cast<size_t>(count) * max_det;
+  if (need > n->dets_cap || max_det != n->dets_max) {
+    cudaFree(n->d_dets); cudaFree(n->d_counts); n->d_dets = nullptr; n->d_counts = nullptr;
+    if (!cuda_ok(n, cudaMalloc(&n->d_dets, need * 5 * sizeof(float)), "cudaMalloc detections", AI_ERROR_ALLOCATION_FAILED)) return false;
+    if (!cuda_ok(n, cudaMalloc(&n->d_counts, static_cast<size_t>(count) * sizeof(int)), "cudaMalloc counts", AI_ERROR_ALLOCATION_FAILED)) return false;
+    n->dets_cap = need; n->dets_max = max_det;
+  }
+  return true;
+}
+
+int32_t decode_on_device(Network* n, const int8_t* d_heads, uint32_t count, int gh, int gw, float conf_thr, float iou_thr,
+                         uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det) {
+  if (!ensure_dets(n, count, max_det)) return -1;
+  DecodeArgs a{};
+  a.head = d_heads; a.n_img = static_cast<int>(count); a.gh = gh; a.gw = gw;
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  a.scale = pd->plan.out_scale; a.zp = pd->plan.out_zp;
+  a.conf_thr = conf_thr; a.iou_thr = iou_thr; a.plus_one = (flags & YF_B200_NMS_PLUS_ONE) ? 1 : 0;
+  a.dets = n->d_dets; a.counts = n->d_counts; a.max_det = static_cast<int>(max_det);
+  if (!cuda_ok(n, launch_decode_nms(a, n->stream), "decode_nms")) return -1;
+  ++n->launches;
+  if (!cuda_ok(n, cudaMemcpyAsync(counts, n->d_counts, sizeof(int) * count, cudaMemcpyDeviceToHost, n->stream), "D2H counts")) return -1;
+  if (!cuda_ok(n, cudaMemcpyAsync(dets, n->d_dets, sizeof(float) * 5 * count * max_det, cudaMemcpyDeviceToHost, n->stream), "D2H detections")) return -1;
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "synchronize")) return -1;
+  long total = 0; for (uint32_t i = 0; i < count; ++i) total += counts[i];
+  return static_cast<int32_t>(total);
+}
+
+// weights handle -> blob pointer: {MARKER, blob, MARKER} table (network_data.c:395-401) or raw blob
+const uint8_t* resolve_weights(const void* data) {
+  if (!data) return nullptr;
+  const uintptr_t* t = static_cast<const uintptr_t*>(data);
+  if (t[0] == static_cast<uintptr_t>(AI_MAGIC_MARKER) && t[2] == static_cast<uintptr_t>(AI_MAGIC_MARKER))
+    return reinterpret_cast<const uint8_t*>(t[1]);
+  return static_cast<const uint8_t*>(data);
+}
+
+std::vector<uint8_t>& own_blob() {       // ST-layout blob regenerated from the embedded model
+  static std::vector<uint8_t> blob;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    TflModel m; std::string e;
+    if (m.parse(yf_embedded_model, yf_embedded_model_len, &e)) blob = st_blob_from_model(m);
+    blob.resize((blob.size() + 7) & ~size_t(7));
+  });
+  return blob;
+}
+
+void fill_report(Network* n, ai_network_report* r) {
+  static ai_buffer in_desc, out_desc;
+  std::memset(r, 0, sizeof *r);
+  r->model_name = AI_NETWORK_MODEL_NAME;
+  r->model_signature = "yoloface_int8.tflite";
+  r->model_datetime = ""; r->compile_datetime = __DATE__ " " __TIME__;
+  r->runtime_revision = "yoloface-b200 " YF_B200_BACKEND;
+  r->runtime_version = ai_platform_version{7, 0, 0, 0};
+  r->tool_revision = "yf_plan";
+  r->tool_version = ai_platform_version{AI_TOOLS_VERSION_MAJOR, AI_TOOLS_VERSION_MINOR, AI_TOOLS_VERSION_MICRO, 0};
+  r->tool_api_version = ai_platform_version{AI_TOOLS_API_VERSION_MAJOR, AI_TOOLS_API_VERSION_MINOR, AI_TOOLS_API_VERSION_MICRO, 0};
+  r->api_version = ai_platform_version{1, 1, 0, 0};
+  r->interface_api_version = ai_platform_version{1, 3, 0, 0};
+  r->n_macc = 1344320;                  /* ST's count incl. pools/activations (network.c:3296) */
+  in_desc = ai_buffer{AI_BUFFER_FORMAT_S8, 1, static_cast<ai_u16>(n->H), static_cast<ai_u16>(n->W), 3, nullptr, nullptr};
+  out_desc = ai_buffer{AI_BUFFER_FORMAT_S8, 1, static_cast<ai_u16>(n->H / 8), static_cast<ai_u16>(n->W / 8), 18, nullptr, nullptr};
+  r->n_inputs = 1; r->n_outputs = 1; r->inputs = &in_desc; r->outputs = &out_desc;
+  r->params = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, AI_NETWORK_DATA_WEIGHTS_SIZE, nullptr, nullptr};
+  r->activations = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, AI_NETWORK_DATA_ACTIVATIONS_SIZE, nullptr, nullptr};
+  r->n_nodes = AI_NETWORK_N_NODES;
+  r->signature = 0;
+}
+
+}  // namespace
+
+// ============================================================================================
+// X-CUBE-AI style API
+// ============================================================================================
+extern "C" {
+
+AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* network_config) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  ai_error err{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+  if (!network) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return err; }
+  *network = AI_HANDLE_NULL;
+  const yf_b200_config* cfg = nullptr;
+  if (network_config && network_config->data) {
+    cfg = static_cast<const yf_b200_config*>(network_config->data);
+    if (cfg->magic != YF_B200_CONFIG_MAGIC) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; set_text("network_config is not a yf_b200_config"); return err; }
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_text("no CUDA device: libyoloface_b200 has no CPU path");
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  int dev = -1;
+  if (cfg && cfg->device >= 0) dev = cfg->device;
+  else if (const char* e = std::getenv("YF_B200_DEVICE")) dev = std::atoi(e);
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return err; }
+  cudaDeviceProp prop{};
+  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  if (prop.major != 10) {
+    set_text("libyoloface_b200 carries sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  if (g_net) { delete g_net; g_net = nullptr; }     // singleton: a second create re-creates
+  std::unique_ptr<Network> n(new Network);
+  n->device = dev; n->sm_count = prop.multiProcessorCount;
+  if (cfg && cfg->chunk_images) n->chunk = cfg->chunk_images;
+  else if (const char* e = std::getenv("YF_B200_CHUNK")) n->chunk = static_cast<uint32_t>(std::max(1, std::atoi(e)));
+  n->observer = cfg && (cfg->flags & YF_B200_FLAG_OBSERVER);
+  const char* path = cfg && cfg->tflite_path ? cfg->tflite_path : std::getenv("YF_B200_TFLITE");
+  std::string perr; bool ok;
+  if (path && *path) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { set_text(std::string("cannot open ") + path); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return err; }
+    std::vector<uint8_t> buf; uint8_t tmp[65536]; size_t k;
+    while ((k = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + k);
+    std::fclose(f);
+    ok = n->model.parse(buf.data(), buf.size(), &perr);
+  } else {
+    ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr);
+  }
+  if (!ok) { set_text("model: " + perr); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; return err; }
+  if (cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
+      cudaEventCreate(&n->ev1) != cudaSuccess || cudaMalloc(&n->d_err, sizeof(int)) != cudaSuccess ||
+      cudaMemset(n->d_err, 0, sizeof(int)) != cudaSuccess || kernels_init() != cudaSuccess) {
+    set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  g_net = n.release();
+  *network = g_net;
+  return err;
+}
+
+AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Network* n = as_net(network);
+  if (!n) return network;
+  cudaSetDevice(n->device);
+  cudaStreamSynchronize(n->stream);
+  n->plans.clear();
+  cudaFree(n->d_err); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
+  cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->stream);
+  delete n; g_net = nullptr;
+  return AI_HANDLE_NULL;
+}
+
+AI_API_ENTRY ai_error ai_network_get_error(ai_handle network) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Network* n = as_net(network);
+  if (!n) return ai_error{AI_ERROR_INVALID_HANDLE, AI_ERROR_CODE_NETWORK};
+  ai_error e = n->err;
+  n->err = ai_error{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+  return e;
+}
+
+AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params* params) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Network* n = as_net(network);
+  if (!n) return false;
+  if (!params) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_NETWORK_PARAMS); return false; }
+  const ai_buffer* wbuf = &params->params; const ai_buffer* abuf = &params->activations;
+  if (params->map_signature == AI_MAGIC_SIGNATURE) {            // ai_network_data_params_get() form
+    if (!params->map_weights.buffer || params->map_weights.size < 1) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); return false; }
+    wbuf = &params->map_weights.buffer[0];
+    abuf = (params->map_activations.buffer && params->map_activations.size) ? &params->map_activations.buffer[0] : nullptr;
+  }
+  const uint8_t* blob = resolve_weights(wbuf->data);
+  if (!blob) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); set_text("weights handle is NULL"); return false; }
+  const size_t wsize = static_cast<size_t>(wbuf->height) * wbuf->width * wbuf->channels;
+  size_t need = 0; st_blob_layout(n->model, &need);
+  if (wsize < need) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); set_text("weights buffer smaller than the model's blob"); return false; }
+  if (abuf) {
+    // caller-owned arena: validated like ST's runtime does, but unused (activations live in HBM)
+    const size_t asize = static_cast<size_t>(abuf->height) * abuf->width * abuf->channels;
+    if (abuf->data && asize < AI_NETWORK_DATA_ACTIVATIONS_SIZE) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_ACTIVATIONS); set_text("activations buffer too small"); return false; }
+  }
+  n->blob.assign(blob, blob + need);
+  cudaSetDevice(n->device);
+  n->plans.clear(); n->active_epi = nullptr;
+  if (!get_plan(n, n->H, n->W)) return false;
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "init synchronize", AI_ERROR_INIT_FAILED)) return false;
+  n->initialized = true;
+  return true;
+}
+
+static ai_i32 process(ai_handle network, const ai_buffer* input, ai_buffer* output) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Network* n = as_net(network);
+  if (!n) return 0;
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return 0; }
+  if (!input || !input->data) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return 0; }
+  if (AI_BUFFER_FMT_GET(input->format) != AI_BUFFER_FORMAT_S8) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_FORMAT); return 0; }
+  if (input->height != n->H || input->width != n->W || input->channels != 3) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_SIZE); return 0; }
+  if (input->n_batches == 0) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_BATCH); return 0; }
+  if (output) {
+    if (!output->data) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return 0; }
+    if (AI_BUFFER_FMT_GET(output->format) != AI_BUFFER_FORMAT_S8) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_FORMAT); return 0; }
+    if (output->height != n->H / 8 || output->width != n->W / 8 || output->channels != 18) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_SIZE); return 0; }
+    if (output->n_batches < input->n_batches) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_BATCH); return 0; }
+  }
+  cudaSetDevice(n->device);
+  int32_t r = run_images(n, input->data, output ? output->data : nullptr, input->n_batches, false, nullptr);
+  return r < 0 ? 0 : r;
+}
+
+AI_API_ENTRY ai_i32 ai_network_run(ai_handle network, const ai_buffer* input, ai_buffer* output) {
+  if (!output) { Network* n = as_net(network); if (n) n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return 0; }
+  return process(network, input, output);
+}
+AI_API_ENTRY ai_i32 ai_network_forward(ai_handle network, const ai_buffer* input) { return process(network, input, nullptr); }
+
+AI_API_ENTRY ai_bool ai_network_get_report(ai_handle network, ai_network_report* report) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Network* n = as_net(network);
+  if (!n || !report) return false;
+  fill_report(n, report);
+  return true;
+}
+AI_API_ENTRY ai_bool ai_network_get_info(ai_handle network, ai_network_report* report) { return ai_network_get_report(network, report); }
+
+AI_API_ENTRY ai_handle ai_network_data_weights_get(void) {
+  static const void* table[3];
+  table[0] = reinterpret_cast<const void*>(static_cast<uintptr_t>(AI_MAGIC_MARKER));
+  table[1] = own_blob().data();
+  table[2] = reinterpret_cast<const void*>(static_cast<uintptr_t>(AI_MAGIC_MARKER));
+  return AI_HANDLE_PTR(table);
+}
+
+AI_API_ENTRY ai_bool ai_network_data_params_get(ai_handle network, ai_network_params* params) {
+  if (!network || !params) return false;
+  static ai_buffer w[1], a[1];
+  w[0] = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, AI_NETWORK_DATA_WEIGHTS_SIZE, own_blob().data(), nullptr};
+  a[0] = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, AI_NETWORK_DATA_ACTIVATIONS_SIZE, nullptr, nullptr};
+  std::memset(params, 0, sizeof *params);
+  params->map_signature = AI_MAGIC_SIGNATURE;
+  params->map_weights = ai_buffer_array{AI_FLAG_NONE, 1, w};
+  params->map_activations = ai_buffer_array{AI_FLAG_NONE, 1, a};
+  return true;
+}
+
+// ============================================================================================
+// B200 extensions
+// ============================================================================================
+#define YF_NET_OR_FAIL(n, network)                                                             \
+  std::lock_guard<std::mutex> lk(g_mu);                                                        \
+  Network* n = as_net(network);                                                                \
+  if (!n) return -1;                                                                           \
+  cudaSetDevice(n->device);
+
+AI_API_ENTRY int32_t yf_b200_set_input_size(ai_handle network, int32_t height, int32_t width) {
+  YF_NET_OR_FAIL(n, network)
+  if (height < 8 || width < 8 || height % 8 || width % 8 || height > 4096 || width > 4096) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_SIZE); return -1; }
+  n->H = height; n->W = width;
+  if (n->initialized && !get_plan(n, n->H, n->W)) return -1;
+  return 0;
+}
+
+AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, uint32_t count) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!in) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (!out) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (count == 0) return 0;
+  return run_images(n, in, out, count, false, nullptr);
+}
+
+AI_API_ENTRY int32_t yf_b200_decode(ai_handle network, const void* heads, uint32_t count, float conf_thr, float iou_thr,
+                                    uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!heads || !dets || !counts || !max_det) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (count == 0) return 0;
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const size_t hsz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  int32_t total = 0;
+  for (uint32_t done = 0; done < count; done += pd->cap) {
+    const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+    const int8_t* dh;
+    if (is_device_ptr(heads)) dh = static_cast<const int8_t*>(heads) + done * hsz;
+    else {
+      if (!cuda_ok(n, cudaMemcpyAsync(pd->d_head, static_cast<const int8_t*>(heads) + done * hsz, nb * hsz, cudaMemcpyHostToDevice, n->stream), "H2D heads")) return -1;
+      dh = pd->d_head;
+    }
+    int32_t r = decode_on_device(n, dh, nb, pd->plan.GH, pd->plan.GW, conf_thr, iou_thr, flags, dets + static_cast<size_t>(done) * max_det, counts + done, max_det);
+    if (r < 0) return -1;
+    total += r;
+  }
+  return total;
+}
+
+AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t count, float conf_thr, float iou_thr,
+                                    uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det, void* heads_out) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!in || !dets || !counts || !max_det) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (count == 0) return 0;
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, hsz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const bool in_dev = is_device_ptr(in);
+  int32_t total = 0;
+  for (uint32_t done = 0; done < count; done += pd->cap) {
+    const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+    const int8_t* src = static_cast<const int8_t*>(in) + done * in_sz;
+    int8_t* dh = nullptr;
+    void* hout = heads_out ? static_cast<int8_t*>(heads_out) + done * hsz : nullptr;
+    // heads stay in the staging buffer unless the caller gave a device destination
+    if (hout && is_device_ptr(hout)) { if (run_images(n, src, hout, nb, false, nullptr) < 0) return -1; dh = static_cast<int8_t*>(hout); }
+    else {
+      if (run_images(n, src, in_dev ? static_cast<void*>(pd->d_head) : nullptr, nb, true, &dh) < 0) return -1;
+      dh = pd->d_head;
+      if (hout && !cuda_ok(n, cudaMemcpyAsync(hout, pd->d_head, nb * hsz, cudaMemcpyDeviceToHost, n->stream), "D2H heads")) return -1;
+    }
+    int32_t r = decode_on_device(n, dh, nb, pd->plan.GH, pd->plan.GW, conf_thr, iou_thr, flags, dets + static_cast<size_t>(done) * max_det, counts + done, max_det);
+    if (r < 0) return -1;
+    total += r;
+  }
+  return total;
+}
+
+AI_API_ENTRY int32_t yf_b200_preprocess_rgb565(ai_handle network, const void* frames, void* out, uint32_t count) {
+  YF_NET_OR_FAIL(n, network)
+  if (!frames || !out) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (count == 0) return 0;
+  const size_t fsz = 112 * 112 * 2, osz = 56 * 56 * 3;
+  const bool fdev = is_device_ptr(frames), odev = is_device_ptr(out);
+  const size_t need = (fdev ? 0 : fsz * count) + (odev ? 0 : osz * count);
+  if (need > n->frames_cap) {
+    cudaFree(n->d_frames); n->d_frames = nullptr; n->frames_cap = 0;
+    if (!cuda_ok(n, cudaMalloc(&n->d_frames, need), "cudaMalloc frames", AI_ERROR_ALLOCATION_FAILED)) return -1;
+    n->frames_cap = need;
+  }
+  const uint8_t* dfr = static_cast<const uint8_t*>(frames);
+  uint8_t* scratch = n->d_frames;
+  if (!fdev) {
+    if (!cuda_ok(n, cudaMemcpyAsync(scratch, frames, fsz * count, cudaMemcpyHostToDevice, n->stream), "H2D frames")) return -1;
+    dfr = scratch; scratch += fsz * count;
+  }
+  PrepArgs a{dfr, odev ? static_cast<int8_t*>(out) : reinterpret_cast<int8_t*>(scratch), static_cast<int>(count)};
+  if (!cuda_ok(n, launch_prep_rgb565(a, n->stream), "prep_rgb565")) return -1;
+  ++n->launches;
+  if (!odev && !cuda_ok(n, cudaMemcpyAsync(out, a.out, osz * count, cudaMemcpyDeviceToHost, n->stream), "D2H inputs")) return -1;
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "synchronize")) return -1;
+  return static_cast<int32_t>(count);
+}
+
+AI_API_ENTRY int32_t yf_b200_set_observer(ai_handle network, int32_t enable) {
+  YF_NET_OR_FAIL(n, network)
+  n->observer = enable != 0;
+  if (n->initialized && !get_plan(n, n->H, n->W)) return -1;
+  return 0;
+}
+
+AI_API_ENTRY int32_t yf_b200_tensor_shape(ai_handle network, int32_t t, int32_t dims[4]) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) return -1;
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const Plan& P = pd->plan;
+  if (t < 0 || t >= static_cast<int>(P.loc.size()) || P.loc[t].buf < 0) return -1;
+  const PBuffer& b = P.buffers[P.loc[t].buf];
+  dims[0] = 1; dims[1] = b.H; dims[2] = b.W; dims[3] = P.loc[t].C;
+  return 0;
+}
+
+AI_API_ENTRY int64_t yf_b200_get_tensor(ai_handle network, int32_t t, uint32_t count, void* dst, uint64_t dst_bytes) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized || !n->observer) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); set_text("observer mode is off"); return -1; }
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const Plan& P = pd->plan;
+  if (t < 0 || t >= static_cast<int>(P.loc.size()) || P.loc[t].buf < 0) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_TENSOR); return -1; }
+  const TensorLoc& L = P.loc[t]; const PBuffer& b = P.buffers[L.buf];
+  if (b.is_input) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_TENSOR); return -1; }
+  if (count > n->last_run_n) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_BATCH); return -1; }
+  const size_t rows = static_cast<size_t>(count) * b.H * b.W, bytes = rows * L.C;
+  if (dst_bytes < bytes) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_SIZE); return -1; }
+  const int8_t* src = b.is_output ? pd->d_head : reinterpret_cast<const int8_t*>(pd->d_arena + b.offset * pd->cap);
+  if (!cuda_ok(n, cudaMemcpy2DAsync(dst, L.C, src + L.coff, b.CP, L.C, rows, cudaMemcpyDeviceToHost, n->stream), "D2H tensor")) return -1;
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "synchronize")) return -1;
+  return static_cast<int64_t>(bytes);
+}
+
+AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* st) {
+  YF_NET_OR_FAIL(n, network)
+  if (!st) return -1;
+  st->kernel_launches = n->launches; st->images = n->images; st->last_run_device_ms = n->last_ms;
+  st->device = n->device; st->sm_count = n->sm_count; st->chunk_images = n->chunk;
+  auto it = n->plans.find(std::make_pair(n->H, n->W));
+  st->steps = it == n->plans.end() ? 0 : static_cast<int32_t>(it->second->plan.steps.size());
+  return 0;
+}
+
+AI_API_ENTRY int32_t yf_b200_step_count(ai_handle network) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) return -1;
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  return static_cast<int32_t>(pd->plan.steps.size());
+}
+
+AI_API_ENTRY int32_t yf_b200_step_info_get(ai_handle network, int32_t step, yf_b200_step_info* info) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized || !info) return -1;
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const Plan& P = pd->plan;
+  if (step < 0 || step >= static_cast<int>(P.steps.size())) return -1;
+  const Step& s = P.steps[step];
+  std::memset(info, 0, sizeof *info);
+  std::snprintf(info->name, sizeof info->name, "%s", s.name.c_str());
+  info->kind = s.kind; info->first_op = s.op_first; info->n_ops = static_cast<int32_t>(s.ops.size());
+  const int64_t opix = static_cast<int64_t>(s.Hout) * s.Wout, ipix = static_cast<int64_t>(s.Hin) * s.Win;
+  switch (s.kind) {
+    case STEP_CONV1X1: info->macs = opix * s.Cout * s.Cin; break;
+    case STEP_CONV_IM2COL: info->macs = opix * s.Cout * s.kh * s.kw * s.Cin; break;
+    case STEP_DW: info->macs = opix * s.Cout * 9; break;
+    default: info->macs = 0;
+  }
+  info->bytes_read = ipix * s.Cin + (s.add.enabled ? opix * s.Cout : 0);
+  info->bytes_written = opix * s.Cout;
+  info->last_ms = pd->step_ms[step];
+  return 0;
+}
+
+AI_API_ENTRY int32_t yf_b200_set_step_profiling(ai_handle network, int32_t enable) {
+  YF_NET_OR_FAIL(n, network)
+  n->step_profiling = enable != 0;
+  return 0;
+}
+
+// ---- plan introspection (host only) ------------------------------------------------------
+static bool host_plan(int32_t H, int32_t W, const void* blob, Plan* P) {
+  static TflModel model; static std::once_flag once; static bool ok = false;
+  std::call_once(once, [] { std::string e; ok = model.parse(yf_embedded_model, yf_embedded_model_len, &e); if (!ok) set_text("model: " + e); });
+  if (!ok) return false;
+  size_t need = 0; st_blob_layout(model, &need);
+  std::string perr;
+  if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr)) { set_text("plan: " + perr); return false; }
+  return true;
+}
+
+AI_API_ENTRY int64_t yf_b200_plan_json(int32_t H, int32_t W, const void* blob, char* dst, uint64_t cap) {
+  Plan P;
+  if (!host_plan(H, W, blob, &P)) return -1;
+  std::string j = "{";
+  auto kv = [&](const char* k, long long v, bool comma = true) { j += std::string("\"") + k + "\":" + std::to_string(v) + (comma ? "," : ""); };
+  kv("H", P.H); kv("W", P.W); kv("GH", P.GH); kv("GW", P.GW); kv("input_buf", P.input_buf); kv("output_buf", P.output_buf);
+  kv("arena_bytes_per_image", static_cast<long long>(P.arena_bytes_per_image));
+  kv("arena_bytes_per_image_observer", static_cast<long long>(P.arena_bytes_per_image_observer));
+  kv("macs_per_image", P.macs_per_image); kv("n_epi", static_cast<long long>(P.epi.size())); kv("n_luts", static_cast<long long>(P.luts.size() / 256));
+  kv("out_zp", P.out_zp);
+  j += "\"out_scale\":" + std::to_string(static_cast<double>(P.out_scale)) + ",";
+  j += "\"buffers\":[";
+  for (size_t i = 0; i < P.buffers.size(); ++i) {
+    const PBuffer& b = P.buffers[i];
+    j += "{"; kv("H", b.H); kv("W", b.W); kv("C", b.C); kv("CP", b.CP); kv("is_input", b.is_input); kv("is_output", b.is_output);
+    kv("observer_only", b.observer_only); kv("offset", static_cast<long long>(b.offset), false); j += i + 1 < P.buffers.size() ? "}," : "}";
+  }
+  j += "],\"loc\":[";
+  for (size_t i = 0; i < P.loc.size(); ++i) {
+    j += "[" + std::to_string(P.loc[i].buf) + "," + std::to_string(P.loc[i].coff) + "," + std::to_string(P.loc[i].C) + "]";
+    if (i + 1 < P.loc.size()) j += ",";
+  }
+  j += "],\"steps\":[";
+  for (size_t i = 0; i < P.steps.size(); ++i) {
+    const Step& s = P.steps[i];
+    j += "{\"name\":\"" + s.name + "\",";
+    kv("kind", s.kind); kv("op_first", s.op_first);
+    j += "\"ops\":["; for (size_t k = 0; k < s.ops.size(); ++k) j += std::to_string(s.ops[k]) + (k + 1 < s.ops.size() ? "," : ""); j += "],";
+    kv("in_buf", s.in_buf); kv("in_coff", s.in_coff); kv("add_buf", s.add_buf); kv("add_coff", s.add_coff);
+    kv("out_buf", s.out_buf); kv("out_coff", s.out_coff); kv("raw_buf", s.raw_buf); kv("mid_buf", s.mid_buf); kv("pre_add_buf", s.pre_add_buf);
+    kv("Hin", s.Hin); kv("Win", s.Win); kv("Cin", s.Cin); kv("Hout", s.Hout); kv("Wout", s.Wout); kv("Cout", s.Cout);
+    kv("kh", s.kh); kv("kw", s.kw); kv("stride", s.stride); kv("pad_t", s.pad_t); kv("pad_l", s.pad_l); kv("in_zp", s.in_zp);
+    kv("Kpad", s.Kpad); kv("Npad", s.Npad); kv("epi_base", s.epi_base); kv("lut1", s.lut1); kv("lut2", s.lut2); kv("lut_fused", s.lut_fused);
+    kv("w_off", static_cast<long long>(s.w_off)); kv("w_bytes", static_cast<long long>(s.w_bytes));
+    kv("band_rows", s.band_rows); kv("bands", s.bands);
+    j += "\"add\":[" + std::to_string(s.add.enabled) + "," + std::to_string(s.add.zp1) + "," + std::to_string(s.add.zp2) + "," + std::to_string(s.add.zp_out) + "," +
+         std::to_string(s.add.m1) + "," + std::to_string(s.add.m2) + "," + std::to_string(s.add.mo) + "," + std::to_string(s.add.s1) + "," +
+         std::to_string(s.add.s2) + "," + std::to_string(s.add.so) + "]";
+    j += i + 1 < P.steps.size() ? "}," : "}";
+  }
+  j += "]}";
+  if (dst && cap) { size_t k = std::min<size_t>(cap - 1, j.size()); std::memcpy(dst, j.data(), k); dst[k] = 0; }
+  return static_cast<int64_t>(j.size() + 1);
+}
+
+AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t H, int32_t W, const void* blob, int32_t what, void* dst, uint64_t cap) {
+  Plan P;
+  if (!host_plan(H, W, blob, &P)) return -1;
+  const void* src; size_t n;
+  switch (what) {
+    case 0: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
+    case 1: src = P.luts.data(); n = P.luts.size(); break;
+    case 2: src = P.wblob.data(); n = P.wblob.size(); break;
+    default: return -1;
+  }
+  if (dst && cap) std::memcpy(dst, src, std::min<size_t>(cap, n));
+  return static_cast<int64_t>(n);
+}
+
+AI_API_ENTRY void* yf_b200_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+AI_API_ENTRY void yf_b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+AI_API_ENTRY const char* yf_b200_last_error_text(void) { return g_text.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,708 @@
+// yf_kernels.cu -- hand-written sm_100a kernels of the layer-by-layer ("observer") path.
+//
+//   conv1x1_tcgen05_kernel   CONV_2D 1x1 as a GEMM [pixels x Cin]*[Cin x Cout]: TMA -> smem -> tcgen05.mma
+//                            kind::i8 -> TMEM -> fused TFLite requant / LeakyReLU table / ADD / concat slice
+//   conv_im2col_tcgen05_kernel  the 3x3 stride-2 first conv as an implicit GEMM (K = 27 -> 32)
+//   dwconv3x3_kernel         DEPTHWISE_CONV_2D, dp4a on NHWC words, same epilogue
+//   maxpool_kernel           MAX_POOL_2D (+ QUANTIZE table), valid cells only
+//   lut_kernel               stand-alone LEAKY_RELU / QUANTIZE
+//   decode_nms_kernel        YOLO head decode + greedy NMS, one warp per image
+//   prep_rgb565_kernel       camera-side RGB565 112x112 -> int8 56x56x3
+//
+// Reference semantics: SURVEY.md 8a rows a2-a14; each kernel cites the row it implements.
+#include "yf_kernels.cuh"
+#include "yf_ptx.cuh"
+
+namespace yf {
+
+__constant__ EpiCh c_epi[kMaxEpiCh];
+
+cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s) {
+  if (n > kMaxEpiCh) return cudaErrorInvalidValue;
+  return cudaMemcpyToSymbolAsync(c_epi, host, sizeof(EpiCh) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fixed-point epilogue arithmetic (folded form documented in yf_plan.h)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t requant(int32_t acc, const EpiCh& k) {
+  const long long p = static_cast<long long>(acc << k.ls) * static_cast<long long>(k.mult) + k.add64;
+  const int32_t t = static_cast<int32_t>(p >> 31);
+  return (t + k.c2 + ((t >> 31) & k.sgn_mask)) >> k.e;     // includes +zp_out, not yet clamped
+}
+__device__ __forceinline__ int32_t clamp_s8(int32_t v) { return max(-128, min(127, v)); }
+// MultiplyByQuantizedMultiplier for shift <= 0 (used by the fused ADD only)
+__device__ __forceinline__ int32_t mbqm_dev(int32_t x, int32_t m, int s) {
+  const long long ab = static_cast<long long>(x) * static_cast<long long>(m);
+  const int32_t t = static_cast<int32_t>((ab + (1ll << 30)) >> 31);
+  const int rs = -s;
+  if (rs == 0) return t;
+  return (t + (1 << (rs - 1)) + (t >> 31)) >> rs;
+}
+// reference_integer_ops::AddElementwise (row a8): x = skip operand, y = this conv's int8 output
+__device__ __forceinline__ int32_t add_dev(int32_t x, int32_t y, const AddParams& a) {
+  const int32_t sx = mbqm_dev((x - a.zp1) << 20, a.m1, a.s1);
+  const int32_t sy = mbqm_dev((y - a.zp2) << 20, a.m2, a.s2);
+  return clamp_s8(mbqm_dev(sx + sy, a.mo, a.so) + a.zp_out);
+}
+
+template <int NW>
+__device__ __forceinline__ void store_row(int8_t* dst, const uint32_t (&w)[NW], int nbytes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+  if ((a & 3) == 0) {
+    int done = 0;
+    if ((a & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < NW / 4; ++i)
+        if (i * 16 + 16 <= nbytes)
+          *reinterpret_cast<uint4*>(dst + i * 16) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      done = nbytes & ~15;
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i)
+      if (i * 4 >= done && i * 4 + 4 <= nbytes) *reinterpret_cast<uint32_t*>(dst + i * 4) = w[i];
+#pragma unroll
+    for (int i = 0; i < NW; ++i)
+      if (i * 4 < nbytes && i * 4 + 4 > nbytes) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+          if (i * 4 + b < nbytes) dst[i * 4 + b] = static_cast<int8_t>((w[i] >> (8 * b)) & 0xff);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (i * 4 + b < nbytes) dst[i * 4 + b] = static_cast<int8_t>((w[i] >> (8 * b)) & 0xff);
+    }
+  }
+}
+
+// One output row (pixel): NPAD int32 accumulators -> requant -> [ADD] -> [table 1] -> [table 2] -> stores.
+// sLut: smem copy of table 1 at [0,256) and table 2 at [256,512).
+template <int NPAD>
+__device__ __forceinline__ void epilogue_row(const uint32_t (&acc)[NPAD], const EpiOut& eo, long long row,
+                                             const uint8_t* sLut) {
+  uint32_t outw[NPAD / 4], raww[NPAD / 4], midw[NPAD / 4];
+#pragma unroll
+  for (int i = 0; i < NPAD / 4; ++i) { outw[i] = 0; raww[i] = 0; midw[i] = 0; }
+  const int8_t* addp = eo.add.enabled ? eo.add_in + row * eo.add_pitch + eo.add_coff : nullptr;
+#pragma unroll
+  for (int c = 0; c < NPAD; ++c) {
+    if (c < eo.cout) {
+      int32_t y = clamp_s8(requant(static_cast<int32_t>(acc[c]), c_epi[eo.epi_base + c]));
+      raww[c / 4] |= static_cast<uint32_t>(y & 0xff) << (8 * (c % 4));
+      if (eo.add.enabled) y = add_dev(static_cast<int32_t>(addp[c]), y, eo.add);
+      if (eo.lut1) y = static_cast<int8_t>(sLut[y + 128]);
+      midw[c / 4] |= static_cast<uint32_t>(y & 0xff) << (8 * (c % 4));
+      if (eo.lut2) y = static_cast<int8_t>(sLut[256 + y + 128]);
+      outw[c / 4] |= static_cast<uint32_t>(y & 0xff) << (8 * (c % 4));
+    }
+  }
+  store_row<NPAD / 4>(eo.out + row * eo.out_pitch + eo.out_coff, outw, max(eo.cout, eo.fill_to));
+  if (eo.add.enabled) { if (eo.pre_add) store_row<NPAD / 4>(eo.pre_add + row * eo.pre_add_pitch, raww, eo.cout); }
+  else if (eo.raw) store_row<NPAD / 4>(eo.raw + row * eo.raw_pitch, raww, eo.cout);
+  if (eo.mid) store_row<NPAD / 4>(eo.mid + row * eo.mid_pitch, midw, eo.cout);
+}
+
+__device__ __forceinline__ void load_luts(uint8_t* sLut, const EpiOut& eo, int tid, int nthreads) {
+  for (int i = tid; i < 128; i += nthreads) {
+    reinterpret_cast<uint32_t*>(sLut)[i] =
+        i < 64 ? (eo.lut1 ? reinterpret_cast<const uint32_t*>(eo.lut1)[i] : 0u)
+               : (eo.lut2 ? reinterpret_cast<const uint32_t*>(eo.lut2)[i - 64] : 0u);
+  }
+}
+
+// pipeline watchdog: a protocol bug must end the kernel, never hang the box
+__device__ __forceinline__ bool wait_or_flag(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (mbar_wait(bar, parity)) return true;
+  atomicCAS(err, 0, code);
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// CONV_2D 1x1 (row a4): persistent, warp-specialised tcgen05 GEMM.
+//   warp 0   TMA producer: A tile = 128 pixels x (nchunk x 16 B) into the canonical no-swizzle
+//            K-major layout (8x16 B core matrices: SBO 128 B between row groups, LBO 2048 B between K chunks)
+//   warp 1   MMA issuer: nk x tcgen05.mma.cta_group::1.kind::i8, M=128, N=NPAD, K=32; accumulators in TMEM
+//   warp 2-5 epilogue: tcgen05.ld (lane quarter = warp%4) -> requant/table/ADD -> int8 stores
+// ------------------------------------------------------------------------------------------
+constexpr int kGemmStages = 4;
+constexpr int kStageBytes = 8192;       // 4 K-chunks x 128 rows x 16 B
+constexpr int kGemmThreads = 192;
+
+template <int NPAD>
+constexpr int gemm_smem_bytes() { return kGemmStages * kStageBytes + 4 * NPAD * 16 + 512 + 16 * 8 + 16; }
+template <int NPAD>
+__host__ __device__ constexpr uint32_t tmem_cols() { return 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : (2 * NPAD <= 128 ? 128 : 256)); }
+
+template <int NPAD>
+__global__ void __launch_bounds__(kGemmThreads)
+conv1x1_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const Conv1x1Args p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + kGemmStages * kStageBytes;
+  uint8_t* sLut = sW + 4 * NPAD * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 512);
+  uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols<NPAD>());
+  for (int i = threadIdx.x; i < p.w_bytes / 16; i += kGemmThreads)
+    reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(p.w_img)[i];
+  load_luts(sLut, p.eo, threadIdx.x, kGemmThreads);
+  fence_proxy_async_smem();            // weights were written through the generic proxy, UMMA reads them
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kGemmStages; const uint32_t ph = (it / kGemmStages) & 1;
+        if (!wait_or_flag(&empty[s], ph ^ 1, p.err, 101)) break;
+        mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(p.nchunk) * 2048u);
+        for (int c = 0; c < p.nchunk; ++c)
+          tma_load_2d(sA + s * kStageBytes + c * 2048, &tmapA, &full[s], c * 16, tile * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_s8(128, NPAD);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kGemmStages; const uint32_t ph = (it / kGemmStages) & 1;
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        if (!wait_or_flag(&tempty[as], aph ^ 1, p.err, 102)) break;
+        if (!wait_or_flag(&full[s], ph, p.err, 103)) break;
+        tc_fence_after();
+        for (int k = 0; k < p.nk; ++k) {
+          const uint64_t da = umma_smem_desc(smem_u32(sA + s * kStageBytes + k * 4096), 2048, 128, 0);
+          const uint64_t db = umma_smem_desc(smem_u32(sW + k * 2 * NPAD * 16), NPAD * 16, 128, 0);
+          mma_i8(tmem_base + as * NPAD, da, db, idesc, k > 0 ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);          // smem slot reusable once the MMAs have read it
+        mma_commit(&tfull[as]);         // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      if (!wait_or_flag(&tfull[as], aph, p.err, 104)) break;
+      tc_fence_after();
+      uint32_t acc[NPAD];
+      const uint32_t taddr = tmem_base + as * NPAD + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int g = 0; g < NPAD / 16; ++g) {
+        uint32_t v[16];
+        tmem_ld16(taddr + g * 16, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[g * 16 + j] = v[j];
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      const long long row = static_cast<long long>(tile) * 128 + q * 32 + lane;
+      if (row < p.M) epilogue_row<NPAD>(acc, p.eo, row, sLut);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols<NPAD>());
+}
+
+// ------------------------------------------------------------------------------------------
+// CONV_2D 3x3 stride 2 on the dense RGB input with PAD(1,0,1,0) folded (rows a2+a3): implicit GEMM.
+//   warp 0    band loader: cp.async.bulk (TMA engine) of the input rows one band of output rows needs
+//   warp 1    MMA issuer (one K=32 MMA per 128-pixel tile)
+//   warp 2-5  epilogue
+//   warp 6-9  im2col builders: one A row (27 taps, zero-point at the top/left border) per thread
+// ------------------------------------------------------------------------------------------
+constexpr int kBandSlotBytes = 16384 + 2048;
+constexpr int kIm2colStages = 4;
+constexpr int kIm2colThreads = 320;
+template <int NPAD>
+constexpr int im2col_smem_bytes() { return 2 * kBandSlotBytes + kIm2colStages * 4096 + 2 * NPAD * 16 + 512 + 24 * 8 + 16; }
+
+template <int NPAD>
+__global__ void __launch_bounds__(kIm2colThreads)
+conv_im2col_tcgen05_kernel(const ConvIm2colArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sBand = smem;
+  uint8_t* sA = smem + 2 * kBandSlotBytes;
+  uint8_t* sW = sA + kIm2colStages * 4096;
+  uint8_t* sLut = sW + 2 * NPAD * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 512);
+  uint64_t* bfull = bars; uint64_t* bempty = bars + 2;
+  uint64_t* afull = bars + 4; uint64_t* aempty = bars + 8; uint64_t* tfull = bars + 12; uint64_t* tempty = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 4); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < kIm2colStages; ++i) { mbar_init(&afull[i], 4); mbar_init(&aempty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols<NPAD>());
+  for (int i = threadIdx.x; i < p.w_bytes / 16; i += kIm2colThreads)
+    reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(p.w_img)[i];
+  load_luts(sLut, p.eo, threadIdx.x, kIm2colThreads);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units = p.n_img * p.bands;
+  const int row_bytes = p.Win * 3;
+  const long long img_bytes = static_cast<long long>(p.Hin) * row_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ui = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+        const int slot = ui & 1; const uint32_t ph = (ui >> 1) & 1;
+        const int img = u / p.bands, band = u % p.bands;
+        const int oy0 = band * p.band_rows;
+        const int rows = min(p.band_rows, p.Hout - oy0);
+        const int r0 = oy0 == 0 ? 0 : 2 * oy0 - 2;           // even => 16-byte aligned source
+        const int r1 = min(p.Hin, 2 * (oy0 + rows));
+        if (!wait_or_flag(&bempty[slot], ph ^ 1, p.err, 201)) break;
+        const uint32_t bytes = static_cast<uint32_t>((r1 - r0) * row_bytes);
+        mbar_arrive_expect_tx(&bfull[slot], bytes);
+        bulk_load_1d(sBand + slot * kBandSlotBytes, p.in + img * img_bytes + static_cast<long long>(r0) * row_bytes, bytes, &bfull[slot]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_s8(128, NPAD);
+      int it = 0; bool ok = true;
+      for (int u = blockIdx.x; u < units && ok; u += gridDim.x) {
+        const int oy0 = (u % p.bands) * p.band_rows;
+        const int rows = min(p.band_rows, p.Hout - oy0);
+        const int tiles = (rows * p.Wout + 127) / 128;
+        for (int t = 0; t < tiles; ++t, ++it) {
+          const int s = it % kIm2colStages; const uint32_t ph = (it / kIm2colStages) & 1;
+          const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+          if (!wait_or_flag(&tempty[as], aph ^ 1, p.err, 202)) { ok = false; break; }
+          if (!wait_or_flag(&afull[s], ph, p.err, 203)) { ok = false; break; }
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc(smem_u32(sA + s * 4096), 2048, 128, 0);
+          const uint64_t db = umma_smem_desc(smem_u32(sW), NPAD * 16, 128, 0);
+          mma_i8(tmem_base + as * NPAD, da, db, idesc, 0u);
+          mma_commit(&aempty[s]);
+          mma_commit(&tfull[as]);
+        }
+      }
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    int it = 0; bool ok = true;
+    for (int u = blockIdx.x; u < units && ok; u += gridDim.x) {
+      const int img = u / p.bands, band = u % p.bands;
+      const int oy0 = band * p.band_rows;
+      const int rows = min(p.band_rows, p.Hout - oy0);
+      const int npix = rows * p.Wout;
+      const int tiles = (npix + 127) / 128;
+      for (int t = 0; t < tiles; ++t, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        if (!wait_or_flag(&tfull[as], aph, p.err, 204)) { ok = false; break; }
+        tc_fence_after();
+        uint32_t acc[NPAD];
+        const uint32_t taddr = tmem_base + as * NPAD + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+        for (int g = 0; g < NPAD / 16; ++g) {
+          uint32_t v[16];
+          tmem_ld16(taddr + g * 16, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[g * 16 + j] = v[j];
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        const int r = t * 128 + q * 32 + lane;
+        if (r < npix) {
+          const long long row = (static_cast<long long>(img) * p.Hout + oy0) * p.Wout + r;
+          epilogue_row<NPAD>(acc, p.eo, row, sLut);
+        }
+      }
+    }
+  } else {
+    const int bt = threadIdx.x - 192;        // builder thread 0..127 = A row inside the tile
+    int it = 0, ui = 0; bool ok = true;
+    const uint32_t zpw = static_cast<uint32_t>(p.in_zp & 0xff) * 0x01010101u;
+    for (int u = blockIdx.x; u < units && ok; u += gridDim.x, ++ui) {
+      const int slot = ui & 1; const uint32_t bph = (ui >> 1) & 1;
+      const int band = u % p.bands;
+      const int oy0 = band * p.band_rows;
+      const int rows = min(p.band_rows, p.Hout - oy0);
+      const int npix = rows * p.Wout;
+      const int tiles = (npix + 127) / 128;
+      const int r0 = oy0 == 0 ? 0 : 2 * oy0 - 2;
+      if (!wait_or_flag(&bfull[slot], bph, p.err, 205)) break;
+      const uint8_t* band_ptr = sBand + slot * kBandSlotBytes;
+      for (int t = 0; t < tiles; ++t, ++it) {
+        const int s = it % kIm2colStages; const uint32_t ph = (it / kIm2colStages) & 1;
+        if (!wait_or_flag(&aempty[s], ph ^ 1, p.err, 206)) { ok = false; break; }
+        const int r = t * 128 + bt;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = 0;
+        if (r < npix) {
+          const int oy = oy0 + r / p.Wout, ox = r % p.Wout;
+          uint8_t tap[27];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            const int ix0 = 2 * ox - 1;
+            const uint8_t* src = band_ptr + (iy - r0) * row_bytes + ix0 * 3;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+              const bool inb = iy >= 0 && (ix0 >= 0 || j >= 3);
+              tap[ky * 9 + j] = inb ? src[j] : static_cast<uint8_t>(zpw & 0xff);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 27; ++k) w[k / 4] |= static_cast<uint32_t>(tap[k]) << (8 * (k % 4));
+        }
+        uint8_t* dst = sA + s * 4096 + (bt >> 3) * 128 + (bt & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(dst + 2048) = make_uint4(w[4], w[5], w[6], w[7]);
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[s]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bempty[slot]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols<NPAD>());
+}
+
+// ------------------------------------------------------------------------------------------
+// DEPTHWISE_CONV_2D 3x3 (row a5): one thread = one output pixel x 4 channels (one NHWC word).
+// dp4a against one-hot weight words avoids unpacking; out-of-bounds taps read the zero point
+// (TFLite skips them; PAD writes the zero point -- identical once -zp*sum(w) is folded in the bias).
+// ------------------------------------------------------------------------------------------
+struct DwSmem { EpiCh epi[64]; uint32_t w1h[9 * 64]; uint8_t lut[512]; };
+
+__device__ __forceinline__ void tail_word(int32_t (&y)[4], int c0, const EpiOut& eo, const uint8_t* sLut, long long row) {
+  // y[] = clamped int8 results of channels c0..c0+3 (already requantised)
+  uint32_t outw = 0, raww = 0, midw = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int32_t v = y[j];
+    if (c0 + j < eo.cout) {
+      raww |= static_cast<uint32_t>(v & 0xff) << (8 * j);
+      if (eo.lut1) v = static_cast<int8_t>(sLut[v + 128]);
+      midw |= static_cast<uint32_t>(v & 0xff) << (8 * j);
+      if (eo.lut2) v = static_cast<int8_t>(sLut[256 + v + 128]);
+      outw |= static_cast<uint32_t>(v & 0xff) << (8 * j);
+    }
+  }
+  const int lim = max(eo.cout, eo.fill_to);
+  int8_t* o = eo.out + row * eo.out_pitch + eo.out_coff + c0;
+  if (c0 + 4 <= lim && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = outw;
+  else for (int j = 0; j < 4; ++j) if (c0 + j < lim) o[j] = static_cast<int8_t>((outw >> (8 * j)) & 0xff);
+  if (eo.raw) { int8_t* r = eo.raw + row * eo.raw_pitch + c0; for (int j = 0; j < 4; ++j) if (c0 + j < eo.cout) r[j] = static_cast<int8_t>((raww >> (8 * j)) & 0xff); }
+  if (eo.mid) { int8_t* r = eo.mid + row * eo.mid_pitch + c0; for (int j = 0; j < 4; ++j) if (c0 + j < eo.cout) r[j] = static_cast<int8_t>((midw >> (8 * j)) & 0xff); }
+}
+
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
+  __shared__ DwSmem sm;
+  for (int i = threadIdx.x; i < p.eo.cout; i += blockDim.x) sm.epi[i] = c_epi[p.eo.epi_base + i];
+  for (int i = threadIdx.x; i < 9 * p.in_pitch; i += blockDim.x) sm.w1h[(i / p.in_pitch) * 64 + i % p.in_pitch] = p.w1h[i];
+  load_luts(sm.lut, p.eo, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long total = static_cast<long long>(p.n_img) * p.Hout * p.Wout * p.words;
+  const uint32_t zpw = static_cast<uint32_t>(p.in_zp & 0xff) * 0x01010101u;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wq = static_cast<int>(idx % p.words);
+    const long long pix = idx / p.words;
+    const int ox = static_cast<int>(pix % p.Wout);
+    const int oy = static_cast<int>((pix / p.Wout) % p.Hout);
+    const long long img = pix / (static_cast<long long>(p.Wout) * p.Hout);
+    const int8_t* base = p.in + img * p.Hin * p.Win * p.in_pitch + wq * 4;
+    int32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * p.stride - p.pad_t + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * p.stride - p.pad_l + kx;
+        uint32_t x = zpw;
+        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+          x = __ldg(reinterpret_cast<const uint32_t*>(base + (static_cast<long long>(iy) * p.Win + ix) * p.in_pitch));
+        const uint32_t* w = &sm.w1h[(ky * 3 + kx) * 64 + wq * 4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = __dp4a(static_cast<int>(x), static_cast<int>(w[j]), acc[j]);
+      }
+    }
+    int32_t y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = (wq * 4 + j < p.eo.cout) ? clamp_s8(requant(acc[j], sm.epi[wq * 4 + j])) : 0;
+    tail_word(y, wq * 4, p.eo, sm.lut, pix);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MAX_POOL_2D (row a7) + folded QUANTIZE table (row a9): max over the in-bounds window cells.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
+  __shared__ uint8_t sLut[512];
+  load_luts(sLut, p.eo, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long total = static_cast<long long>(p.n_img) * p.Hout * p.Wout * p.words;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wq = static_cast<int>(idx % p.words);
+    const long long pix = idx / p.words;
+    const int ox = static_cast<int>(pix % p.Wout);
+    const int oy = static_cast<int>((pix / p.Wout) % p.Hout);
+    const long long img = pix / (static_cast<long long>(p.Wout) * p.Hout);
+    const int8_t* base = p.in + img * p.Hin * p.Win * p.in_pitch + wq * 4;
+    const int y0 = max(0, oy * p.stride - p.pad_t), y1 = min(p.Hin, oy * p.stride - p.pad_t + p.k);
+    const int x0 = max(0, ox * p.stride - p.pad_l), x1 = min(p.Win, ox * p.stride - p.pad_l + p.k);
+    uint32_t m = 0x80808080u;
+    for (int iy = y0; iy < y1; ++iy)
+      for (int ix = x0; ix < x1; ++ix)
+        m = __vmaxs4(m, __ldg(reinterpret_cast<const uint32_t*>(base + (static_cast<long long>(iy) * p.Win + ix) * p.in_pitch)));
+    int32_t y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = static_cast<int8_t>((m >> (8 * j)) & 0xff);
+    tail_word(y, wq * 4, p.eo, sLut, pix);
+  }
+}
+
+// stand-alone LEAKY_RELU / QUANTIZE (rows a6, a9) when the producer could not absorb it
+__global__ void __launch_bounds__(256) lut_kernel(const LutArgs p) {
+  __shared__ uint8_t sLut[512];
+  load_luts(sLut, p.eo, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const long long total = p.rows * p.words;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wq = static_cast<int>(idx % p.words);
+    const long long row = idx / p.words;
+    const int8_t* src = p.in + row * p.in_pitch + p.in_coff + wq * 4;
+    int32_t y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = (wq * 4 + j < p.eo.cout) ? src[j] : 0;
+    tail_word(y, wq * 4, p.eo, sLut, row);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Head decode + greedy NMS (rows a13, a14): one warp per image.
+// Candidate order = memory order of the head (cell-major, anchor-minor: yoloface.c:109-116).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxSurvivors = 192;
+struct Cand { float x1, y1, x2, y2, conf; int idx; };
+
+__device__ __forceinline__ float sigmoid_dev(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs p) {
+  __shared__ Cand s_c[4][kMaxSurvivors];
+  __shared__ int s_order[4][kMaxSurvivors];
+  __shared__ unsigned char s_dead[4][kMaxSurvivors];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * 4 + warp;
+  if (img >= p.n_img) return;
+  Cand* c = s_c[warp]; int* order = s_order[warp]; unsigned char* dead = s_dead[warp];
+  const int8_t* head = p.head + static_cast<long long>(img) * p.gh * p.gw * 18;
+  const int ncand = p.gh * p.gw * 3;
+  const float aw[3] = {9.f, 12.f, 22.f}, ah[3] = {14.f, 17.f, 21.f};   // yoloface.c:20
+  const float zp = static_cast<float>(p.zp);
+  int n = 0;
+  for (int base = 0; base < ncand; base += 32) {
+    const int k = base + lane;
+    bool keep = false; float conf = 0.f;
+    if (k < ncand) {
+      const int8_t* q = head + (k / 3) * 18 + (k % 3) * 6;
+      conf = sigmoid_dev((static_cast<float>(q[4]) - zp) * p.scale);
+      keep = conf >= p.conf_thr;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int pos = n + __popc(mask & ((1u << lane) - 1));
+    if (keep && pos < kMaxSurvivors) {
+      const int cell = k / 3, a = k % 3;
+      const int8_t* q = head + cell * 18 + a * 6;
+      const int gx = cell % p.gw, gy = cell / p.gw;
+      float x = (static_cast<float>(q[0]) - zp) * p.scale, y = (static_cast<float>(q[1]) - zp) * p.scale;
+      float w = (static_cast<float>(q[2]) - zp) * p.scale, h = (static_cast<float>(q[3]) - zp) * p.scale;
+      x = (sigmoid_dev(x) + static_cast<float>(gx)) * 8.f; y = (sigmoid_dev(y) + static_cast<float>(gy)) * 8.f;
+      w = expf(w) * aw[a]; h = expf(h) * ah[a];
+      c[pos] = Cand{x - w / 2, y - h / 2, x + w / 2, y + h / 2, conf, k};
+    }
+    n += __popc(mask);
+  }
+  n = min(n, kMaxSurvivors);
+  __syncwarp();
+  // rank = number of candidates that sort before me (conf desc, index asc); candidates are
+  // already in index order so ties resolve by position
+  for (int i = lane; i < n; i += 32) {
+    int r = 0; const float ci = c[i].conf;
+    for (int j = 0; j < n; ++j) r += (c[j].conf > ci) || (c[j].conf == ci && j < i);
+    order[r] = i; dead[i] = 0;
+  }
+  __syncwarp();
+  float* dets = p.dets + static_cast<long long>(img) * p.max_det * 5;
+  const float one = p.plus_one ? 1.f : 0.f;
+  int kept = 0;
+  for (int a = 0; a < n && kept < p.max_det; ++a) {
+    const int ia = order[a];
+    if (dead[ia]) continue;                       // warp-uniform (smem)
+    const Cand ca = c[ia];
+    if (lane == 0) { float* d = dets + kept * 5; d[0] = ca.x1; d[1] = ca.y1; d[2] = ca.x2; d[3] = ca.y2; d[4] = ca.conf; }
+    ++kept;
+    if (p.iou_thr >= 0.f) {
+      float ax1 = ca.x1, ay1 = ca.y1, ax2 = ca.x2, ay2 = ca.y2;
+      if (p.plus_one) { ax1 = truncf(ax1); ay1 = truncf(ay1); ax2 = truncf(ax2); ay2 = truncf(ay2); }
+      const float area_a = (ax2 - ax1 + one) * (ay2 - ay1 + one);
+      for (int b = a + 1 + lane; b < n; b += 32) {
+        const int ib = order[b];
+        if (dead[ib]) continue;
+        float bx1 = c[ib].x1, by1 = c[ib].y1, bx2 = c[ib].x2, by2 = c[ib].y2;
+        if (p.plus_one) { bx1 = truncf(bx1); by1 = truncf(by1); bx2 = truncf(bx2); by2 = truncf(by2); }
+        const float area_b = (bx2 - bx1 + one) * (by2 - by1 + one);
+        const float iw = fmaxf(0.f, fminf(ax2, bx2) - fmaxf(ax1, bx1) + one);
+        const float ih = fmaxf(0.f, fminf(ay2, by2) - fmaxf(ay1, by1) + one);
+        const float inter = iw * ih;
+        const float iou = inter / (area_a + area_b - inter);
+        if (!(iou <= p.iou_thr)) dead[ib] = 1;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) p.counts[img] = kept;
+}
+
+// ------------------------------------------------------------------------------------------
+// Camera-side pre-processing (yoloface.c:26-93), one thread per output pixel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_rgb565_kernel(const PrepArgs p) {
+  const long long total = static_cast<long long>(p.n_img) * 56 * 56;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % 56), y = static_cast<int>((idx / 56) % 56);
+    const long long img = idx / (56 * 56);
+    const uint8_t* f = p.frames + img * (112 * 112 * 2);
+    uint32_t sr = 0, sg = 0, sb = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      // two horizontally adjacent pixels = 4 consecutive bytes
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(f + ((2 * y + dy) * 112 + 2 * x) * 2);
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const uint32_t hi = (v >> (16 * dx)) & 0xff, lo = (v >> (16 * dx + 8)) & 0xff;
+        const uint32_t px = (hi << 8) | lo;
+        sr += (px >> 11) & 0x1f; sg += (px >> 5) & 0x3f; sb += px & 0x1f;
+      }
+    }
+    int8_t* o = p.out + idx * 3;
+    o[0] = static_cast<int8_t>(static_cast<int>(((sr >> 2) << 3) & 0xff) - 128);
+    o[1] = static_cast<int8_t>(static_cast<int>(((sg >> 2) << 2) & 0xff) - 128);
+    o[2] = static_cast<int8_t>(static_cast<int>(((sb >> 2) << 3) & 0xff) - 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------
+template <int NPAD>
+static cudaError_t launch_conv1x1_t(const CUtensorMap& tmapA, const Conv1x1Args& a, int sm_count, cudaStream_t s) {
+  const int grid = a.num_tiles < sm_count * 4 ? a.num_tiles : sm_count * 4;
+  conv1x1_tcgen05_kernel<NPAD><<<grid, kGemmThreads, gemm_smem_bytes<NPAD>(), s>>>(tmapA, a);
+  return cudaGetLastError();
+}
+cudaError_t launch_conv1x1(const CUtensorMap& tmapA, const Conv1x1Args& a, int npad, int sm_count, cudaStream_t s) {
+  if (a.num_tiles <= 0) return cudaSuccess;
+  switch (npad) {
+    case 16: return launch_conv1x1_t<16>(tmapA, a, sm_count, s);
+    case 32: return launch_conv1x1_t<32>(tmapA, a, sm_count, s);
+    case 48: return launch_conv1x1_t<48>(tmapA, a, sm_count, s);
+    case 64: return launch_conv1x1_t<64>(tmapA, a, sm_count, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+template <int NPAD>
+static cudaError_t launch_conv_im2col_t(const ConvIm2colArgs& a, int sm_count, cudaStream_t s) {
+  const int units = a.n_img * a.bands;
+  const int grid = units < sm_count * 2 ? units : sm_count * 2;
+  conv_im2col_tcgen05_kernel<NPAD><<<grid, kIm2colThreads, im2col_smem_bytes<NPAD>(), s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_conv_im2col(const ConvIm2colArgs& a, int npad, int sm_count, cudaStream_t s) {
+  if (a.n_img <= 0) return cudaSuccess;
+  switch (npad) {
+    case 16: return launch_conv_im2col_t<16>(a, sm_count, s);
+    case 32: return launch_conv_im2col_t<32>(a, sm_count, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+cudaError_t launch_dw(const DwArgs& a, cudaStream_t s) {
+  const long long total = static_cast<long long>(a.n_img) * a.Hout * a.Wout * a.words;
+  if (total <= 0) return cudaSuccess;
+  if (a.in_pitch > 64 || a.eo.cout > 64) return cudaErrorInvalidValue;
+  dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool(const PoolArgs& a, cudaStream_t s) {
+  const long long total = static_cast<long long>(a.n_img) * a.Hout * a.Wout * a.words;
+  if (total <= 0) return cudaSuccess;
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_lut(const LutArgs& a, cudaStream_t s) {
+  const long long total = a.rows * a.words;
+  if (total <= 0) return cudaSuccess;
+  lut_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_decode_nms(const DecodeArgs& a, cudaStream_t s) {
+  if (a.n_img <= 0) return cudaSuccess;
+  decode_nms_kernel<<<(a.n_img + 3) / 4, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_prep_rgb565(const PrepArgs& a, cudaStream_t s) {
+  const long long total = static_cast<long long>(a.n_img) * 56 * 56;
+  if (total <= 0) return cudaSuccess;
+  prep_rgb565_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t kernels_init() {
+  cudaError_t e;
+#define YF_OPTIN(k, bytes) if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  YF_OPTIN(conv1x1_tcgen05_kernel<16>, gemm_smem_bytes<16>())
+  YF_OPTIN(conv1x1_tcgen05_kernel<32>, gemm_smem_bytes<32>())
+  YF_OPTIN(conv1x1_tcgen05_kernel<48>, gemm_smem_bytes<48>())
+  YF_OPTIN(conv1x1_tcgen05_kernel<64>, gemm_smem_bytes<64>())
+  YF_OPTIN(conv_im2col_tcgen05_kernel<16>, im2col_smem_bytes<16>())
+  YF_OPTIN(conv_im2col_tcgen05_kernel<32>, im2col_smem_bytes<32>())
+#undef YF_OPTIN
+  return cudaSuccess;
+}
+
+}  // namespace yf

@@ -1,0 +1,88 @@
+// yf_kernels.cuh -- launch interface of the layer kernels (implemented in yf_kernels.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "yf_plan.h"
+
+namespace yf {
+
+constexpr int kMaxEpiCh = 1024;          // __constant__ EpiCh table entries (32 KB)
+
+// Where an epilogue writes (shared by every kernel).  Pointers are to element [row 0, channel 0]
+// of the destination buffer; a row is one pixel, `*_pitch` bytes apart.
+struct EpiOut {
+  int8_t* out; int out_pitch; int out_coff; int cout; int fill_to;   // [cout, fill_to) zero-filled
+  int8_t* raw; int raw_pitch;           // observer: main op output (before tables)
+  int8_t* mid; int mid_pitch;           // observer: after table 1 when a second table follows
+  int8_t* pre_add; int pre_add_pitch;   // observer: conv output before the fused ADD
+  const int8_t* add_in; int add_pitch; int add_coff;
+  AddParams add;
+  int epi_base;
+  const uint8_t* lut1;                  // device pointers to 256-byte tables (nullptr = none)
+  const uint8_t* lut2;
+};
+
+struct Conv1x1Args {
+  const uint8_t* w_img; int w_bytes;
+  int nchunk, nk;                        // 16-byte K chunks loaded / 32-wide MMAs issued per tile
+  long long M; int num_tiles;            // valid rows (pixels), 128-row tiles
+  EpiOut eo;
+  int* err;
+};
+
+struct ConvIm2colArgs {
+  const int8_t* in;                      // dense [n, Hin, Win, 3]
+  const uint8_t* w_img; int w_bytes;
+  int n_img, Hin, Win, Hout, Wout, band_rows, bands, in_zp;
+  EpiOut eo;
+  int* err;
+};
+
+struct DwArgs {
+  const int8_t* in; int in_pitch;
+  const uint32_t* w1h;                   // [9][in_pitch] one-hot dp4a words
+  int n_img, Hin, Win, Hout, Wout, stride, pad_t, pad_l, in_zp, words;   // words = ceil(C/4)
+  EpiOut eo;
+};
+
+struct PoolArgs {
+  const int8_t* in; int in_pitch;
+  int n_img, Hin, Win, Hout, Wout, k, stride, pad_t, pad_l, words;
+  EpiOut eo;
+};
+
+struct LutArgs {
+  const int8_t* in; int in_pitch; int in_coff;
+  long long rows; int words;
+  EpiOut eo;
+};
+
+struct DecodeArgs {
+  const int8_t* head;                    // [n, gh, gw, 18]
+  int n_img, gh, gw;
+  float scale; int zp;
+  float conf_thr, iou_thr; int plus_one;
+  float* dets;                           // [n, max_det, 5]
+  int* counts;                           // [n]
+  int max_det;
+};
+
+struct PrepArgs {                        // yoloface.c:26-93 on device
+  const uint8_t* frames;                 // [n, 112*112*2] RGB565 big-endian byte pairs
+  int8_t* out;                           // [n, 56, 56, 3]
+  int n_img;
+};
+
+cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s);
+cudaError_t launch_conv1x1(const CUtensorMap& tmapA, const Conv1x1Args& a, int npad, int sm_count, cudaStream_t s);
+cudaError_t launch_conv_im2col(const ConvIm2colArgs& a, int npad, int sm_count, cudaStream_t s);
+cudaError_t launch_dw(const DwArgs& a, cudaStream_t s);
+cudaError_t launch_pool(const PoolArgs& a, cudaStream_t s);
+cudaError_t launch_lut(const LutArgs& a, cudaStream_t s);
+cudaError_t launch_decode_nms(const DecodeArgs& a, cudaStream_t s);
+cudaError_t launch_prep_rgb565(const PrepArgs& a, cudaStream_t s);
+cudaError_t kernels_init();              // opt-in dynamic smem sizes
+
+}  // namespace yf

@@ -1,0 +1,140 @@
+// yf_plan.h -- model compiler of the B200 yoloface runtime (host side).
+//
+// Reads the int8 .tflite (the artefact X-CUBE-AI's "generate" step consumes,
+// stm32/X-CUBE-AI/App/network_generate_report.txt:3) and lowers its 54 operators to a short list of
+// fused device steps, the way ST's code generator lowers them to 31 c-nodes
+// (stm32/X-CUBE-AI/App/network.c:2193-2938): PAD folded into the consumer's border handling,
+// LEAKY_RELU / QUANTIZE turned into 256-entry tables applied in the producer's epilogue,
+// ADD fused into the second producer, CONCATENATION made zero-copy (producers write channel slices).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace yf {
+
+enum TflOp : int {
+  OP_ADD = 0, OP_CONCATENATION = 2, OP_CONV_2D = 3, OP_DEPTHWISE_CONV_2D = 4, OP_MAX_POOL_2D = 17,
+  OP_PAD = 34, OP_LEAKY_RELU = 98, OP_QUANTIZE = 114
+};
+
+struct TflTensor {
+  std::vector<int> shape;
+  int type = 0;                 // 9 = INT8, 2 = INT32
+  std::vector<float> scale;
+  std::vector<int64_t> zp;
+  int qdim = 0;
+  const uint8_t* data = nullptr;
+  size_t size = 0;
+  std::string name;
+};
+struct TflOperator {
+  int opcode = -1;
+  std::vector<int> in;
+  int out = -1;
+  int padding_same = 0, stride_w = 1, stride_h = 1, filter_w = 1, filter_h = 1, depth_mult = 1, axis = 3, fused_act = 0;
+  float alpha = 0.f;
+};
+struct TflModel {
+  std::vector<uint8_t> bytes;   // owned copy of the flatbuffer
+  std::vector<TflTensor> tensors;
+  std::vector<TflOperator> ops;
+  int input = -1, output = -1;
+  bool parse(const uint8_t* buf, size_t len, std::string* err);
+};
+
+// ---- fixed-point parameters (TFLite quantization_util.cc / common.h) ----
+void quantize_multiplier(double d, int32_t* mult, int* shift);
+int32_t mbqm_host(int32_t x, int32_t mult, int shift);
+
+// Per-output-channel requantisation constants in the folded form the CUDA epilogues evaluate:
+//   t = ((int64)(acc << ls) * mult + add64) >> 31          == SRDHM((acc + bias') << ls, mult)
+//   y = (t + c2 + ((t >> 31) & sgn_mask)) >> e             == RoundingDivideByPOT(t, e) + zp_out
+// with bias' = bias - zp_in * sum(w) (zero-point folded: the MMA runs on raw int8).
+struct alignas(16) EpiCh {
+  int64_t add64;
+  int32_t mult;
+  int32_t c2;
+  int32_t e;
+  int32_t ls;
+  int32_t sgn_mask;
+  int32_t pad_;
+};
+static_assert(sizeof(EpiCh) == 32, "EpiCh layout");
+
+// ADD (add.cc::Prepare): left_shift 20, three Q31 multipliers
+struct AddParams {
+  int32_t zp1, zp2, zp_out;
+  int32_t m1, m2, mo;
+  int32_t s1, s2, so;     // TFLite shifts (<= 0)
+  int32_t enabled;
+};
+
+enum StepKind : int { STEP_CONV_IM2COL = 0, STEP_CONV1X1 = 1, STEP_DW = 2, STEP_MAXPOOL = 3, STEP_LUT = 4 };
+
+// A physical activation buffer in HBM: [capacity, H, W, CP] int8, CP = channel pitch (multiple of 16).
+struct PBuffer {
+  int H = 0, W = 0, C = 0, CP = 0;       // C = channels in use (incl. slot padding)
+  bool is_input = false;                 // the caller's dense [B,H,W,3] input (pitch 3)
+  bool is_output = false;                // the caller's dense [B,H/8,W/8,18] head (pitch 18)
+  bool observer_only = false;            // side tensor, allocated only in observer mode
+  size_t offset = 0;                     // byte offset inside the per-chunk arena (x capacity)
+};
+// where a TFLite tensor lives: buffer + first physical channel
+struct TensorLoc { int buf = -1; int coff = 0; int C = 0; };
+
+struct Step {
+  StepKind kind;
+  int op_first = -1;            // TFLite op index of the main operator (for reports/observer)
+  std::vector<int> ops;         // every TFLite op folded into this step
+  std::string name;
+  // data flow (indices into Plan::buffers)
+  int in_buf = -1, in_coff = 0;
+  int add_buf = -1, add_coff = 0;         // skip operand of a fused ADD
+  int out_buf = -1, out_coff = 0;
+  int raw_buf = -1;             // observer: conv/pool output before any table (TFLite tensor of the main op)
+  int mid_buf = -1;             // observer: after table 1 (LEAKY_RELU output) when a second table follows
+  int pre_add_buf = -1;         // observer: conv output before the fused ADD
+  // geometry
+  int Hin = 0, Win = 0, Cin = 0, Hout = 0, Wout = 0, Cout = 0;
+  int kh = 1, kw = 1, stride = 1, pad_t = 0, pad_l = 0;
+  int in_zp = 0;                // value of out-of-bounds cells (PAD writes the zero point)
+  // GEMM shape
+  int Kpad = 0, Npad = 0;
+  // parameters (offsets into Plan blobs)
+  int epi_base = -1;            // first EpiCh of this step in Plan::epi
+  int lut1 = -1, lut2 = -1;     // indices into Plan::luts (256-byte tables), -1 = none
+  int lut_fused = -1;           // lut2 o lut1 composed (fast mode)
+  size_t w_off = 0, w_bytes = 0;  // packed weights inside Plan::wblob
+  AddParams add{};
+  // im2col band decomposition (STEP_CONV_IM2COL)
+  int band_rows = 0, bands = 0;
+};
+
+struct Plan {
+  int H = 0, W = 0;                       // network input size
+  int GH = 0, GW = 0;                     // head grid
+  std::vector<PBuffer> buffers;
+  std::vector<TensorLoc> loc;             // per TFLite tensor
+  std::vector<Step> steps;
+  std::vector<EpiCh> epi;
+  std::vector<uint8_t> luts;              // n x 256
+  std::vector<uint8_t> wblob;             // packed weights (device image), 16-B aligned pieces
+  size_t arena_bytes_per_image = 0;       // fast mode
+  size_t arena_bytes_per_image_observer = 0;
+  int input_buf = -1, output_buf = -1;
+  float out_scale = 0.f; int out_zp = 0;
+  long macs_per_image = 0;
+};
+
+// ST weight-blob layout (stm32/X-CUBE-AI/App/network.c:3117-3263): per conv/depthwise operator in
+// graph order, int8 weights then int32 bias, each piece starting on a 4-byte boundary.
+struct BlobPiece { int op; size_t w_off, w_len, b_off, b_len; };
+std::vector<BlobPiece> st_blob_layout(const TflModel& m, size_t* total);
+std::vector<uint8_t> st_blob_from_model(const TflModel& m);
+
+// Build the execution plan for an HxWx3 input.  `blob` (optional, ST layout) overrides the
+// flatbuffer's weight/bias bytes -- this is how ai_network_init(params) feeds weights.
+bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err);
+
+}  // namespace yf

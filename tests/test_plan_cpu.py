@@ -1,0 +1,121 @@
+"""CPU checks of the product's host logic: the C-ABI library loads and exports every declared
+symbol, fails loudly without a GPU, regenerates ST's weight blob, and lowers the 54 TFLite ops to
+26 fused steps whose tables reproduce the oracle bit-exactly (evaluated by tests/plan_emulator.py)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pkg
+from oracle_lib import vector_a, vector_b
+from plan_emulator import Emulator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def yf():
+    m = pkg.load()
+    m.build()
+    return m
+
+
+def test_library_exports_every_declared_symbol(yf):
+    L = yf.lib()
+    declared = set()
+    for h in ("network.h", "network_data.h", "yoloface_b200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        declared |= set(re.findall(r"AI_API_ENTRY\s+[\w\s\*]+?\b((?:ai_network|yf_b200)_\w+)\s*\(", src))
+    assert len(declared) >= 27
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared <= set(yf.EXPORTS)
+
+
+def test_abi_struct_layout(yf):
+    # ai_platform.h:517-525 (32 bytes on LP64), :467-470, :348-357
+    assert C.sizeof(yf.AiBuffer) == 32 and yf.AiBuffer.data.offset == 16 and yf.AiBuffer.channels.offset == 12
+    assert C.sizeof(yf.AiError) == 4 and C.sizeof(yf.AiNetworkParams) == 64
+    assert yf.AI_BUFFER_FORMAT_S8 == 0x00840440 and yf.AI_BUFFER_FORMAT_U8 == 0x00040440
+
+
+def test_no_cpu_fallback(yf):
+    """Without a CUDA device the product must refuse to create a network (never compute on CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(yf.AiRuntimeError) as ei:
+        yf.Network()
+    assert ei.value.type == 0x33      # AI_ERROR_CREATE_FAILED
+    assert "no CPU path" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_weights_blob_matches_st(yf, golden):
+    """ai_network_data_weights_get() regenerates network_data.c's 11,304-byte blob from the .tflite."""
+    blob = yf.weights_blob()
+    assert blob == golden["st_blob"].tobytes()
+
+
+def test_plan_structure(yf):
+    P = yf.plan(56, 56)
+    assert len(P["steps"]) == 26 and P["GH"] == 7 and P["GW"] == 7
+    assert P["macs_per_image"] == 1029000
+    kinds = [s["kind"] for s in P["steps"]]
+    assert kinds.count(0) == 1 and kinds.count(1) == 16 and kinds.count(2) == 7 and kinds.count(3) == 2
+    folded = sorted(o for s in P["steps"] for o in s["ops"])
+    assert folded == [i for i in range(54) if i not in (22, 46)]   # concats are zero-copy
+    assert P["n_epi"] == 544                                   # sum of conv/depthwise output channels
+    # ST folds the same way: 31 c-nodes = 26 compute nodes + 3 eltwise + 2 concat (network.c:2193-2938)
+    assert sum(1 for s in P["steps"] if s["add"][0]) == 3
+
+
+@pytest.mark.parametrize("observer", [True, False])
+def test_plan_tables_reproduce_oracle(yf, oracle, golden, observer):
+    P = yf.plan(56, 56)
+    emu = Emulator(P)
+    imgs = [vector_a(), vector_b(), golden["images"][0], golden["images"][13],
+            np.random.default_rng(3).integers(-128, 128, (56, 56, 3), dtype=np.int8)]
+    for img in imgs:
+        head, outs = oracle.run(img, dump=True)
+        bufs = emu.run(img, observer=observer)
+        assert np.array_equal(emu.tensor(bufs, 100), head)
+        if observer:
+            checked = 0
+            for op in range(54):
+                t = oracle.op(op)["output"]
+                got = emu.tensor(bufs, t)
+                if got is None or oracle.op(op)["opcode"] == 2:
+                    continue
+                assert np.array_equal(got, outs[op]), "op %d tensor %d" % (op, t)
+                checked += 1
+            assert checked == 49      # 54 ops - 3 PAD (folded) - 2 CONCAT (views)
+            # concat outputs: slots hold the inputs in order
+            for op in (22, 46):
+                o = oracle.op(op)
+                cat = np.concatenate([emu.tensor(bufs, t) for t in o["inputs"]], axis=-1)
+                assert np.array_equal(cat, outs[op])
+
+
+def test_plan_with_caller_supplied_blob(yf, oracle, golden):
+    """Weights come from ai_network_init's params, not from the embedded model: perturb one weight
+    in the ST blob and the plan must change accordingly."""
+    blob = bytearray(golden["st_blob"].tobytes())
+    P0 = yf.plan(56, 56, bytes(blob))
+    assert np.array_equal(P0["wblob"], yf.plan(56, 56)["wblob"])
+    blob[5] = (blob[5] + 1) & 0xFF
+    P1 = yf.plan(56, 56, bytes(blob))
+    assert not np.array_equal(P0["wblob"], P1["wblob"])
+
+
+def test_plan_other_resolutions(yf, oracle):
+    for H, W in ((112, 112), (224, 224), (64, 96)):
+        P = yf.plan(H, W)
+        assert (P["GH"], P["GW"]) == (H // 8, W // 8)
+    P = yf.plan(112, 112)
+    img = np.random.default_rng(9).integers(-128, 128, (112, 112, 3), dtype=np.int8)
+    bufs = Emulator(P).run(img, observer=False)
+    assert np.array_equal(Emulator(P).tensor(bufs, 100), oracle.run(img))
+    with pytest.raises(RuntimeError):
+        yf.plan(60, 56)
