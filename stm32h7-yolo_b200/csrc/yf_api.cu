@@ -652,7 +652,7 @@ AI_API_ENTRY int32_t yf_b200_tensor_shape(ai_handle network, int32_t t, int32_t 
   if (!n->initialized) return -1;
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
   const Plan& P = pd->plan;
-  if (t < 0 || t >= static_cast<int>(P.loc.size()) || P.loc[t].buf < 0) return -1;
+  if (t < 0 || t >= static_cast<int>(P.loc.size()) || P.loc[t].buf < 0 || P.loc[t].view) return -1;
   const PBuffer& b = P.buffers[P.loc[t].buf];
   dims[0] = 1; dims[1] = b.H; dims[2] = b.W; dims[3] = P.loc[t].C;
   return 0;
@@ -663,7 +663,7 @@ AI_API_ENTRY int64_t yf_b200_get_tensor(ai_handle network, int32_t t, uint32_t c
   if (!n->initialized || !n->observer) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); set_text("observer mode is off"); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
   const Plan& P = pd->plan;
-  if (t < 0 || t >= static_cast<int>(P.loc.size()) || P.loc[t].buf < 0) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_TENSOR); return -1; }
+  if (t < 0 || t >= static_cast<int>(P.loc.size()) || P.loc[t].buf < 0 || P.loc[t].view) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_TENSOR); return -1; }
   const TensorLoc& L = P.loc[t]; const PBuffer& b = P.buffers[L.buf];
   if (b.is_input) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_TENSOR); return -1; }
   if (count > n->last_run_n) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_BATCH); return -1; }

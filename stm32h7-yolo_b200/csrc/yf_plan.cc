@@ -463,7 +463,7 @@ struct Builder {
         if (ti.scale[0] != to.scale[0] || ti.zp[0] != to.zp[0]) return fail("concat input with different quantisation");
         P.loc[t] = TensorLoc{b, slots[k].first, tc[t]};
       }
-      P.loc[O.out] = TensorLoc{b, 0, off};
+      P.loc[O.out] = TensorLoc{b, 0, off, 1};
       concat_slots[O.out] = slots;
       done[i] = 1;
     }

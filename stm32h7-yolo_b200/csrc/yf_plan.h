@@ -81,7 +81,7 @@ struct PBuffer {
   size_t offset = 0;                     // byte offset inside the per-chunk arena (x capacity)
 };
 // where a TFLite tensor lives: buffer + first physical channel
-struct TensorLoc { int buf = -1; int coff = 0; int C = 0; };
+struct TensorLoc { int buf = -1; int coff = 0; int C = 0; int view = 0; };   // view: concat output (slotted)
 
 struct Step {
   StepKind kind;

@@ -1,0 +1,232 @@
+"""GPU parity tests proper (run on the B200 box with -m gpu): the CUDA path, called through the
+C ABI, against the CPU oracle on the same inputs.  Bit-exact for every int8 tensor; decoded
+boxes within the stated float tolerance."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import pkg
+from oracle_lib import vector_a, vector_b
+
+pytestmark = pytest.mark.gpu
+CONF_TOL, COORD_TOL = 1e-5, 1e-3
+
+
+@pytest.fixture(scope="module")
+def yf():
+    m = pkg.load()
+    if not os.path.exists(m.LIB_PATH):
+        m.build()
+    return m
+
+
+@pytest.fixture(scope="module")
+def net(yf):
+    n = yf.Network(chunk_images=512)
+    yield n
+    n.close()
+
+
+def real_batch(golden, n, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.integers(-128, 128, (n, 56, 56, 3), dtype=np.int8)
+    imgs = golden["images"]
+    x[::2] = imgs[np.arange(len(x[::2])) % len(imgs)]       # every other image is a real face
+    return x
+
+
+def test_reference_call_sequence_single_image(yf, net, oracle, golden):
+    """aiInit()/aiRun() of yoloface.c:188-240 with n_batches = 1 (BASELINE config 1)."""
+    for img, pin in ((vector_a(), golden["head_a"]), (vector_b(), golden["head_b"])):
+        out = net.ai_run(img[None])
+        assert out.dtype == np.int8 and out.shape == (1, 7, 7, 18)
+        assert np.array_equal(out[0], pin)
+        assert np.array_equal(out[0], oracle.run(img))
+    assert net.get_error() == (0, 0)
+
+
+def test_golden_images(net, golden):
+    out = net.ai_run(golden["images"])
+    assert np.array_equal(out, golden["heads_images"])
+
+
+def test_observer_every_tensor(yf, oracle, golden):
+    """Config 1: compare all intermediate tensors, not just the head (observer mode)."""
+    n = yf.Network(observer=True, chunk_images=64)
+    try:
+        batch = np.stack([vector_a(), vector_b(), golden["images"][3], golden["images"][20]])
+        heads = n.ai_run(batch)
+        ref = [oracle.run(b, dump=True) for b in batch]
+        checked = 0
+        for op in range(oracle.num_ops):
+            t = oracle.op(op)["output"]
+            exp = np.stack([r[1][op] for r in ref])
+            if oracle.op(op)["opcode"] == 2:      # CONCATENATION output = slots holding its inputs
+                got = np.concatenate([n.get_tensor(i, len(batch)) for i in oracle.op(op)["inputs"]], axis=-1)
+            else:
+                got = n.get_tensor(t, len(batch))
+            if got is None:
+                assert oracle.op(op)["opcode"] == 34   # only PAD outputs are folded away
+                continue
+            assert np.array_equal(got, exp), "op %d (tensor %d)" % (op, t)
+            checked += 1
+        assert checked == 51          # 54 ops minus the 3 folded PAD outputs
+        assert np.array_equal(heads, np.stack([r[0] for r in ref]))
+    finally:
+        n.close()
+
+
+def test_batch_256_bit_exact(net, oracle, golden):
+    """BASELINE config 2: batch 256 on one GPU, byte-equal int8 heads."""
+    x = np.random.default_rng(0).integers(-128, 128, (256, 56, 56, 3), dtype=np.int8)
+    assert np.array_equal(net.ai_run(x), oracle.run_batch(x, threads=os.cpu_count()))
+    x = real_batch(golden, 256, 1)
+    assert np.array_equal(net.ai_run(x), oracle.run_batch(x, threads=os.cpu_count()))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 511, 513, 1025])
+def test_ragged_batches(net, oracle, golden, n):
+    """Tile tails, chunk boundaries (chunk = 512) and tiny batches."""
+    x = real_batch(golden, n, n)
+    assert np.array_equal(net.run(x), oracle.run_batch(x, threads=os.cpu_count()))
+
+
+def test_large_batch_properties(net, oracle, golden):
+    """Full-size check through size-independent properties: a 16,384-image batch built by tiling
+    64 distinct images must give the tiled 64 heads (batch independence), and a permutation of the
+    batch must permute the heads (no cross-image state)."""
+    base = real_batch(golden, 64, 7)
+    ref = oracle.run_batch(base, threads=os.cpu_count())
+    big = np.tile(base, (256, 1, 1, 1))
+    out = net.run(big)
+    assert np.array_equal(out, np.tile(ref, (256, 1, 1, 1)))
+    perm = np.random.default_rng(2).permutation(len(big))[:4096]
+    assert np.array_equal(net.run(np.ascontiguousarray(big[perm])), out[perm])
+
+
+def test_u16_batch_limit_and_extension(net, golden):
+    """ai_buffer.n_batches is 16-bit (ai_platform.h:519): 65,535 per ai_network_run call;
+    yf_b200_run takes the 32-bit count (BASELINE config 3 issues 65,536)."""
+    base = real_batch(golden, 32, 11)
+    ref = net.run(base)
+    big = np.tile(base, (2048, 1, 1, 1))                    # 65,536 images
+    out = net.run(big)
+    assert np.array_equal(out.reshape(2048, 32, 7, 7, 18), np.broadcast_to(ref, (2048, 32, 7, 7, 18)))
+    out2 = net.ai_run(big[:65535])
+    assert np.array_equal(out2, out[:65535])
+
+
+def test_device_pointers(yf, net, oracle, golden):
+    torch = pytest.importorskip("torch")
+    x = real_batch(golden, 300, 5)
+    xd = torch.from_numpy(x).cuda()
+    od = torch.empty((300, 7, 7, 18), dtype=torch.int8, device="cuda")
+    net.run(xd, od, n=300)
+    torch.cuda.synchronize()
+    assert np.array_equal(od.cpu().numpy(), oracle.run_batch(x, threads=os.cpu_count()))
+    # pinned host input
+    xp = torch.from_numpy(x).pin_memory()
+    assert np.array_equal(net.run(xp, n=300), od.cpu().numpy())
+
+
+def test_decode_and_nms_match_oracle(net, oracle, golden):
+    """Rows a13/a14: decoded boxes/scores after NMS within tolerance, identical keep-set."""
+    x = real_batch(golden, 128, 3)
+    heads = net.run(x)
+    for iou, plus_one in ((0.4, False), (-1.0, False), (0.4, True)):
+        dets, counts = net.decode(heads, 0.7, iou, plus_one, max_det=32)
+        total = 0
+        for i in range(len(x)):
+            ref = oracle.decode_nms(heads[i], 0.7, iou, plus_one)
+            assert counts[i] == len(ref), (i, iou)
+            if len(ref):
+                got = dets[i, :counts[i]]
+                assert np.all(np.abs(got[:, :4] - ref[:, :4]) <= COORD_TOL)
+                assert np.all(np.abs(got[:, 4] - ref[:, 4]) <= CONF_TOL)
+            total += len(ref)
+        assert total > 20                                   # the real faces do produce detections
+    d2, c2 = net.detect(x, 0.7, 0.4, False, max_det=32)
+    d1, c1 = net.decode(heads, 0.7, 0.4, False, max_det=32)
+    assert np.array_equal(c1, c2) and np.array_equal(d1, d2)
+
+
+def test_rgb565_preprocessing_bit_exact(net, oracle):
+    """yoloface.c:26-93 on device."""
+    frames = np.random.default_rng(4).integers(0, 256, (9, 112 * 112 * 2), dtype=np.uint8)
+    got = net.preprocess_rgb565(frames)
+    for i in range(len(frames)):
+        assert np.array_equal(got[i], oracle.rgb565_to_input(frames[i]))
+
+
+def test_other_resolutions(yf, oracle):
+    """BASELINE config 4: 224x224 (4x per side) and 112x112, same weights, bit-exact."""
+    n = yf.Network(chunk_images=64)
+    try:
+        rng = np.random.default_rng(8)
+        for H, W, b in ((224, 224, 5), (112, 112, 9), (64, 96, 3)):
+            n.set_input_size(H, W)
+            x = rng.integers(-128, 128, (b, H, W, 3), dtype=np.int8)
+            out = n.run(x)
+            assert out.shape == (b, H // 8, W // 8, 18)
+            for i in range(b):
+                assert np.array_equal(out[i], oracle.run(x[i])), (H, W, i)
+        n.set_input_size(56, 56)
+        assert np.array_equal(n.run(vector_a()[None])[0], oracle.run(vector_a()))
+    finally:
+        n.close()
+
+
+def test_error_behaviour(yf, golden):
+    """Error latch semantics of network.h:120-132,190-196: run returns <=0, first error is kept
+    until read, reading clears it."""
+    n = yf.Network(chunk_images=16)
+    try:
+        L = n.L
+        x = np.zeros((1, 56, 56, 3), np.int8); y = np.zeros((1, 7, 7, 18), np.int8)
+        bi = yf.AiBuffer(yf.AI_BUFFER_FORMAT_S8, 1, 56, 56, 3, x.ctypes.data, None)
+        bo = yf.AiBuffer(yf.AI_BUFFER_FORMAT_S8, 1, 7, 7, 18, y.ctypes.data, None)
+        assert L.ai_network_run(n.handle, C.byref(bi), C.byref(bo)) == 1
+        bad = yf.AiBuffer(yf.AI_BUFFER_FORMAT_S8, 1, 55, 56, 3, x.ctypes.data, None)
+        assert L.ai_network_run(n.handle, C.byref(bad), C.byref(bo)) <= 0
+        assert n.get_error() == (0x12, 0x18)               # INVALID_INPUT / INVALID_SIZE
+        assert n.get_error() == (0, 0)                     # cleared on read
+        bad = yf.AiBuffer(yf.AI_BUFFER_FORMAT_U8, 1, 56, 56, 3, x.ctypes.data, None)
+        assert L.ai_network_run(n.handle, C.byref(bad), C.byref(bo)) <= 0
+        bad2 = yf.AiBuffer(yf.AI_BUFFER_FORMAT_S8, 0, 56, 56, 3, x.ctypes.data, None)
+        assert L.ai_network_run(n.handle, C.byref(bad2), C.byref(bo)) <= 0
+        assert n.get_error() == (0x12, 0x19)               # first error (format) is the one latched
+        bi2 = yf.AiBuffer(yf.AI_BUFFER_FORMAT_S8, 2, 56, 56, 3, x.ctypes.data, None)
+        assert L.ai_network_run(n.handle, C.byref(bi2), C.byref(bo)) <= 0
+        assert n.get_error() == (0x13, 0x21)               # INVALID_OUTPUT / INVALID_BATCH
+        assert L.ai_network_run(n.handle, None, C.byref(bo)) <= 0
+        assert n.get_error() == (0x12, 0x17)
+        assert L.ai_network_forward(n.handle, C.byref(bi)) == 1
+    finally:
+        n.close()
+
+
+def test_caller_supplied_weights_are_used(yf, oracle, golden):
+    """ai_network_init takes its weights from params (network_data.c blob), not from the library."""
+    blob = bytearray(golden["st_blob"].tobytes())
+    n = yf.Network(chunk_images=16, weights=bytes(blob))
+    try:
+        ok = n.ai_run(vector_a()[None])[0]
+        assert np.array_equal(ok, oracle.run(vector_a()))
+    finally:
+        n.close()
+    blob[11232] ^= 0x40                                     # first bias word of conv2d_53 (network.c:3262)
+    n = yf.Network(chunk_images=16, weights=bytes(blob))
+    try:
+        assert not np.array_equal(n.ai_run(vector_a()[None])[0], ok)
+    finally:
+        n.close()
+
+
+def test_launch_counter(net):
+    s0 = net.stats()
+    net.run(np.zeros((8, 56, 56, 3), np.int8))
+    s1 = net.stats()
+    assert s1["kernel_launches"] - s0["kernel_launches"] == s1["steps"] == 26
+    assert s1["sm_count"] == 148
