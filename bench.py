@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py -- yoloface int8 images/sec on N B200s (one process per GPU), next to the CPU baseline.
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU arithmetic (oracle port)
+
+A "step" is one pass of the hot path over one batch of 256 synthetic 56x56x3 int8 images per GPU
+(BASELINE.json configs[1]).  `value` = device-resident throughput (inputs already in HBM, kernels
+queued back to back, CUDA events on the launching stream); `e2e` = the same batch through
+yf_b200_run with pinned HOST buffers (H2D + kernels + D2H of the raw heads inside the timed
+region).  No collective is involved: the batch is sharded by image, ranks only meet at barriers.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BATCH = 256
+RING = 64                       # distinct input batches: 64 x 2.4 MB = 154 MB > 126 MB of L2
+IN_BYTES, OUT_BYTES = 56 * 56 * 3, 7 * 7 * 18
+METRIC = "yoloface int8 images/sec (bit-exact vs TFLite reference kernels)"
+CONFIG = {
+    "workload": "yoloface int8 batch 256 per GPU, 56x56x3 in -> 7x7x18 raw head out (BASELINE configs[1])",
+    "batch_per_gpu": BATCH,
+    "input": "synthetic uniform int8 [256,56,56,3]",
+    "l2": "inputs larger than L2: %d distinct input batches (%.0f MB) used round-robin" % (RING, RING * BATCH * IN_BYTES / 1e6),
+    "sharding": "by image, one process per GPU, no collective",
+}
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        for k, bit in names.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def run(self):
+        if not self.nv:
+            return
+        while not self.stop_flag:
+            try:
+                self.sample()
+            except Exception:  # noqa: BLE001
+                break
+            time.sleep(0.002)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_sample(seconds=10.0):
+    """Oracle port of the reference's CPU arithmetic on all host threads, bounded sample."""
+    import numpy as np
+    from oracle_lib import Oracle
+    o = Oracle()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    probe = rng.integers(-128, 128, (max(64, 2 * cores), 56, 56, 3), dtype=np.int8)
+    t = time.perf_counter(); o.run_batch(probe, threads=cores); dt = time.perf_counter() - t
+    rate = len(probe) / dt
+    n = int(min(32768, max(BATCH, rate * seconds)))
+    n -= n % BATCH
+    x = rng.integers(-128, 128, (n, 56, 56, 3), dtype=np.int8)
+    t = time.perf_counter(); o.run_batch(x, threads=cores); dt = time.perf_counter() - t
+    return {"value": n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "%d images (%d batches of %d) once through the C oracle (TFLite reference-kernel restatement), %d threads, %.1f s"
+                      % (n, n // BATCH, BATCH, cores, dt)}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path.  Its arithmetic lives in TensorFlow-Lite
+    (absent here and not installable) and in ST's closed Cortex-M7 library, so this arm times the
+    oracle port on the box's host cores (DESIGN.md 'Reference arm')."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle_lib import Oracle
+    o = Oracle()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    ring = [rng.integers(-128, 128, (BATCH, 56, 56, 3), dtype=np.int8) for _ in range(4)]
+    for k in range(args.warmup):
+        o.run_batch(ring[k % 4], threads=cores)
+    t = time.perf_counter()
+    for k in range(args.steps):
+        o.run_batch(ring[k % 4], threads=cores)
+    dt = time.perf_counter() - t
+    value = BATCH * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "each step = one 256-image batch through the C oracle on %d host threads" % cores},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import pkg
+    yf = pkg.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if not dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    net = yf.Network(device=local_rank, chunk_images=BATCH)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1234 + rank)
+    d_in = [torch.randint(-128, 128, (BATCH, 56, 56, 3), dtype=torch.int8, device="cuda", generator=gen) for _ in range(RING)]
+    d_out = [torch.empty((BATCH, 7, 7, 18), dtype=torch.int8, device="cuda") for _ in range(RING)]
+    stream = torch.cuda.current_stream()
+    net.set_stream(stream.cuda_stream)
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for k in range(max(args.warmup, 3)):
+        net.enqueue(d_in[k % RING], d_out[k % RING], BATCH)
+    net.sync()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = net.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        net.enqueue(d_in[k % RING], d_out[k % RING], BATCH)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    net.sync()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.result()
+    launches = net.stats()["kernel_launches"] - l0
+    value = world * BATCH * args.steps / (ms * 1e-3)
+
+    # ---------------- end to end through the public API with HOST buffers (`e2e`) ----------------
+    net.set_stream(None)
+    h_in = [torch.empty((BATCH, 56, 56, 3), dtype=torch.int8).pin_memory() for _ in range(RING)]
+    for i, t in enumerate(h_in):
+        t.copy_(d_in[i])
+    h_out = torch.empty((BATCH, 7, 7, 18), dtype=torch.int8).pin_memory()
+    for k in range(max(args.warmup, 3)):
+        net.run(h_in[k % RING], h_out, n=BATCH)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        net.run(h_in[k % RING], h_out, n=BATCH)          # H2D + 26 kernels + D2H, blocking
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": world * BATCH * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": BATCH * IN_BYTES,
+           "d2h_bytes_per_step": BATCH * OUT_BYTES, "api": "yf_b200_run(host pinned in, host pinned out)", "ms_per_step": 1e3 * dt / args.steps}
+    # sanity: the e2e result of the last step equals the device-resident result for that input
+    last = (args.steps - 1) % RING
+    net.run(d_in[last], d_out[last], n=BATCH)
+    assert torch.equal(h_out, d_out[last].cpu()), "host-path and device-path heads differ"
+
+    # ---------------- per-kernel timing -> roofline of the dominant kernel ----------------
+    roofline, per_step = None, []
+    if rank == 0:
+        net.set_step_profiling(True)
+        acc = None
+        reps = 20
+        for k in range(reps + 3):
+            net.run(d_in[k % RING], d_out[k % RING], n=BATCH)
+            if k >= 3:
+                cur = [s["last_ms"] for s in net.steps()]
+                acc = cur if acc is None else [a + c for a, c in zip(acc, cur)]
+        net.set_step_profiling(False)
+        steps = net.steps()
+        total = sum(acc)
+        peak, peak_src = measured_peak_hbm()
+        for s, a in zip(steps, acc):
+            avg_ms = a / reps
+            bytes_launch = (s["bytes_read"] + s["bytes_written"]) * BATCH
+            per_step.append({"name": s["name"], "ms": round(avg_ms, 5), "share": round(a / total, 4),
+                             "alg_bytes": bytes_launch, "GBps": round(bytes_launch / (avg_ms * 1e-3) / 1e9, 2),
+                             "macs": s["macs"] * BATCH})
+        dom = max(per_step, key=lambda d: d["ms"])
+        roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                    "note": "algorithmic bytes per launch (unpadded in+out of the step x 256 images) / mean CUDA-event "
+                            "duration of that kernel over %d launches; step share of the summed per-kernel time %.3f" % (reps, dom["share"])}
+
+    cpu = cpu_baseline_sample() if (rank == 0 and world == 1 and not args.no_cpu) else None
+    net.close()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
+                "data": "synthetic", "config": CONFIG, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu, "kernels": per_step}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,8 +49,8 @@ AI_API_ENTRY ai_bool ai_network_get_report(ai_handle network, ai_network_report*
 /* replaces network.h:131-132 / network.c:3359: first error since the last call; reading clears it */
 AI_API_ENTRY ai_error ai_network_get_error(ai_handle network);
 /* replaces network.h:143-145 / network.c:3365.  network_config: NULL (defaults) or a yf_b200_config
- * wrapped in an ai_buffer (yoloface_b200.h).  The context is a process-wide singleton, as in ST's
- * runtime (g_network, network.c:36). */
+ * wrapped in an ai_buffer (yoloface_b200.h).  ST's runtime hands out one static context
+ * (g_network, network.c:36); here every call creates an independent context (one per GPU/config). */
 AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* network_config);
 /* replaces network.h:156-157 / network.c:3375: AI_HANDLE_NULL on success */
 AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network);

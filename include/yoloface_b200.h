@@ -35,6 +35,8 @@ typedef struct yf_b200_config_ {
 } yf_b200_config;
 
 #define YF_B200_FLAG_OBSERVER 0x1u   /* keep every operator's tensor (slower, more memory) */
+#define YF_B200_FLAG_LAYERED 0x2u    /* always run the layer-by-layer kernels (one launch per fused step) */
+#define YF_B200_FLAG_FUSED_ONLY 0x4u /* fail instead of falling back when the single-kernel path cannot be used */
 
 typedef struct yf_b200_det_ {
   float x1, y1, x2, y2, conf;        /* corners in input pixels (tflite_prediction.py:5-11), confidence */
@@ -48,6 +50,13 @@ AI_API_ENTRY int32_t yf_b200_set_input_size(ai_handle network, int32_t height, i
 /* n images [n,H,W,3] int8 -> heads [n,H/8,W/8,18] int8.  `in`/`out` may each be host or device
  * memory (host memory is fastest when page-locked).  Returns n. */
 AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, uint32_t n);
+
+/* Stream integration: run on the caller's CUDA stream (cudaStream_t; NULL = the library's own).
+ * yf_b200_enqueue queues the kernels for n device-resident images without synchronising (device
+ * pointers only, input 16-byte aligned); yf_b200_sync waits and reports pipeline errors. */
+AI_API_ENTRY int32_t yf_b200_set_stream(ai_handle network, void* cuda_stream);
+AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* d_out, uint32_t n);
+AI_API_ENTRY int32_t yf_b200_sync(ai_handle network);
 
 /* Decode + NMS of heads already computed ([n,gh,gw,18] int8, host or device).
  * conf_thr: keep conf >= conf_thr (0.7 in yoloface.c:123); iou_thr < 0: threshold only (what the
@@ -82,6 +91,8 @@ typedef struct yf_b200_stats_ {
   int32_t sm_count;
   uint32_t chunk_images;
   int32_t steps;              /* fused device steps per image batch (26 for yoloface) */
+  int32_t fused;              /* 1: runs go through the single persistent kernel; 0: layer-by-layer */
+  int32_t fused_smem_bytes;   /* dynamic shared memory of the fused kernel */
 } yf_b200_stats;
 AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* stats);
 
@@ -109,6 +120,9 @@ AI_API_ENTRY void yf_b200_host_free(void* p);
  * NULL).  yf_b200_plan_blob: raw tables, what = 0 EpiCh[], 1 LUTs (n x 256), 2 packed weights.
  * Both return the number of bytes needed (copying min(cap, needed)), <0 on failure. */
 AI_API_ENTRY int64_t yf_b200_plan_json(int32_t height, int32_t width, const void* blob, char* dst, uint64_t cap);
+/* same for the fused single-kernel program (smem map + phases); plan_blob what = 3: its parameter
+ * blob, 4: its EpiCh table.  <0 if this input size cannot run fused. */
+AI_API_ENTRY int64_t yf_b200_fused_json(int32_t height, int32_t width, const void* blob, char* dst, uint64_t cap);
 AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t height, int32_t width, const void* blob, int32_t what, void* dst, uint64_t cap);
 
 /* Human-readable text of the last failure (CUDA error string, plan error, ...). */

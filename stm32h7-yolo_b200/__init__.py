@@ -26,6 +26,8 @@ AI_NETWORK_DATA_WEIGHTS_SIZE = 11304
 AI_NETWORK_DATA_ACTIVATIONS_SIZE = 29784
 YF_B200_CONFIG_MAGIC = 0x32424659
 YF_B200_FLAG_OBSERVER = 1
+YF_B200_FLAG_LAYERED = 2
+YF_B200_FLAG_FUSED_ONLY = 4
 YF_B200_NMS_PLUS_ONE = 1
 
 
@@ -53,7 +55,8 @@ class Det(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("images", C.c_uint64), ("last_run_device_ms", C.c_float),
-                ("device", C.c_int32), ("sm_count", C.c_int32), ("chunk_images", C.c_uint32), ("steps", C.c_int32)]
+                ("device", C.c_int32), ("sm_count", C.c_int32), ("chunk_images", C.c_uint32), ("steps", C.c_int32),
+                ("fused", C.c_int32), ("fused_smem_bytes", C.c_int32)]
 
 
 class StepInfo(C.Structure):
@@ -69,7 +72,7 @@ EXPORTS = [
     "ai_network_data_params_get", "yf_b200_set_input_size", "yf_b200_run", "yf_b200_decode", "yf_b200_detect",
     "yf_b200_preprocess_rgb565", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
     "yf_b200_get_stats", "yf_b200_step_count", "yf_b200_step_info_get", "yf_b200_set_step_profiling",
-    "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob",
+    "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
 ]
 
 _lib = None
@@ -110,6 +113,12 @@ def lib():
     L.yf_b200_set_input_size.argtypes = [vp, i32, i32]
     L.yf_b200_run.restype = i32
     L.yf_b200_run.argtypes = [vp, vp, vp, u32]
+    L.yf_b200_set_stream.restype = i32
+    L.yf_b200_set_stream.argtypes = [vp, vp]
+    L.yf_b200_enqueue.restype = i32
+    L.yf_b200_enqueue.argtypes = [vp, vp, vp, u32]
+    L.yf_b200_sync.restype = i32
+    L.yf_b200_sync.argtypes = [vp]
     L.yf_b200_decode.restype = i32
     L.yf_b200_decode.argtypes = [vp, vp, u32, C.c_float, C.c_float, u32, vp, vp, u32]
     L.yf_b200_detect.restype = i32
@@ -136,6 +145,8 @@ def lib():
     L.yf_b200_last_error_text.restype = C.c_char_p
     L.yf_b200_plan_json.restype = C.c_int64
     L.yf_b200_plan_json.argtypes = [i32, i32, vp, C.c_char_p, C.c_uint64]
+    L.yf_b200_fused_json.restype = C.c_int64
+    L.yf_b200_fused_json.argtypes = [i32, i32, vp, C.c_char_p, C.c_uint64]
     L.yf_b200_plan_blob.restype = C.c_int64
     L.yf_b200_plan_blob.argtypes = [i32, i32, vp, i32, vp, C.c_uint64]
     _lib = L
@@ -190,13 +201,38 @@ def plan(height=56, width=56, blob=None):
     return desc
 
 
+EPI_DTYPE = np.dtype([("add64", "<i8"), ("mult", "<i4"), ("c2", "<i4"), ("e", "<i4"), ("ls", "<i4"), ("sgn_mask", "<i4"), ("pad", "<i4")])
+
+
+def fused_program(height=56, width=56, blob=None):
+    """Fused single-kernel program (smem map, phases, parameter blob, EpiCh table); no GPU needed."""
+    L = lib()
+    bp = C.create_string_buffer(blob, len(blob)) if blob is not None else None
+    n = L.yf_b200_fused_json(height, width, bp, None, 0)
+    if n < 0:
+        raise RuntimeError(L.yf_b200_last_error_text().decode())
+    buf = C.create_string_buffer(n)
+    L.yf_b200_fused_json(height, width, bp, buf, n)
+    prog = json.loads(buf.value.decode())
+    for key, what in (("params", 3), ("epi", 4)):
+        k = L.yf_b200_plan_blob(height, width, bp, what, None, 0)
+        raw = C.create_string_buffer(max(int(k), 1))
+        L.yf_b200_plan_blob(height, width, bp, what, raw, k)
+        prog[key] = raw.raw[:k]
+    prog["params"] = np.frombuffer(prog["params"], dtype=np.uint8)
+    prog["epi"] = np.frombuffer(prog["epi"], dtype=EPI_DTYPE)
+    return prog
+
+
 class Network:
     """aiInit()/aiRun() of stm32/X-CUBE-AI/App/yoloface.c:188-240, batch-capable."""
 
-    def __init__(self, device=-1, chunk_images=0, observer=False, tflite_path=None, weights=None):
+    def __init__(self, device=-1, chunk_images=0, observer=False, tflite_path=None, weights=None, mode="auto"):
         L = self.L = lib()
         self.handle = C.c_void_p()
-        self._cfg = Config(YF_B200_CONFIG_MAGIC, device, chunk_images, YF_B200_FLAG_OBSERVER if observer else 0,
+        flags = (YF_B200_FLAG_OBSERVER if observer else 0) | {"auto": 0, "layered": YF_B200_FLAG_LAYERED,
+                                                              "fused": YF_B200_FLAG_FUSED_ONLY}[mode]
+        self._cfg = Config(YF_B200_CONFIG_MAGIC, device, chunk_images, flags,
                            tflite_path.encode() if tflite_path else None)
         cfgbuf = AiBuffer(AI_BUFFER_FORMAT_U8, 1, 1, 1, C.sizeof(Config), C.cast(C.pointer(self._cfg), C.c_void_p), None)
         err = L.ai_network_create(C.byref(self.handle), C.byref(cfgbuf))
@@ -261,6 +297,20 @@ class Network:
         if self.L.yf_b200_run(self.handle, ip, op, n) != n:
             self._raise("yf_b200_run")
         return out
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        if self.L.yf_b200_set_stream(self.handle, cuda_stream) < 0:
+            self._raise("yf_b200_set_stream")
+
+    def enqueue(self, d_in, d_out, n):
+        """Queue n device-resident images without synchronising (torch CUDA tensors or addresses)."""
+        if self.L.yf_b200_enqueue(self.handle, _ptr(d_in)[0], _ptr(d_out)[0], n) != n:
+            self._raise("yf_b200_enqueue")
+
+    def sync(self):
+        if self.L.yf_b200_sync(self.handle) < 0:
+            self._raise("yf_b200_sync")
 
     def detect(self, inp, conf_thr=0.7, iou_thr=0.4, plus_one=False, max_det=32, heads_out=None, n=None):
         if n is None:

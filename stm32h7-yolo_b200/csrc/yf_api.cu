@@ -44,8 +44,11 @@ struct PlanDev {
   int8_t* d_head = nullptr;             // staging for host outputs [cap,GH,GW,18]
   std::vector<CUtensorMap> tmaps;       // per step (conv1x1 only)
   std::vector<float> step_ms;
+  Plan fplan;                           // same steps with 16-aligned concat slots, for the fused kernel
+  FusedProgram fprog;
+  uint8_t* d_fparams = nullptr;
   ~PlanDev() {
-    cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head);
+    cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams);
   }
 };
 
@@ -57,6 +60,7 @@ struct Network {
   int device = 0, sm_count = 148;
   uint32_t chunk = 1024;
   bool observer = false, step_profiling = false;
+  int mode = 0;                         // 0 auto (fused when possible), 1 layer-by-layer, 2 fused only
   int H = 56, W = 56;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -64,7 +68,7 @@ struct Network {
   float* d_dets = nullptr; int* d_counts = nullptr; size_t dets_cap = 0; uint32_t dets_max = 0;
   uint8_t* d_frames = nullptr; size_t frames_cap = 0;
   std::map<std::pair<int, int>, std::unique_ptr<PlanDev>> plans;
-  PlanDev* active_epi = nullptr;        // whose EpiCh table sits in __constant__ memory
+  cudaStream_t own_stream = nullptr;    // created by the library; `stream` may be a caller's
   uint32_t last_run_n = 0;
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
@@ -72,7 +76,11 @@ struct Network {
 };
 
 std::mutex g_mu;
-Network* g_net = nullptr;               // singleton context, like ST's g_network (network.c:36)
+// ST's runtime has one static context (g_network, network.c:36); a GPU process may want one per
+// device or per configuration, so every create returns a fresh context and all stay valid.
+std::vector<Network*> g_nets;
+const void* g_active_epi[64] = {};      // per device: whose EpiCh table sits in __constant__ memory
+const void* g_active_fused[64] = {};    // per device: whose fused tables sit in __constant__ memory
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -95,7 +103,8 @@ bool cuda_ok(Network* n, cudaError_t e, const char* what, int type = AI_ERROR_IN
 }
 
 Network* as_net(ai_handle h) {
-  return (h && h == g_net) ? g_net : nullptr;
+  for (Network* n : g_nets) if (n == h) return n;
+  return nullptr;
 }
 
 bool is_device_ptr(const void* p) {
@@ -109,7 +118,11 @@ PlanDev* get_plan(Network* n, int H, int W) {
   auto key = std::make_pair(H, W);
   auto it = n->plans.find(key);
   if (it != n->plans.end() && it->second->observer == n->observer && it->second->cap == n->chunk) return it->second.get();
-  if (it != n->plans.end()) { if (n->active_epi == it->second.get()) n->active_epi = nullptr; n->plans.erase(it); }
+  if (it != n->plans.end()) {
+    if (g_active_epi[n->device & 63] == it->second.get()) g_active_epi[n->device & 63] = nullptr;
+    if (g_active_fused[n->device & 63] == it->second.get()) g_active_fused[n->device & 63] = nullptr;
+    n->plans.erase(it);
+  }
   std::unique_ptr<PlanDev> pd(new PlanDev);
   std::string perr;
   if (!build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->plan, &perr)) {
@@ -148,6 +161,18 @@ PlanDev* get_plan(Network* n, int H, int W) {
       n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_TENSOR); return nullptr; }
   }
   pd->step_ms.assign(P.steps.size(), -1.f);
+  // fused single-kernel program (falls back to the layered path when it cannot be built)
+  std::string ferr;
+  if (build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->fplan, &ferr, 16) &&
+      build_fused(pd->fplan, &pd->fprog) && pd->fprog.ok) {
+    if (!cuda_ok(n, cudaMalloc(&pd->d_fparams, pd->fprog.params.size()), "cudaMalloc fused params", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+    if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fparams, pd->fprog.params.data(), pd->fprog.params.size(), cudaMemcpyHostToDevice, n->stream), "upload fused params")) return nullptr;
+    if (!cuda_ok(n, fused_init(pd->fprog.smem_bytes), "fused kernel attributes")) return nullptr;
+  } else {
+    pd->fprog.ok = false;
+    if (pd->fprog.why.empty()) pd->fprog.why = ferr;
+  }
+  if (n->mode == 2 && !pd->fprog.ok) { set_text("fused path unavailable: " + pd->fprog.why); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr; }
   PlanDev* raw = pd.get();
   n->plans[key] = std::move(pd);
   return raw;
@@ -190,9 +215,22 @@ EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* 
 // run the fused steps for nb images whose input is at d_in (device) writing heads to d_head (device)
 bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb) {
   const Plan& P = pd->plan;
-  if (n->active_epi != pd) {
+  if (!pd->observer && !n->step_profiling && n->mode != 1 && pd->fprog.ok) {
+    if (g_active_fused[n->device & 63] != pd) {
+      if (!cuda_ok(n, cudaDeviceSynchronize(), "synchronize before table switch")) return false;
+      if (!cuda_ok(n, upload_fused_tables(pd->fplan.epi.data(), static_cast<int>(pd->fplan.epi.size()), pd->fprog.phases.data(),
+                                          static_cast<int>(pd->fprog.phases.size()), n->stream), "upload fused tables")) return false;
+      g_active_fused[n->device & 63] = pd;
+    }
+    if (!cuda_ok(n, launch_fused(pd->fprog, d_in, d_head, pd->d_fparams, static_cast<int>(nb), n->sm_count, n->d_err, n->stream), "fused kernel")) return false;
+    ++n->launches;
+    return true;
+  }
+  if (g_active_epi[n->device & 63] != pd) {
+    // the table is shared by every context on this device: order the overwrite after prior work
+    if (!cuda_ok(n, cudaDeviceSynchronize(), "synchronize before table switch")) return false;
     if (!cuda_ok(n, upload_epi_table(P.epi.data(), static_cast<int>(P.epi.size()), n->stream), "upload epilogue table")) return false;
-    n->active_epi = pd;
+    g_active_epi[n->device & 63] = pd;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (n->step_profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
@@ -398,12 +436,14 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     set_text("libyoloface_b200 carries sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
     err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
   }
-  if (g_net) { delete g_net; g_net = nullptr; }     // singleton: a second create re-creates
   std::unique_ptr<Network> n(new Network);
   n->device = dev; n->sm_count = prop.multiProcessorCount;
   if (cfg && cfg->chunk_images) n->chunk = cfg->chunk_images;
   else if (const char* e = std::getenv("YF_B200_CHUNK")) n->chunk = static_cast<uint32_t>(std::max(1, std::atoi(e)));
   n->observer = cfg && (cfg->flags & YF_B200_FLAG_OBSERVER);
+  if (cfg && (cfg->flags & YF_B200_FLAG_LAYERED)) n->mode = 1;
+  else if (cfg && (cfg->flags & YF_B200_FLAG_FUSED_ONLY)) n->mode = 2;
+  else if (const char* e = std::getenv("YF_B200_MODE")) n->mode = !std::strcmp(e, "layered") ? 1 : (!std::strcmp(e, "fused") ? 2 : 0);
   const char* path = cfg && cfg->tflite_path ? cfg->tflite_path : std::getenv("YF_B200_TFLITE");
   std::string perr; bool ok;
   if (path && *path) {
@@ -417,14 +457,15 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr);
   }
   if (!ok) { set_text("model: " + perr); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; return err; }
-  if (cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
       cudaEventCreate(&n->ev1) != cudaSuccess || cudaMalloc(&n->d_err, sizeof(int)) != cudaSuccess ||
       cudaMemset(n->d_err, 0, sizeof(int)) != cudaSuccess || kernels_init() != cudaSuccess) {
     set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
     err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
   }
-  g_net = n.release();
-  *network = g_net;
+  n->stream = n->own_stream;
+  g_nets.push_back(n.get());
+  *network = n.release();
   return err;
 }
 
@@ -434,10 +475,15 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   if (!n) return network;
   cudaSetDevice(n->device);
   cudaStreamSynchronize(n->stream);
+  for (auto& kv : n->plans) {
+    if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
+    if (g_active_fused[n->device & 63] == kv.second.get()) g_active_fused[n->device & 63] = nullptr;
+  }
   n->plans.clear();
   cudaFree(n->d_err); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
-  cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->stream);
-  delete n; g_net = nullptr;
+  cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream);
+  g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end());
+  delete n;
   return AI_HANDLE_NULL;
 }
 
@@ -473,7 +519,11 @@ AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params*
   }
   n->blob.assign(blob, blob + need);
   cudaSetDevice(n->device);
-  n->plans.clear(); n->active_epi = nullptr;
+  for (auto& kv : n->plans) {
+    if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
+    if (g_active_fused[n->device & 63] == kv.second.get()) g_active_fused[n->device & 63] = nullptr;
+  }
+  n->plans.clear();
   if (!get_plan(n, n->H, n->W)) return false;
   if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "init synchronize", AI_ERROR_INIT_FAILED)) return false;
   n->initialized = true;
@@ -559,6 +609,34 @@ AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, u
   if (!out) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (count == 0) return 0;
   return run_images(n, in, out, count, false, nullptr);
+}
+
+AI_API_ENTRY int32_t yf_b200_set_stream(ai_handle network, void* cuda_stream) {
+  YF_NET_OR_FAIL(n, network)
+  cudaStreamSynchronize(n->stream);
+  n->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : n->own_stream;
+  return 0;
+}
+
+AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* d_out, uint32_t count) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15)) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (!d_out) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  for (uint32_t done = 0; done < count; done += pd->cap) {
+    const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+    if (!run_steps(n, pd, static_cast<const int8_t*>(d_in) + done * in_sz, static_cast<int8_t*>(d_out) + done * out_sz, nb)) return -1;
+    n->last_run_n = nb;
+  }
+  n->images += count;
+  return static_cast<int32_t>(count);
+}
+
+AI_API_ENTRY int32_t yf_b200_sync(ai_handle network) {
+  YF_NET_OR_FAIL(n, network)
+  return check_device_err(n) ? 0 : -1;
 }
 
 AI_API_ENTRY int32_t yf_b200_decode(ai_handle network, const void* heads, uint32_t count, float conf_thr, float iou_thr,
@@ -682,6 +760,8 @@ AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* st) {
   st->device = n->device; st->sm_count = n->sm_count; st->chunk_images = n->chunk;
   auto it = n->plans.find(std::make_pair(n->H, n->W));
   st->steps = it == n->plans.end() ? 0 : static_cast<int32_t>(it->second->plan.steps.size());
+  st->fused = (it != n->plans.end() && !n->observer && !n->step_profiling && n->mode != 1 && it->second->fprog.ok) ? 1 : 0;
+  st->fused_smem_bytes = it == n->plans.end() ? 0 : it->second->fprog.smem_bytes;
   return 0;
 }
 
@@ -777,14 +857,56 @@ AI_API_ENTRY int64_t yf_b200_plan_json(int32_t H, int32_t W, const void* blob, c
   return static_cast<int64_t>(j.size() + 1);
 }
 
+static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedProgram* F) {
+  static TflModel model; static std::once_flag once; static bool ok = false;
+  std::call_once(once, [] { std::string e; ok = model.parse(yf_embedded_model, yf_embedded_model_len, &e); });
+  if (!ok) return false;
+  size_t need = 0; st_blob_layout(model, &need);
+  std::string perr;
+  if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr, 16)) { set_text("plan: " + perr); return false; }
+  build_fused(*P, F);
+  if (!F->ok) { set_text("fused: " + F->why); return false; }
+  return true;
+}
+
+AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, char* dst, uint64_t cap) {
+  Plan P; FusedProgram F;
+  if (!host_fused(H, W, blob, &P, &F)) return -1;
+  std::string j = "{";
+  auto kv = [&](const char* k, long long v, bool comma = true) { j += std::string("\"") + k + "\":" + std::to_string(v) + (comma ? "," : ""); };
+  kv("in_off", F.in_off); kv("in_bytes", F.in_bytes); kv("arena_off", F.arena_off); kv("arena_bytes", F.arena_bytes);
+  kv("slot_off", F.slot_off); kv("slot_bytes", F.slot_bytes); kv("smem_bytes", F.smem_bytes); kv("head_bytes", F.head_bytes);
+  kv("warpgroups", kFusedWarpgroups);
+  j += "\"phases\":[";
+  for (size_t i = 0; i < F.phases.size(); ++i) {
+    const FusedPhase& p = F.phases[i];
+    j += "{";
+    kv("kind", p.kind); kv("Hin", p.Hin); kv("Win", p.Win); kv("Hout", p.Hout); kv("Wout", p.Wout); kv("rows_in", p.rows_in); kv("rows_out", p.rows_out);
+    kv("stride", p.stride); kv("pad_t", p.pad_t); kv("pad_l", p.pad_l); kv("ksize", p.ksize); kv("in_off", p.in_off); kv("in_cs", p.in_cs);
+    kv("out_off", p.out_off); kv("out_cs", p.out_cs); kv("add_off", p.add_off); kv("add_cs", p.add_cs); kv("nk", p.nk); kv("npad", p.npad);
+    kv("cout", p.cout); kv("chunks_out", p.chunks_out); kv("epi_base", p.epi_base); kv("has_lut", p.has_lut); kv("in_zp", p.in_zp);
+    kv("to_global", p.to_global); kv("param_off", p.param_off); kv("param_bytes", p.param_bytes); kv("w_off", p.w_off); kv("lut_off", p.lut_off);
+    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("scratch_off", p.scratch_off);
+    j += "\"add\":[" + std::to_string(p.add.enabled) + "," + std::to_string(p.add.zp1) + "," + std::to_string(p.add.zp2) + "," + std::to_string(p.add.zp_out) + "," +
+         std::to_string(p.add.m1) + "," + std::to_string(p.add.m2) + "," + std::to_string(p.add.mo) + "," + std::to_string(p.add.s1) + "," +
+         std::to_string(p.add.s2) + "," + std::to_string(p.add.so) + "]";
+    j += i + 1 < F.phases.size() ? "}," : "}";
+  }
+  j += "]}";
+  if (dst && cap) { size_t k = std::min<size_t>(cap - 1, j.size()); std::memcpy(dst, j.data(), k); dst[k] = 0; }
+  return static_cast<int64_t>(j.size() + 1);
+}
+
 AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t H, int32_t W, const void* blob, int32_t what, void* dst, uint64_t cap) {
-  Plan P;
-  if (!host_plan(H, W, blob, &P)) return -1;
+  Plan P; FusedProgram F;
+  if (what >= 3 ? !host_fused(H, W, blob, &P, &F) : !host_plan(H, W, blob, &P)) return -1;
   const void* src; size_t n;
   switch (what) {
     case 0: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
     case 1: src = P.luts.data(); n = P.luts.size(); break;
     case 2: src = P.wblob.data(); n = P.wblob.size(); break;
+    case 3: src = F.params.data(); n = F.params.size(); break;
+    case 4: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
     default: return -1;
   }
   if (dst && cap) std::memcpy(dst, src, std::min<size_t>(cap, n));

@@ -1,0 +1,439 @@
+// yf_fused.cu -- the whole yoloface int8 network as ONE persistent sm_100a kernel.
+//
+// One CTA (256 threads) takes one image at a time through all 26 fused steps (SURVEY.md 8a rows
+// a2-a11).  Activations never leave the SM: they sit in shared memory in chunk-planar form
+// [C/16][H*W][16 B], which is directly the canonical no-swizzle K-major UMMA operand layout, so every
+// CONV_2D is  tcgen05.mma.kind::i8 (smem x smem -> TMEM)  on the data where the previous epilogue
+// left it.  Per-phase parameters (packed weights, 256-entry tables, depthwise words) stream through
+// four smem slots with cp.async.bulk (TMA engine), three phases ahead; the next image is prefetched
+// the same way.  HBM traffic per image is the I/O floor: 9,408 B in + 882 B out.
+//
+//   conv phases   one thread issues the MMAs of ALL 128-pixel tiles of the layer (they fit TMEM
+//                 together: <= 224 of the 256 allocated columns) and commits once; then the 8 warps
+//                 split the (tile, 16-channel) units evenly: tcgen05.ld -> TFLite requant ->
+//                 table / ADD -> one 16-byte st.shared per unit row.  No intra-phase barriers.
+//   first conv    implicit GEMM: all threads build A tiles (3 x 16-B chunks per pixel, K laid out
+//                 as [ky][9 taps + 7 don't-care bytes] against zero weights), two tiles per round
+//   depthwise     CUDA cores: one thread = one 4-channel word, fixed per thread (weights and
+//                 requant constants in registers), dp4a against one-hot words, interior fast path
+//   max-pool      separable (row maxima to scratch, then columns), VIMNMX3.S16x2 on unpacked lanes
+#include "yf_kernels.cuh"
+#include "yf_ptx.cuh"
+
+namespace yf {
+
+struct alignas(16) EpiChF { long long add64; int32_t mult; int32_t c2p; int32_t e; int32_t pad_[3]; };
+static_assert(sizeof(EpiChF) == 32, "EpiChF layout");
+__constant__ EpiChF c_epif[kMaxEpiCh];
+__constant__ FusedPhase c_fphase[kFusedMaxPhases];
+
+cudaError_t upload_fused_tables(const EpiCh* epi, int n, const FusedPhase* phases, int nph, cudaStream_t s) {
+  if (n + 16 > kMaxEpiCh || nph > kFusedMaxPhases) return cudaErrorInvalidValue;
+  static EpiChF host[kMaxEpiCh];
+  for (int i = 0; i < kMaxEpiCh; ++i) host[i] = EpiChF{};
+  for (int i = 0; i < n; ++i) {
+    // fold "+128" (table index / int8 bias) into the post-shift constant
+    host[i].add64 = epi[i].add64; host[i].mult = epi[i].mult; host[i].c2p = epi[i].c2 + (128 << epi[i].e); host[i].e = epi[i].e;
+  }
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_epif, host, sizeof(EpiChF) * kMaxEpiCh, 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbolAsync(c_fphase, phases, sizeof(FusedPhase) * static_cast<size_t>(nph), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);      // `host` is static scratch
+}
+
+// ---- fixed-point pieces -------------------------------------------------------------------------
+// returns the int8 result + 128 clamped to [0,255]; c2p = half + (zp_out + 128) << e; needs e >= 1
+__device__ __forceinline__ int32_t requant_idx(int32_t acc, long long add64, int32_t mult, int32_t c2p, int32_t e) {
+  const long long p = static_cast<long long>(acc) * static_cast<long long>(mult) + add64;
+  const int32_t t = static_cast<int32_t>(p >> 31);
+  return __vimin_s32_relu((t + c2p + (t >> 31)) >> e, 255);
+}
+__device__ __forceinline__ int32_t mbqm_f(int32_t x, int32_t m, int s) {
+  const long long ab = static_cast<long long>(x) * static_cast<long long>(m);
+  const int32_t t = static_cast<int32_t>((ab + (1ll << 30)) >> 31);
+  const int rs = -s;
+  if (rs == 0) return t;
+  return (t + (1 << (rs - 1)) + (t >> 31)) >> rs;
+}
+// reference_integer_ops::AddElementwise; x = skip operand, y = this conv's int8 output
+__device__ __noinline__ uint32_t add_word(uint32_t skipw, uint32_t yw, const AddParams a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int32_t x = static_cast<int8_t>((skipw >> (8 * j)) & 0xff), y = static_cast<int8_t>((yw >> (8 * j)) & 0xff);
+    const int32_t sx = mbqm_f((x - a.zp1) << 20, a.m1, a.s1), sy = mbqm_f((y - a.zp2) << 20, a.m2, a.s2);
+    o |= static_cast<uint32_t>(max(-128, min(127, mbqm_f(sx + sy, a.mo, a.so) + a.zp_out)) & 0xff) << (8 * j);
+  }
+  return o;
+}
+
+struct FusedArgs {
+  const int8_t* in; int8_t* out; const uint8_t* params;
+  int n_img, nphases;
+  int in_off, in_bytes, slot_off, slot_bytes, head_bytes;
+  int* err;
+};
+
+constexpr int kFusedThreads = kFusedWarpgroups * 128;
+
+// One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
+__device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, uint32_t taddr, int row, int g,
+                                          int8_t* ghead) {
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+  if (row >= ph.rows_out) return;
+  const int nreal = ph.cout - g * 16;                        // real channels in this chunk (> 0)
+  const EpiChF* ek = &c_epif[ph.epi_base + g * 16];
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (ph.has_lut) {
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi)
+      if (wi * 4 < nreal) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const EpiChF k = ek[wi * 4 + j];
+          w[wi] |= static_cast<uint32_t>(lut[requant_idx(static_cast<int32_t>(v[wi * 4 + j]), k.add64, k.mult, k.c2p, k.e)]) << (8 * j);
+        }
+      }
+  } else {
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi)
+      if (wi * 4 < nreal) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const EpiChF k = ek[wi * 4 + j];
+          w[wi] |= static_cast<uint32_t>(requant_idx(static_cast<int32_t>(v[wi * 4 + j]), k.add64, k.mult, k.c2p, k.e)) << (8 * j);
+        }
+        w[wi] ^= 0x80808080u;                                // index -> int8
+      }
+    if (ph.add_off >= 0) {
+      const uint4 sk = *reinterpret_cast<const uint4*>(smem + ph.add_off + g * ph.add_cs + row * 16);
+      w[0] = add_word(sk.x, w[0], ph.add);
+      if (nreal > 4) w[1] = add_word(sk.y, w[1], ph.add);
+      if (nreal > 8) w[2] = add_word(sk.z, w[2], ph.add);
+      if (nreal > 12) w[3] = add_word(sk.w, w[3], ph.add);
+    }
+  }
+  if (ph.to_global) {                                        // dense [pixels][cout] int8 head, 2-byte aligned rows
+    uint16_t* o = reinterpret_cast<uint16_t*>(ghead + row * ph.cout + g * 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
+  } else {
+    *reinterpret_cast<uint4*>(smem + ph.out_off + g * ph.out_cs + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// all (tile, chunk) units of a conv phase, split across the 8 warps
+__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, uint32_t tmem_base,
+                                              int warp, int lane, int8_t* ghead) {
+  const int ntiles = (ph.rows_out + 127) >> 7;
+  const int q = warp & 3, half = warp >> 2;
+  const uint8_t* lut = slot + ph.lut_off;
+  const int units = ntiles * ph.chunks_out;
+  for (int u = half; u < units; u += kFusedWarpgroups) {
+    const int t = u / ph.chunks_out, g = u - t * ph.chunks_out;
+    if (t * 128 + q * 32 >= ph.rows_out) continue;           // this warp's 32 rows are all padding
+    conv_unit(ph, smem, lut, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+  }
+}
+
+// DEPTHWISE_CONV_2D 3x3
+__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
+  const int nw = (ph.cout + 3) >> 2;                          // real 4-channel words
+  const int per = kFusedThreads / nw;                         // pixels advanced per iteration
+  if (tid >= per * nw) return;
+  const int wd = tid % nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
+  const uint32_t* w1h = reinterpret_cast<const uint32_t*>(slot + ph.dw_off);
+  const EpiCh* epi = reinterpret_cast<const EpiCh*>(slot + ph.dwepi_off);
+  const uint8_t* lut = slot + ph.lut_off;
+  uint32_t w[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const uint4 v = *reinterpret_cast<const uint4*>(w1h + t * cp + ch0);
+    w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
+  }
+  long long k_add[4]; int32_t k_mult[4], k_c2p[4], k_e[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const EpiCh k = epi[ch0 + j]; k_add[j] = k.add64; k_mult[j] = k.mult; k_c2p[j] = k.c2 + (128 << k.e); k_e[j] = k.e; }
+  const int Hin = ph.Hin, Win = ph.Win, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out;
+  const int row16 = Win * 16;
+  const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4;
+  uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
+  const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
+  const bool has_lut = ph.has_lut != 0;
+  int pix = tid / nw;
+  int oy = pix / Wout, ox = pix - oy * Wout;
+  const int dy = per / Wout, dx = per - dy * Wout;
+  for (; pix < rows; pix += per) {
+    const int iy0 = oy * stride - ph.pad_t, ix0 = ox * stride - ph.pad_l;
+    const uint8_t* p = ib + (iy0 * Win + ix0) * 16;
+    uint32_t x[9];
+    if (iy0 >= 0 && iy0 + 2 < Hin && ix0 >= 0 && ix0 + 2 < Win) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) x[ky * 3 + kx] = *reinterpret_cast<const uint32_t*>(p + ky * row16 + kx * 16);
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const bool in = (iy0 + ky >= 0) && (iy0 + ky < Hin) && (ix0 + kx >= 0) && (ix0 + kx < Win);
+          x[ky * 3 + kx] = in ? *reinterpret_cast<const uint32_t*>(p + ky * row16 + kx * 16) : zpw;
+        }
+    }
+    uint32_t ow = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int32_t acc = 0;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc = __dp4a(static_cast<int>(x[t]), static_cast<int>(w[t][j]), acc);
+      const int32_t idx = requant_idx(acc, k_add[j], k_mult[j], k_c2p[j], k_e[j]);
+      ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(lut[idx]) : (idx ^ 0x80)) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(ob + pix * 16) = ow;
+    ox += dx; oy += dy;
+    if (ox >= Wout) { ox -= Wout; ++oy; }
+  }
+}
+
+// signed bytes (b0,b2) / (b1,b3) of a word as two 16-bit lanes each
+__device__ __forceinline__ uint32_t unpack_even(uint32_t x) { return __byte_perm(x, 0u, 0xA280u); }
+__device__ __forceinline__ uint32_t unpack_odd(uint32_t x) { return __byte_perm(x, 0u, 0xB391u); }
+__device__ __forceinline__ uint32_t repack(uint32_t ev, uint32_t od) { return __byte_perm(ev, od, 0x6240u); }
+
+// MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only
+__device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
+  const int nw = (ph.cout + 3) >> 2;
+  const int per = kFusedThreads / nw;
+  const bool active = tid < per * nw;
+  const int wd = tid % nw;
+  const int Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout, k = ph.ksize, stride = ph.stride;
+  const int scs = Hin * Wout * 16;                            // chunk stride of the row-maxima scratch
+  const uint32_t neg = 0x80808080u;
+  if (active) {                                               // pass 1: horizontal window of every input row
+    const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4;
+    uint8_t* sb = smem + ph.scratch_off + (wd >> 2) * scs + (wd & 3) * 4;
+    const int total = Hin * Wout;
+    int it = tid / nw;
+    int y = it / Wout, ox = it - y * Wout;
+    const int dy = per / Wout, dx = per - dy * Wout;
+    for (; it < total; it += per) {
+      const int x0 = max(0, ox * stride - ph.pad_l), x1 = min(Win, ox * stride - ph.pad_l + k);
+      uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
+      const uint8_t* p = ib + (y * Win + x0) * 16;
+      int n = x1 - x0;
+      for (; n >= 2; n -= 2, p += 32) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 16);
+        ev = __vimax3_s16x2(ev, unpack_even(a), unpack_even(b));
+        od = __vimax3_s16x2(od, unpack_odd(a), unpack_odd(b));
+      }
+      if (n) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(p);
+        ev = __vmaxs2(ev, unpack_even(a)); od = __vmaxs2(od, unpack_odd(a));
+      }
+      *reinterpret_cast<uint32_t*>(sb + it * 16) = repack(ev, od);
+      ox += dx; y += dy;
+      if (ox >= Wout) { ox -= Wout; ++y; }
+    }
+  }
+  __syncthreads();
+  if (active) {                                               // pass 2: vertical window over the row maxima
+    const uint8_t* sb = smem + ph.scratch_off + (wd >> 2) * scs + (wd & 3) * 4;
+    uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
+    const uint8_t* lut = slot + ph.lut_off;
+    const int total = Hout * Wout;
+    int it = tid / nw;
+    int oy = it / Wout, ox = it - oy * Wout;
+    const int dy = per / Wout, dx = per - dy * Wout;
+    for (; it < total; it += per) {
+      const int y0 = max(0, oy * stride - ph.pad_t), y1 = min(Hin, oy * stride - ph.pad_t + k);
+      uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
+      const uint8_t* p = sb + (y0 * Wout + ox) * 16;
+      const int step = Wout * 16;
+      int n = y1 - y0;
+      for (; n >= 2; n -= 2, p += 2 * step) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + step);
+        ev = __vimax3_s16x2(ev, unpack_even(a), unpack_even(b));
+        od = __vimax3_s16x2(od, unpack_odd(a), unpack_odd(b));
+      }
+      if (n) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(p);
+        ev = __vmaxs2(ev, unpack_even(a)); od = __vmaxs2(od, unpack_odd(a));
+      }
+      uint32_t m = repack(ev, od);
+      if (ph.has_lut) {
+        m ^= neg;                                             // int8 -> table index
+        m = static_cast<uint32_t>(lut[m & 0xff]) | (static_cast<uint32_t>(lut[(m >> 8) & 0xff]) << 8) |
+            (static_cast<uint32_t>(lut[(m >> 16) & 0xff]) << 16) | (static_cast<uint32_t>(lut[m >> 24]) << 24);
+      }
+      *reinterpret_cast<uint32_t*>(ob + it * 16) = m;
+      ox += dx; oy += dy;
+      if (ox >= Wout) { ox -= Wout; ++oy; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const FusedArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.slot_off + kFusedParamSlots * a.slot_bytes);
+  uint64_t* in_full = bars;                 // input image landed
+  uint64_t* par_full = bars + 1;            // [kFusedParamSlots] parameter slot landed
+  uint64_t* mma_done = bars + 1 + kFusedParamSlots;   // [2] accumulators ready (two used by the first conv's rounds)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + kFusedParamSlots);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(in_full, 1);
+    for (int i = 0; i < kFusedParamSlots; ++i) mbar_init(&par_full[i], 1);
+    mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  uint32_t mma_uses[2] = {0u, 0u}, in_uses = 0u;
+  bool ok = true;
+  uint8_t* img_smem = smem + a.in_off;
+  const int my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t total_pc = static_cast<uint32_t>(my_images) * static_cast<uint32_t>(a.nphases);
+
+  auto load_params = [&](uint32_t pcx) {                    // thread 0 only
+    const FusedPhase& nx = c_fphase[pcx % static_cast<uint32_t>(a.nphases)];
+    uint64_t* bar = &par_full[pcx % kFusedParamSlots];
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
+    bulk_load_1d(smem + a.slot_off + (pcx % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
+  };
+  if (tid == 0 && my_images > 0) {
+    mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
+    bulk_load_1d(img_smem, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+    for (uint32_t i = 0; i + 1 < kFusedParamSlots && i < total_pc; ++i) load_params(i);
+  }
+
+  uint32_t pc = 0;
+  for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
+    int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
+    for (int p = 0; p < a.nphases; ++p, ++pc) {
+      const FusedPhase& ph = c_fphase[p];
+      if (tid == 0 && pc + kFusedParamSlots - 1 < total_pc) load_params(pc + kFusedParamSlots - 1);
+      if (ok && !mbar_wait(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1)) { atomicCAS(a.err, 0, 302); ok = false; }
+      const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
+
+      if (ph.kind == STEP_CONV1X1) {
+        if (tid == 0) {                                       // every tile of the layer, one commit
+          tc_fence_after();
+          const int ntiles = (ph.rows_out + 127) >> 7;
+          const uint32_t sA = smem_u32(smem + ph.in_off), sW = smem_u32(slot + ph.w_off);
+          const uint32_t idesc = umma_idesc_s8(128, ph.npad);
+          for (int t = 0; t < ntiles; ++t)
+            for (int k = 0; k < ph.nk; ++k)
+              mma_i8(tmem_base + t * ph.npad, umma_smem_desc(sA + t * 2048 + k * 2 * ph.in_cs, ph.in_cs, 128, 0),
+                     umma_smem_desc(sW + k * 2 * ph.npad * 16, ph.npad * 16, 128, 0), idesc, k > 0 ? 1u : 0u);
+          mma_commit(&mma_done[0]);
+        }
+        if (ok && !mbar_wait(&mma_done[0], mma_uses[0] & 1)) { atomicCAS(a.err, 0, 301); ok = false; }
+        ++mma_uses[0];
+        tc_fence_after();
+        conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
+        tc_fence_before();
+      } else if (ph.kind == STEP_CONV_IM2COL) {
+        if (p == 0) {
+          if (ok && !mbar_wait(in_full, in_uses & 1)) { atomicCAS(a.err, 0, 303); ok = false; }
+          ++in_uses;
+        }
+        // rounds of two 128-pixel tiles; round r uses A stages (2r, 2r+1) mod 4 and barrier r & 1
+        const int ntiles = (ph.rows_out + 127) >> 7, rounds = (ntiles + 1) >> 1;
+        const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
+        const int row_bytes = ph.Win * 3, rt = tid & 127, hf = tid >> 7;
+        const uint8_t* image = smem + ph.in_off;
+        const uint32_t sW = smem_u32(slot + ph.w_off);
+        const uint32_t idesc = umma_idesc_s8(128, ph.npad);
+        for (int r = 0; r < rounds; ++r) {
+          if (r >= 2) {                                       // stages of round r-2 must have been consumed
+            if (ok && !mbar_wait(&mma_done[r & 1], mma_uses[r & 1] & 1)) { atomicCAS(a.err, 0, 304); ok = false; }
+            ++mma_uses[r & 1];
+          }
+          const int t = 2 * r + hf;
+          uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
+          const int rr = t * 128 + rt;
+          if (rr < ph.rows_out) {
+            const int oy = rr / ph.Wout, ox = rr - oy * ph.Wout;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int iy = 2 * oy - 1 + ky;
+              uint32_t a0 = zpw, a1 = zpw, a2 = zpw;
+              if (iy >= 0) {
+                const int o = iy * row_bytes + (2 * ox - 1) * 3;      // -3 for ox = 0: the image sits 16 B into smem
+                const int base = o & ~3;
+                const uint32_t sel = 0x3210u + 0x1111u * static_cast<uint32_t>(o & 3);
+                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(image + base), w1 = *reinterpret_cast<const uint32_t*>(image + base + 4);
+                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(image + base + 8);
+                a0 = __byte_perm(w0, w1, sel); a1 = __byte_perm(w1, w2, sel); a2 = __byte_perm(w2, 0u, sel);
+                if (ox == 0) a0 = (a0 & 0xff000000u) | (zpw & 0x00ffffffu);
+              }
+              *reinterpret_cast<uint4*>(stage + ky * 2048 + rt * 16) = make_uint4(a0, a1, a2, 0u);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (tid == 0) {
+            tc_fence_after();
+            for (int h = 0; h < 2; ++h) {
+              const int tt = 2 * r + h;
+              if (tt >= ntiles) break;
+              const uint32_t sS = smem_u32(smem + ph.scratch_off + ((2 * r + h) & 3) * 6144);
+              for (int k = 0; k < 2; ++k)
+                mma_i8(tmem_base + tt * ph.npad, umma_smem_desc(sS + k * 4096, 2048, 128, 0),
+                       umma_smem_desc(sW + k * 2 * ph.npad * 16, ph.npad * 16, 128, 0), idesc, k > 0 ? 1u : 0u);
+            }
+            mma_commit(&mma_done[r & 1]);
+          }
+        }
+        for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
+          if (ok && !mbar_wait(&mma_done[r & 1], mma_uses[r & 1] & 1)) { atomicCAS(a.err, 0, 305); ok = false; }
+          ++mma_uses[r & 1];
+        }
+        tc_fence_after();
+        conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
+        tc_fence_before();
+      } else if (ph.kind == STEP_DW) {
+        dw_phase(ph, smem, slot, tid);
+      } else if (ph.kind == STEP_MAXPOOL) {
+        pool_phase(ph, smem, slot, tid);
+      }
+      fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
+      __syncthreads();
+      if (p == 0 && tid == 0 && img + static_cast<int>(gridDim.x) < a.n_img) {   // image buffer free: prefetch the next one
+        mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
+        bulk_load_1d(img_smem, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kFusedTmemCols);
+}
+
+cudaError_t fused_init(int smem_bytes) {
+  return cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+}
+
+cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
+                         int sm_count, int* d_err, cudaStream_t s) {
+  if (n_img <= 0) return cudaSuccess;
+  FusedArgs a{};
+  a.in = d_in; a.out = d_out; a.params = d_params; a.n_img = n_img; a.nphases = static_cast<int>(F.phases.size());
+  a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes;
+  a.head_bytes = F.head_bytes; a.err = d_err;
+  const int per_sm = F.smem_bytes <= 113 * 1024 ? 2 : 1;
+  const int grid = n_img < sm_count * per_sm ? n_img : sm_count * per_sm;
+  yoloface_fused_kernel<<<grid, kFusedThreads, F.smem_bytes, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace yf

@@ -590,6 +590,7 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs p) {
     }
     __syncwarp();
   }
+  for (int k = kept * 5 + lane; k < p.max_det * 5; k += 32) dets[k] = 0.f;    // unused slots read as zeros
   if (lane == 0) p.counts[img] = kept;
 }
 

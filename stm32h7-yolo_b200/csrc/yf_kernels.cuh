@@ -8,7 +8,7 @@
 
 namespace yf {
 
-constexpr int kMaxEpiCh = 1024;          // __constant__ EpiCh table entries (32 KB)
+constexpr int kMaxEpiCh = 832;           // __constant__ EpiCh table entries (26 KB per table)
 
 // Where an epilogue writes (shared by every kernel).  Pointers are to element [row 0, channel 0]
 // of the destination buffer; a row is one pixel, `*_pitch` bytes apart.
@@ -84,5 +84,11 @@ cudaError_t launch_lut(const LutArgs& a, cudaStream_t s);
 cudaError_t launch_decode_nms(const DecodeArgs& a, cudaStream_t s);
 cudaError_t launch_prep_rgb565(const PrepArgs& a, cudaStream_t s);
 cudaError_t kernels_init();              // opt-in dynamic smem sizes
+
+// fused single-kernel path (yf_fused.cu)
+cudaError_t upload_fused_tables(const EpiCh* epi, int n, const FusedPhase* phases, int nph, cudaStream_t s);
+cudaError_t fused_init(int smem_bytes);
+cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
+                         int sm_count, int* d_err, cudaStream_t s);
 
 }  // namespace yf

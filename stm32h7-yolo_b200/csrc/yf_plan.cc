@@ -158,7 +158,7 @@ namespace {
 
 struct Builder {
   const TflModel& m; Plan& P; std::string& err;
-  const uint8_t* blob; size_t blob_len;
+  const uint8_t* blob; size_t blob_len; int slot_align;
   std::vector<std::vector<int>> consumers;           // tensor -> ops
   std::vector<int> th, tw, tc;                       // propagated tensor shapes
   std::vector<char> done;                            // op already folded
@@ -454,7 +454,7 @@ struct Builder {
       const TflOperator& O = m.ops[i]; if (O.opcode != OP_CONCATENATION) continue;
       if (O.axis != 3 && O.axis != -1) return fail("concat axis must be channels");
       int off = 0; std::vector<std::pair<int, int>> slots;
-      for (int t : O.in) { off = round_up(off, 4); slots.push_back({off, tc[t]}); off += tc[t]; }
+      for (int t : O.in) { off = round_up(off, slot_align); slots.push_back({off, tc[t]}); off += tc[t]; }
       int b = new_buffer(th[O.out], tw[O.out], off, false);
       for (size_t k = 0; k < O.in.size(); ++k) {
         int t = O.in[k];
@@ -526,13 +526,135 @@ struct Builder {
 
 }  // namespace
 
-bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err) {
+bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err,
+                int slot_align) {
   *plan = Plan{}; plan->H = H; plan->W = W;
   std::string e;
-  Builder b{m, *plan, e, blob, blob_len};
+  Builder b{m, *plan, e, blob, blob_len, slot_align};
   bool ok = b.run();
   if (!ok && err) *err = e;
   return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused program: shared-memory placement by liveness + per-phase parameter blocks
+// ------------------------------------------------------------------------------------------
+bool build_fused(const Plan& P, FusedProgram* F) {
+  *F = FusedProgram{};
+  auto no = [&](const std::string& w) { F->ok = false; F->why = w; return false; };
+  const int ns = static_cast<int>(P.steps.size());
+  if (ns > kFusedMaxPhases) return no("too many steps");
+  for (const EpiCh& e : P.epi) if (e.e < 1 || e.ls != 0) return no("requant shift outside the fused epilogue's range");
+  // live range of every buffer: first writer .. last reader (in step order)
+  const int nb = static_cast<int>(P.buffers.size());
+  std::vector<int> birth(nb, 1 << 30), death(nb, -1);
+  for (int i = 0; i < ns; ++i) {
+    const Step& s = P.steps[i];
+    if (s.kind == STEP_LUT) return no("stand-alone table step");
+    if (s.kind == STEP_CONV_IM2COL && i != 0) return no("im2col conv is not the first step");
+    if (s.kind != STEP_CONV_IM2COL && P.buffers[s.in_buf].is_input) return no("network input read by a non-im2col step");
+    if (P.buffers[s.out_buf].is_output && (s.kind != STEP_CONV1X1 || i != ns - 1)) return no("head not produced by the last 1x1 conv");
+    if (s.out_coff % 16 || s.in_coff != 0 || s.add_coff % 16) return no("unaligned channel slot");
+    if ((s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && s.Npad > 48) return no("N > 48");
+    if (s.kind == STEP_CONV_IM2COL && s.Npad != 16) return no("first conv with more than 16 output channels");
+    death[s.in_buf] = std::max(death[s.in_buf], i);
+    if (s.add_buf >= 0) death[s.add_buf] = std::max(death[s.add_buf], i);
+    birth[s.out_buf] = std::min(birth[s.out_buf], i); death[s.out_buf] = std::max(death[s.out_buf], i);
+  }
+  auto bytes_of = [&](int b) { const PBuffer& B = P.buffers[b]; return (B.H * B.W * B.CP + 127) & ~127; };
+  // scratch regions live for exactly one phase: the first conv's A stages, the pools' row maxima
+  std::vector<int> scratch_size(ns, 0);
+  for (int i = 0; i < ns; ++i) {
+    const Step& s = P.steps[i];
+    if (s.kind == STEP_CONV_IM2COL) scratch_size[i] = 4 * 6144 + 2048;
+    if (s.kind == STEP_MAXPOOL) scratch_size[i] = ((s.Cout + 15) / 16) * s.Hin * s.Wout * 16;
+    if ((s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && ((s.Hout * s.Wout + 127) / 128) * s.Npad > kFusedTmemCols)
+      return no("accumulator tiles of step " + s.name + " exceed TMEM");
+  }
+  // first-fit placement in birth order (scratch of phase i is born with the buffers written at i)
+  struct Item { int id, birth, death, size; };          // id >= 0: buffer, id < 0: scratch of phase -id-1
+  std::vector<Item> items;
+  for (int b = 0; b < nb; ++b) if (!P.buffers[b].is_input && !P.buffers[b].is_output && !P.buffers[b].observer_only && death[b] >= 0)
+    items.push_back(Item{b, birth[b], death[b], bytes_of(b)});
+  for (int i = 0; i < ns; ++i) if (scratch_size[i]) items.push_back(Item{-i - 1, i, i, (scratch_size[i] + 127) & ~127});
+  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.birth != b.birth ? a.birth < b.birth : a.id > b.id; });
+  struct Live { int off, size, death; };
+  std::vector<Live> live; std::vector<int> off(nb, -1), scratch_off(ns, -1);
+  int arena = 0;
+  for (const Item& it : items) {
+    live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.death < it.birth; }), live.end());
+    std::vector<int> cand{0}; for (const Live& l : live) cand.push_back(l.off + l.size);
+    std::sort(cand.begin(), cand.end());
+    int best = -1;
+    for (int c : cand) {
+      bool clash = false;
+      for (const Live& l : live) if (c < l.off + l.size && l.off < c + it.size) { clash = true; break; }
+      if (!clash) { best = c; break; }
+    }
+    if (it.id >= 0) off[it.id] = best; else scratch_off[-it.id - 1] = best;
+    live.push_back(Live{best, it.size, it.death}); arena = std::max(arena, best + it.size);
+  }
+  // smem map: [input image][arena + over-read guard][parameter slots]
+  const Step& s0 = P.steps[0];
+  F->in_off = 16;                                // the im2col builder reads up to 4 bytes before the image
+  F->in_bytes = s0.Hin * s0.Win * s0.Cin;
+  if (F->in_bytes % 16) return no("input image size is not a multiple of 16 bytes");
+  F->arena_off = (F->in_off + F->in_bytes + 16 + 1023) & ~1023;
+  F->arena_bytes = arena + 8192;                 // a 128-row MMA tile may read past the last rows
+  F->slot_off = F->arena_off + F->arena_bytes;
+  // parameter blocks
+  int slot = 0;
+  for (int i = 0; i < ns; ++i) {
+    const Step& s = P.steps[i];
+    FusedPhase ph{}; ph.kind = s.kind;
+    ph.Hin = s.Hin; ph.Win = s.Win; ph.Hout = s.Hout; ph.Wout = s.Wout; ph.rows_in = s.Hin * s.Win; ph.rows_out = s.Hout * s.Wout;
+    ph.stride = s.stride; ph.pad_t = s.pad_t; ph.pad_l = s.pad_l; ph.ksize = s.kh; ph.in_zp = s.in_zp;
+    const PBuffer& ib = P.buffers[s.in_buf]; const PBuffer& ob = P.buffers[s.out_buf];
+    ph.in_off = ib.is_input ? F->in_off : F->arena_off + off[s.in_buf]; ph.in_cs = ph.rows_in * 16;
+    ph.to_global = ob.is_output ? 1 : 0;
+    ph.out_cs = ph.rows_out * 16;
+    ph.out_off = ob.is_output ? 0 : F->arena_off + off[s.out_buf] + (s.out_coff / 16) * ph.out_cs;
+    ph.add_off = -1; ph.scratch_off = scratch_off[i] >= 0 ? F->arena_off + scratch_off[i] : -1;
+    if (s.add.enabled) { ph.add = s.add; ph.add_cs = ph.rows_out * 16; ph.add_off = F->arena_off + off[s.add_buf] + (s.add_coff / 16) * ph.add_cs; }
+    ph.cout = s.Cout; ph.chunks_out = (s.Cout + 15) / 16; ph.epi_base = s.epi_base; ph.has_lut = s.lut_fused >= 0;
+    ph.npad = s.Npad;
+    // block: [weights][table][depthwise EpiCh]
+    std::vector<uint8_t> blk;
+    auto put = [&](const void* src, size_t n) { size_t o = blk.size(); blk.resize((o + n + 15) & ~size_t(15), 0); std::memcpy(blk.data() + o, src, n); return static_cast<int>(o); };
+    if (s.kind == STEP_CONV1X1) {
+      ph.nk = s.Kpad / 32;
+      ph.w_off = put(P.wblob.data() + s.w_off, s.w_bytes);
+    } else if (s.kind == STEP_CONV_IM2COL) {
+      // K = 64 layout for the fused builder: chunk ky holds the 9 bytes (kx, c) of input row ky,
+      // bytes 9..15 and chunk 3 carry zero weights (the A bytes there are don't-care)
+      if (s.kh != 3 || s.kw != 3 || s.Cin != 3) return no("im2col conv shape");
+      ph.nk = 2;
+      const int8_t* w32 = reinterpret_cast<const int8_t*>(P.wblob.data() + s.w_off);   // [2][Npad][16], k = (ky*3+kx)*3+c
+      std::vector<uint8_t> w64(static_cast<size_t>(4) * s.Npad * 16, 0);
+      for (int o = 0; o < s.Cout; ++o) for (int ky = 0; ky < 3; ++ky) for (int j = 0; j < 9; ++j) {
+        const int k = ky * 9 + j;
+        w64[(static_cast<size_t>(ky) * s.Npad + o) * 16 + j] = static_cast<uint8_t>(w32[(static_cast<size_t>(k / 16) * s.Npad + o) * 16 + k % 16]);
+      }
+      ph.w_off = put(w64.data(), w64.size());
+    } else if (s.kind == STEP_DW) {
+      ph.dw_off = put(P.wblob.data() + s.w_off, s.w_bytes);             // [9][CP] one-hot words
+      std::vector<EpiCh> e(static_cast<size_t>(ph.chunks_out) * 16, EpiCh{});
+      for (int c = 0; c < s.Cout; ++c) e[c] = P.epi[s.epi_base + c];
+      ph.dwepi_off = put(e.data(), e.size() * sizeof(EpiCh));
+    }
+    if (ph.has_lut) ph.lut_off = put(P.luts.data() + static_cast<size_t>(s.lut_fused) * 256, 256);
+    if (blk.empty()) blk.resize(16, 0);
+    ph.param_off = static_cast<int>(F->params.size()); ph.param_bytes = static_cast<int>(blk.size());
+    F->params.insert(F->params.end(), blk.begin(), blk.end());
+    slot = std::max(slot, ph.param_bytes);
+    F->phases.push_back(ph);
+  }
+  F->slot_bytes = (slot + 127) & ~127;
+  F->smem_bytes = F->slot_off + kFusedParamSlots * F->slot_bytes + 256;
+  F->head_bytes = P.GH * P.GW * 18;
+  if (F->smem_bytes > 200 * 1024) return no("activations do not fit shared memory (" + std::to_string(F->smem_bytes) + " bytes)");
+  F->ok = true;
+  return true;
 }
 
 }  // namespace yf

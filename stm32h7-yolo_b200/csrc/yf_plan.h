@@ -135,6 +135,54 @@ std::vector<uint8_t> st_blob_from_model(const TflModel& m);
 
 // Build the execution plan for an HxWx3 input.  `blob` (optional, ST layout) overrides the
 // flatbuffer's weight/bias bytes -- this is how ai_network_init(params) feeds weights.
-bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err);
+// slot_align: alignment (in channels) of concat slots inside their buffer: 4 for the layer-by-layer
+// path (word stores), 16 for the fused kernel (every producer writes whole 16-byte chunks).
+bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err,
+                int slot_align = 4);
+
+// ------------------------------------------------------------------------------------------------
+// Fused single-kernel program: the same steps executed by one persistent CTA per image with every
+// activation resident in shared memory in "chunk-planar" form  [C/16 chunks][H*W rows][16 bytes],
+// which is at the same time (a) the canonical no-swizzle K-major UMMA operand layout (8-row x 16-B
+// core matrices are contiguous: SBO = 128 B, LBO = rows*16 B) and (b) conflict-free for the
+// CUDA-core phases (a warp touches 8 pixels x 16 B = 128 contiguous bytes).
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) FusedPhase {
+  int32_t kind;                 // StepKind (0 im2col conv, 1 conv1x1, 2 depthwise, 3 maxpool)
+  int32_t Hin, Win, Hout, Wout;
+  int32_t rows_in, rows_out;    // pixels per image
+  int32_t stride, pad_t, pad_l, ksize;
+  int32_t in_off, in_cs;        // smem byte offset of the input buffer, bytes between its chunks
+  int32_t out_off, out_cs;      // output buffer (offset already includes the concat slot's first chunk)
+  int32_t add_off, add_cs;      // skip operand of a fused ADD (-1 = none)
+  int32_t nk, npad, cout, chunks_out;   // 32-wide MMAs per tile, padded N, real channels, ceil(cout/16)
+  int32_t epi_base;             // first EpiCh in the __constant__ table
+  int32_t has_lut;
+  int32_t in_zp;
+  int32_t to_global;            // 1: last conv writes the dense int8 head to global memory
+  int32_t param_off, param_bytes;       // this phase's block inside the parameter blob
+  int32_t w_off, lut_off, dw_off, dwepi_off;   // offsets inside the block (bytes)
+  AddParams add;
+  int32_t scratch_off;          // smem scratch: im2col A stages (4 x 6 KB) / separable max-pool row maxima
+  int32_t pad_[1];
+};
+
+struct FusedProgram {
+  bool ok = false;              // false: this resolution/model cannot run fused (use the layered path)
+  std::string why;
+  std::vector<FusedPhase> phases;
+  std::vector<uint8_t> params;  // concatenated per-phase blocks (16-B aligned pieces)
+  int in_off = 0;               // smem: dense input image [H*W*3]
+  int in_bytes = 0;
+  int arena_off = 0, arena_bytes = 0;
+  int slot_off = 0, slot_bytes = 0;     // smem: kFusedParamSlots parameter slots
+  int smem_bytes = 0;
+  int head_bytes = 0;           // bytes per image of the dense head
+};
+constexpr int kFusedMaxPhases = 32;
+constexpr int kFusedWarpgroups = 2;
+constexpr int kFusedParamSlots = 4;
+constexpr int kFusedTmemCols = 256;     // all accumulator tiles of one conv phase live in TMEM at once
+bool build_fused(const Plan& plan, FusedProgram* prog);
 
 }  // namespace yf

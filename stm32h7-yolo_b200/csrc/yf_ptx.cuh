@@ -48,25 +48,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must never hang the GPU box.  Gives up after ~2 s of wall time
-// (%globaltimer); callers record the failure in a global error word and drain.
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  const uint64_t t0 = globaltimer_ns();
+// Bounded wait: a pipeline bug must never hang the GPU box.  Gives up after ~2^32 SM cycles (~2 s);
+// callers record the failure in a global error word and drain.
+static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
 #pragma unroll 1
   for (;;) {
 #pragma unroll 1
-    for (int i = 0; i < 256; ++i)
+    for (int i = 0; i < 64; ++i)
       if (mbar_try_wait(bar, parity)) return true;
-    if (globaltimer_ns() - t0 > 2000000000ull) return false;
+    if (clock64() - t0 > (1ll << 32)) return false;
   }
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;
+#pragma unroll 1
+  for (int i = 0; i < 16; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
   return mbar_wait_slow(bar, parity);
 }
 

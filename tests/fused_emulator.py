@@ -1,0 +1,96 @@
+"""numpy emulation of the fused single-kernel program (yf_b200_fused_json + parameter blob).
+
+Shared memory is one flat byte array pre-filled with random garbage and addressed with the very
+offsets / chunk strides the kernel uses (UMMA operand rows at in_off + chunk*in_cs + row*16, weight
+images [K/16][N][16] in the parameter slot, 16-byte epilogue stores, aliasing by liveness), so that
+layout, aliasing or parameter-block mistakes in csrc/yf_plan.cc::build_fused surface on CPU.
+Test infrastructure only."""
+import numpy as np
+
+from plan_emulator import lut_apply, mbqm, requant
+
+
+def run_fused(F, img, seed=0):
+    rng = np.random.default_rng(seed)
+    smem = rng.integers(0, 256, F["smem_bytes"] + (1 << 16), dtype=np.uint8)
+    smem[F["in_off"]:F["in_off"] + F["in_bytes"]] = np.ascontiguousarray(img).view(np.uint8).reshape(-1)
+    params, epi_all = F["params"], F["epi"]
+    head = None
+
+    def chunk_rows(off, cs, chunk, rows):          # -> int8 [rows,16] view of one chunk
+        a = off + chunk * cs
+        return smem[a:a + rows * 16].view(np.int8).reshape(rows, 16)
+
+    for ph in F["phases"]:
+        slot = params[ph["param_off"]:ph["param_off"] + ph["param_bytes"]]
+        kind, rows_o, cout, npad = ph["kind"], ph["rows_out"], ph["cout"], ph["npad"]
+        lut = slot[ph["lut_off"]:ph["lut_off"] + 256].view(np.int8) if ph["has_lut"] else None
+        if ph["scratch_off"] >= 0:      # the kernel scribbles here during this phase: must not alias anything live
+            size = 4 * 6144 + 2048 if kind == 0 else ph["chunks_out"] * ph["Hin"] * ph["Wout"] * 16
+            smem[ph["scratch_off"]:ph["scratch_off"] + size] = rng.integers(0, 256, size, dtype=np.uint8)
+        if kind in (0, 1):
+            K = ph["nk"] * 32
+            wimg = slot[ph["w_off"]:ph["w_off"] + (K // 16) * npad * 16].view(np.int8).reshape(K // 16, npad, 16)
+            wmat = wimg.transpose(0, 2, 1).reshape(K, npad).astype(np.int64)
+            if kind == 1:
+                A = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, rows_o) for c in range(K // 16)], axis=1).astype(np.int64)
+            else:
+                H, W = ph["Hin"], ph["Win"]
+                x = smem[F["in_off"]:F["in_off"] + H * W * 3].view(np.int8).reshape(H, W, 3).astype(np.int64)
+                xp = np.full((H + 1, W + 3, 3), ph["in_zp"], np.int64); xp[1:, 1:W + 1] = x
+                flat = xp.reshape(H + 1, -1)
+                A = rng.integers(-128, 128, (rows_o, 64)).astype(np.int64)       # don't-care bytes are garbage
+                Ho, Wo = ph["Hout"], ph["Wout"]
+                for r in range(rows_o):
+                    oy, ox = divmod(r, Wo)
+                    for ky in range(3):
+                        A[r, ky * 16:ky * 16 + 9] = flat[2 * oy + ky, (2 * ox) * 3:(2 * ox) * 3 + 9]
+            acc = A @ wmat
+            epi = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
+            y = np.clip(requant(acc[:, :cout], epi), -128, 127)
+            if ph["add_off"] >= 0:
+                _, zp1, zp2, zpo, m1, m2, mo, s1, s2, so = ph["add"]
+                skip = np.concatenate([chunk_rows(ph["add_off"], ph["add_cs"], g, rows_o) for g in range(ph["chunks_out"])], axis=1)[:, :cout].astype(np.int64)
+                y = np.clip(mbqm(mbqm((skip - zp1) << 20, m1, s1) + mbqm((y - zp2) << 20, m2, s2), mo, so) + zpo, -128, 127)
+            elif lut is not None:
+                y = lut_apply(y, lut)
+        elif kind == 2:
+            chunks = ph["chunks_out"]; cp = chunks * 16
+            w1h = slot[ph["dw_off"]:ph["dw_off"] + 9 * cp * 4].view(np.uint32).reshape(9, cp)
+            w = np.zeros((9, cp), np.int64)
+            for c in range(cp):
+                w[:, c] = ((w1h[:, c] >> (8 * (c % 4))) & 0xFF).astype(np.uint8).view(np.int8)
+            epi = slot[ph["dwepi_off"]:ph["dwepi_off"] + cp * 32].view(epi_all.dtype)[:cout]
+            H, W, Ho, Wo, st = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"]
+            x = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, H * W) for c in range(chunks)], axis=1).reshape(H, W, cp).astype(np.int64)
+            xp = np.full((H + 2 + st, W + 2 + st, cp), ph["in_zp"], np.int64)
+            xp[ph["pad_t"]:ph["pad_t"] + H, ph["pad_l"]:ph["pad_l"] + W] = x
+            acc = np.zeros((Ho, Wo, cp), np.int64)
+            for ky in range(3):
+                for kx in range(3):
+                    acc += xp[ky:ky + st * Ho:st, kx:kx + st * Wo:st] * w[ky * 3 + kx]
+            y = np.clip(requant(acc.reshape(Ho * Wo, cp)[:, :cout], epi), -128, 127)
+            if lut is not None:
+                y = lut_apply(y, lut)
+        elif kind == 3:
+            chunks = ph["chunks_out"]; cp = chunks * 16
+            H, W, Ho, Wo, st, k = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"], ph["ksize"]
+            x = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, H * W) for c in range(chunks)], axis=1).reshape(H, W, cp).astype(np.int64)
+            y = np.zeros((Ho * Wo, cout), np.int64)
+            for oy in range(Ho):
+                for ox in range(Wo):
+                    y0, x0 = oy * st - ph["pad_t"], ox * st - ph["pad_l"]
+                    y[oy * Wo + ox] = x[max(0, y0):min(H, y0 + k), max(0, x0):min(W, x0 + k), :cout].reshape(-1, cout).max(axis=0)
+            if lut is not None:
+                y = lut_apply(y, lut)
+        else:
+            raise AssertionError(kind)
+        if ph["to_global"]:
+            head = y.astype(np.int8)
+            continue
+        out = np.zeros((rows_o, ph["chunks_out"] * 16), np.int8)
+        out[:, :cout] = y
+        for g in range(ph["chunks_out"]):
+            a = ph["out_off"] + g * ph["out_cs"]
+            smem[a:a + rows_o * 16] = out[:, g * 16:(g + 1) * 16].reshape(-1).view(np.uint8)
+    return head

@@ -22,9 +22,11 @@ def yf():
     return m
 
 
-@pytest.fixture(scope="module")
-def net(yf):
-    n = yf.Network(chunk_images=512)
+@pytest.fixture(scope="module", params=["fused", "layered"])
+def net(yf, request):
+    """Both execution paths: the single persistent kernel and the layer-by-layer kernels."""
+    n = yf.Network(chunk_images=512, mode=request.param)
+    assert n.stats()["fused"] == (1 if request.param == "fused" else 0)
     yield n
     n.close()
 
@@ -165,8 +167,9 @@ def test_other_resolutions(yf, oracle):
     n = yf.Network(chunk_images=64)
     try:
         rng = np.random.default_rng(8)
-        for H, W, b in ((224, 224, 5), (112, 112, 9), (64, 96, 3)):
+        for H, W, b in ((224, 224, 5), (112, 112, 9), (64, 96, 3), (64, 64, 150)):
             n.set_input_size(H, W)
+            assert n.stats()["fused"] == (1 if H * W <= 64 * 64 else 0)   # large inputs use the layered kernels
             x = rng.integers(-128, 128, (b, H, W, 3), dtype=np.int8)
             out = n.run(x)
             assert out.shape == (b, H // 8, W // 8, 18)
@@ -228,5 +231,5 @@ def test_launch_counter(net):
     s0 = net.stats()
     net.run(np.zeros((8, 56, 56, 3), np.int8))
     s1 = net.stats()
-    assert s1["kernel_launches"] - s0["kernel_launches"] == s1["steps"] == 26
-    assert s1["sm_count"] == 148
+    assert s1["steps"] == 26 and s1["sm_count"] == 148
+    assert s1["kernel_launches"] - s0["kernel_launches"] == (1 if s1["fused"] else 26)

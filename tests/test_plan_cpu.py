@@ -119,3 +119,23 @@ def test_plan_other_resolutions(yf, oracle):
     assert np.array_equal(Emulator(P).tensor(bufs, 100), oracle.run(img))
     with pytest.raises(RuntimeError):
         yf.plan(60, 56)
+
+
+def test_fused_program_reproduces_oracle(yf, oracle, golden):
+    """The single-kernel program (smem map by liveness, chunk-planar operands, per-phase parameter
+    blocks) emulated on a flat, garbage-filled byte array gives the oracle's head bit-exactly."""
+    from fused_emulator import run_fused
+    F = yf.fused_program(56, 56)
+    assert F["smem_bytes"] <= 113 * 1024          # two CTAs per SM
+    assert len(F["phases"]) == 26
+    for seed, img in enumerate([vector_a(), vector_b(), golden["images"][5]]):
+        head = run_fused(F, img, seed)
+        assert np.array_equal(head.reshape(7, 7, 18), oracle.run(img))
+
+
+def test_fused_program_limits(yf):
+    F = yf.fused_program(64, 64)                  # still fits shared memory and TMEM
+    assert F["smem_bytes"] < 113 * 1024
+    for hw in ((64, 96), (224, 224)):             # a layer's accumulator tiles exceed TMEM / smem -> layered path
+        with pytest.raises(RuntimeError):
+            yf.fused_program(*hw)

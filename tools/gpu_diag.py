@@ -57,10 +57,39 @@ def main():
     exp_heads = np.stack([ref[i][0] for i in range(n)])
     print("heads (observer mode) equal:", np.array_equal(heads, exp_heads))
     net.set_observer(False)
+    print("stats after observer off:", net.stats())
     h2 = net.run(batch)
-    print("heads (fast mode) equal:", np.array_equal(h2, exp_heads))
-    if not np.array_equal(h2, exp_heads):
+    eq = np.array_equal(h2, exp_heads)
+    print("heads (auto mode: fused=%d) equal: %s" % (net.stats()["fused"], eq))
+    if not eq:
         bad_total += 1
+        bad = np.argwhere(h2 != exp_heads)
+        print("  fused mismatches: %d/%d first %s; images %s; cells %s; channels %s" % (
+            len(bad), h2.size, bad[:5].tolist(), sorted(set(bad[:, 0])), sorted(set(map(tuple, bad[:, 1:3].tolist())))[:10], sorted(set(bad[:, 3]))))
+    lay = yf.Network(chunk_images=256, mode="layered")
+    h3 = lay.run(batch)
+    print("heads (layered fast mode) equal:", np.array_equal(h3, exp_heads))
+    if not np.array_equal(h3, exp_heads):
+        bad_total += 1
+    import time as _t
+    for nimg in (256, 4096, 32768):
+        big = np.concatenate([batch] * (nimg // n + 1))[:nimg]
+        try:
+            import torch
+            dbig = torch.from_numpy(big).cuda(); dout = torch.empty((nimg, 7, 7, 18), dtype=torch.int8, device="cuda")
+            for who, nn in (("fused", net), ("layered", lay)):
+                nn.enqueue(dbig, dout, nimg); nn.sync()
+                t0 = _t.perf_counter()
+                reps = 20 if nimg <= 4096 else 5
+                for _ in range(reps):
+                    nn.enqueue(dbig, dout, nimg)
+                nn.sync()
+                dt = (_t.perf_counter() - t0) / reps
+                okk = np.array_equal(dout.cpu().numpy()[:n], exp_heads)
+                print("  %-8s n=%6d  %.3f ms  %.2f Mimg/s  ok=%s" % (who, nimg, dt * 1e3, nimg / dt / 1e6, okk))
+        except Exception as e:  # noqa: BLE001
+            print("  timing failed:", e)
+    lay.close()
     # timing per step
     net.set_step_profiling(True)
     big = np.concatenate([batch] * (256 // n + 1))[:256]
