@@ -110,6 +110,10 @@ AI_API_ENTRY int32_t yf_b200_step_info_get(ai_handle network, int32_t step, yf_b
 /* time every step of the next run with CUDA events (adds a sync per step) */
 AI_API_ENTRY int32_t yf_b200_set_step_profiling(ai_handle network, int32_t enable);
 
+/* Cycle trace of the fused kernel: enable, run once, then read nphases+1 SM-clock stamps taken by
+ * CTA 0 at every phase boundary of its first image (profiling aid). */
+AI_API_ENTRY int32_t yf_b200_fused_trace(ai_handle network, int32_t enable, int64_t* stamps, int32_t cap);
+
 /* Page-locked host memory for the fast host path. */
 AI_API_ENTRY void* yf_b200_host_alloc(uint64_t bytes);
 AI_API_ENTRY void yf_b200_host_free(void* p);

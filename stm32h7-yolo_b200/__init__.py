@@ -72,7 +72,7 @@ EXPORTS = [
     "ai_network_data_params_get", "yf_b200_set_input_size", "yf_b200_run", "yf_b200_decode", "yf_b200_detect",
     "yf_b200_preprocess_rgb565", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
     "yf_b200_get_stats", "yf_b200_step_count", "yf_b200_step_info_get", "yf_b200_set_step_profiling",
-    "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
+    "yf_b200_fused_trace", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
 ]
 
 _lib = None
@@ -113,6 +113,8 @@ def lib():
     L.yf_b200_set_input_size.argtypes = [vp, i32, i32]
     L.yf_b200_run.restype = i32
     L.yf_b200_run.argtypes = [vp, vp, vp, u32]
+    L.yf_b200_fused_trace.restype = i32
+    L.yf_b200_fused_trace.argtypes = [vp, i32, C.POINTER(C.c_int64), i32]
     L.yf_b200_set_stream.restype = i32
     L.yf_b200_set_stream.argtypes = [vp, vp]
     L.yf_b200_enqueue.restype = i32
@@ -297,6 +299,11 @@ class Network:
         if self.L.yf_b200_run(self.handle, ip, op, n) != n:
             self._raise("yf_b200_run")
         return out
+
+    def fused_trace(self, enable=True, read=False):
+        buf = (C.c_int64 * 128)()
+        k = self.L.yf_b200_fused_trace(self.handle, int(enable), buf if read else None, 128 if read else 0)
+        return list(buf)[:k] if read else None
 
     def set_stream(self, cuda_stream):
         """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""

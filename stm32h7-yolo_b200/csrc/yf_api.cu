@@ -65,6 +65,7 @@ struct Network {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int* d_err = nullptr;
+  long long* d_trace = nullptr; bool trace_on = false;
   float* d_dets = nullptr; int* d_counts = nullptr; size_t dets_cap = 0; uint32_t dets_max = 0;
   uint8_t* d_frames = nullptr; size_t frames_cap = 0;
   std::map<std::pair<int, int>, std::unique_ptr<PlanDev>> plans;
@@ -222,7 +223,8 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
                                           static_cast<int>(pd->fprog.phases.size()), n->stream), "upload fused tables")) return false;
       g_active_fused[n->device & 63] = pd;
     }
-    if (!cuda_ok(n, launch_fused(pd->fprog, d_in, d_head, pd->d_fparams, static_cast<int>(nb), n->sm_count, n->d_err, n->stream), "fused kernel")) return false;
+    if (!cuda_ok(n, launch_fused(pd->fprog, d_in, d_head, pd->d_fparams, static_cast<int>(nb), n->sm_count, n->d_err, n->stream,
+                                 n->trace_on ? n->d_trace : nullptr), "fused kernel")) return false;
     ++n->launches;
     return true;
   }
@@ -480,7 +482,7 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
     if (g_active_fused[n->device & 63] == kv.second.get()) g_active_fused[n->device & 63] = nullptr;
   }
   n->plans.clear();
-  cudaFree(n->d_err); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
+  cudaFree(n->d_trace); cudaFree(n->d_err); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
   cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream);
   g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end());
   delete n;
@@ -795,6 +797,20 @@ AI_API_ENTRY int32_t yf_b200_step_info_get(ai_handle network, int32_t step, yf_b
   return 0;
 }
 
+// Per-phase cycle trace of the fused kernel (CTA 0, first image): enable, run, then read nphases+1 clock64 stamps.
+AI_API_ENTRY int32_t yf_b200_fused_trace(ai_handle network, int32_t enable, int64_t* stamps, int32_t cap) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->d_trace && !cuda_ok(n, cudaMalloc(&n->d_trace, sizeof(long long) * 128), "cudaMalloc trace", AI_ERROR_ALLOCATION_FAILED)) return -1;
+  n->trace_on = enable != 0;
+  if (stamps && cap > 0) {
+    if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "synchronize")) return -1;
+    const int k = std::min<int>(cap, 128);
+    if (!cuda_ok(n, cudaMemcpy(stamps, n->d_trace, sizeof(long long) * k, cudaMemcpyDeviceToHost), "D2H trace")) return -1;
+    return k;
+  }
+  return 0;
+}
+
 AI_API_ENTRY int32_t yf_b200_set_step_profiling(ai_handle network, int32_t enable) {
   YF_NET_OR_FAIL(n, network)
   n->step_profiling = enable != 0;
@@ -886,7 +902,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
     kv("out_off", p.out_off); kv("out_cs", p.out_cs); kv("add_off", p.add_off); kv("add_cs", p.add_cs); kv("nk", p.nk); kv("npad", p.npad);
     kv("cout", p.cout); kv("chunks_out", p.chunks_out); kv("epi_base", p.epi_base); kv("has_lut", p.has_lut); kv("in_zp", p.in_zp);
     kv("to_global", p.to_global); kv("param_off", p.param_off); kv("param_bytes", p.param_bytes); kv("w_off", p.w_off); kv("lut_off", p.lut_off);
-    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("scratch_off", p.scratch_off);
+    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw);
     j += "\"add\":[" + std::to_string(p.add.enabled) + "," + std::to_string(p.add.zp1) + "," + std::to_string(p.add.zp2) + "," + std::to_string(p.add.zp_out) + "," +
          std::to_string(p.add.m1) + "," + std::to_string(p.add.m2) + "," + std::to_string(p.add.mo) + "," + std::to_string(p.add.s1) + "," +
          std::to_string(p.add.s2) + "," + std::to_string(p.add.so) + "]";

@@ -73,9 +73,17 @@ struct FusedArgs {
   int n_img, nphases;
   int in_off, in_bytes, slot_off, slot_bytes, head_bytes;
   int* err;
+  long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first image
 };
 
-constexpr int kFusedThreads = kFusedWarpgroups * 128;
+constexpr int kWorkers = kFusedWorkerThreads;            // 8 worker warps
+constexpr int kFusedThreads = kWorkers + 32;              // + 1 control warp (parameter prefetch, MMA issue)
+
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
+// UMMA smem descriptor: template low word (LBO) + start address; high word: SBO = 128 B, version 1, no swizzle
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
+  return (static_cast<uint64_t>(0x4008u) << 32) | static_cast<uint64_t>(lo_tmpl | ((saddr >> 4) & 0x3FFFu));
+}
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, uint32_t taddr, int row, int g,
@@ -126,28 +134,32 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
   }
 }
 
-// all (tile, chunk) units of a conv phase, split across the 8 warps
+// all (tile, chunk) units of a conv phase, split across the worker warps (no divisions)
 __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, uint32_t tmem_base,
                                               int warp, int lane, int8_t* ghead) {
-  const int ntiles = (ph.rows_out + 127) >> 7;
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, chunks = ph.chunks_out, ntiles = ph.ntiles;
   const uint8_t* lut = slot + ph.lut_off;
-  const int units = ntiles * ph.chunks_out;
-  for (int u = half; u < units; u += kFusedWarpgroups) {
-    const int t = u / ph.chunks_out, g = u - t * ph.chunks_out;
-    if (t * 128 + q * 32 >= ph.rows_out) continue;           // this warp's 32 rows are all padding
-    conv_unit(ph, smem, lut, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+  int t = 0, g = warp >> 2;
+  while (g >= chunks) { g -= chunks; ++t; }
+  while (t < ntiles) {
+    if (t * 128 + q * 32 < ph.rows_out)                      // else: this warp's 32 rows are all padding
+      conv_unit(ph, smem, lut, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+    g += kFusedWarpgroups;
+    while (g >= chunks) { g -= chunks; ++t; }
   }
 }
 
+// x / d for small x (x < 4096) with a host-free magic: exact for d <= 64
+__device__ __forceinline__ int small_div(int x, int d) { return static_cast<int>(__fdividef(static_cast<float>(x) + 0.5f, static_cast<float>(d))); }
+
 // DEPTHWISE_CONV_2D 3x3
 __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
-  const int nw = (ph.cout + 3) >> 2;                          // real 4-channel words
-  const int per = kFusedThreads / nw;                         // pixels advanced per iteration
+  const int nw = ph.nw, per = ph.per;
   if (tid >= per * nw) return;
-  const int wd = tid % nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
+  int pix = small_div(tid, nw);
+  const int wd = tid - pix * nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
   const uint32_t* w1h = reinterpret_cast<const uint32_t*>(slot + ph.dw_off);
-  const EpiCh* epi = reinterpret_cast<const EpiCh*>(slot + ph.dwepi_off);
+  const uint8_t* kb = slot + ph.dwepi_off + wd * 80;
   const uint8_t* lut = slot + ph.lut_off;
   uint32_t w[9][4];
 #pragma unroll
@@ -156,19 +168,23 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
     w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
   }
   long long k_add[4]; int32_t k_mult[4], k_c2p[4], k_e[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { const EpiCh k = epi[ch0 + j]; k_add[j] = k.add64; k_mult[j] = k.mult; k_c2p[j] = k.c2 + (128 << k.e); k_e[j] = k.e; }
-  const int Hin = ph.Hin, Win = ph.Win, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out;
-  const int row16 = Win * 16;
+  {
+    const longlong2 a01 = *reinterpret_cast<const longlong2*>(kb), a23 = *reinterpret_cast<const longlong2*>(kb + 16);
+    const int4 m = *reinterpret_cast<const int4*>(kb + 32), c = *reinterpret_cast<const int4*>(kb + 48), e = *reinterpret_cast<const int4*>(kb + 64);
+    k_add[0] = a01.x; k_add[1] = a01.y; k_add[2] = a23.x; k_add[3] = a23.y;
+    k_mult[0] = m.x; k_mult[1] = m.y; k_mult[2] = m.z; k_mult[3] = m.w;
+    k_c2p[0] = c.x; k_c2p[1] = c.y; k_c2p[2] = c.z; k_c2p[3] = c.w;
+    k_e[0] = e.x; k_e[1] = e.y; k_e[2] = e.z; k_e[3] = e.w;
+  }
+  const int Hin = ph.Hin, Win = ph.Win, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out, pad_t = ph.pad_t, pad_l = ph.pad_l;
+  const int row16 = Win * 16, dy = ph.dy, dx = ph.dx;
   const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4;
   uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
   const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
   const bool has_lut = ph.has_lut != 0;
-  int pix = tid / nw;
-  int oy = pix / Wout, ox = pix - oy * Wout;
-  const int dy = per / Wout, dx = per - dy * Wout;
+  int oy = small_div(pix, Wout), ox = pix - oy * Wout;
   for (; pix < rows; pix += per) {
-    const int iy0 = oy * stride - ph.pad_t, ix0 = ox * stride - ph.pad_l;
+    const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
     const uint8_t* p = ib + (iy0 * Win + ix0) * 16;
     uint32_t x[9];
     if (iy0 >= 0 && iy0 + 2 < Hin && ix0 >= 0 && ix0 + 2 < Win) {
@@ -205,22 +221,21 @@ __device__ __forceinline__ uint32_t unpack_even(uint32_t x) { return __byte_perm
 __device__ __forceinline__ uint32_t unpack_odd(uint32_t x) { return __byte_perm(x, 0u, 0xB391u); }
 __device__ __forceinline__ uint32_t repack(uint32_t ev, uint32_t od) { return __byte_perm(ev, od, 0x6240u); }
 
-// MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only
+// MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only (worker threads only)
 __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
-  const int nw = (ph.cout + 3) >> 2;
-  const int per = kFusedThreads / nw;
+  const int nw = ph.nw, per = ph.per;
   const bool active = tid < per * nw;
-  const int wd = tid % nw;
+  const int it0 = small_div(tid, nw), wd = tid - it0 * nw;
   const int Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout, k = ph.ksize, stride = ph.stride;
   const int scs = Hin * Wout * 16;                            // chunk stride of the row-maxima scratch
   const uint32_t neg = 0x80808080u;
+  const int dy = ph.dy, dx = ph.dx;
   if (active) {                                               // pass 1: horizontal window of every input row
     const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4;
     uint8_t* sb = smem + ph.scratch_off + (wd >> 2) * scs + (wd & 3) * 4;
     const int total = Hin * Wout;
-    int it = tid / nw;
-    int y = it / Wout, ox = it - y * Wout;
-    const int dy = per / Wout, dx = per - dy * Wout;
+    int it = it0;
+    int y = small_div(it, Wout), ox = it - y * Wout;
     for (; it < total; it += per) {
       const int x0 = max(0, ox * stride - ph.pad_l), x1 = min(Win, ox * stride - ph.pad_l + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
@@ -240,15 +255,14 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
       if (ox >= Wout) { ox -= Wout; ++y; }
     }
   }
-  __syncthreads();
+  workers_sync();
   if (active) {                                               // pass 2: vertical window over the row maxima
     const uint8_t* sb = smem + ph.scratch_off + (wd >> 2) * scs + (wd & 3) * 4;
     uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
     const uint8_t* lut = slot + ph.lut_off;
     const int total = Hout * Wout;
-    int it = tid / nw;
-    int oy = it / Wout, ox = it - oy * Wout;
-    const int dy = per / Wout, dx = per - dy * Wout;
+    int it = it0;
+    int oy = small_div(it, Wout), ox = it - oy * Wout;
     for (; it < total; it += per) {
       const int y0 = max(0, oy * stride - ph.pad_t), y1 = min(Hin, oy * stride - ph.pad_t + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
@@ -277,6 +291,32 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
   }
 }
 
+// first conv: every worker thread builds one A row (3 x 16-byte chunks) of tile 2r + (tid >> 7)
+__device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem, int tid, int r) {
+  const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
+  const int row_bytes = ph.Win * 3, rt = tid & 127, hf = tid >> 7;
+  const uint8_t* image = smem + ph.in_off;
+  uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
+  const int rr = (2 * r + hf) * 128 + rt;
+  if (rr >= ph.rows_out) return;
+  const int oy = small_div(rr, ph.Wout), ox = rr - oy * ph.Wout;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy - 1 + ky;
+    uint32_t a0 = zpw, a1 = zpw, a2 = zpw;
+    if (iy >= 0) {
+      const int o = iy * row_bytes + (2 * ox - 1) * 3;      // -3 for ox = 0: the image sits 16 B into smem
+      const int base = o & ~3;
+      const uint32_t sel = 0x3210u + 0x1111u * static_cast<uint32_t>(o & 3);
+      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(image + base), w1 = *reinterpret_cast<const uint32_t*>(image + base + 4);
+      const uint32_t w2 = *reinterpret_cast<const uint32_t*>(image + base + 8);
+      a0 = __byte_perm(w0, w1, sel); a1 = __byte_perm(w1, w2, sel); a2 = __byte_perm(w2, 0u, sel);
+      if (ox == 0) a0 = (a0 & 0xff000000u) | (zpw & 0x00ffffffu);
+    }
+    *reinterpret_cast<uint4*>(stage + ky * 2048 + rt * 16) = make_uint4(a0, a1, a2, 0u);
+  }
+}
+
 __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.slot_off + kFusedParamSlots * a.slot_bytes);
@@ -285,6 +325,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
   uint64_t* mma_done = bars + 1 + kFusedParamSlots;   // [2] accumulators ready (two used by the first conv's rounds)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + kFusedParamSlots);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_ctrl = warp == kWorkers / 32;
 
   if (tid == 0) {
     mbar_init(in_full, 1);
@@ -297,122 +338,130 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  uint32_t mma_uses[2] = {0u, 0u}, in_uses = 0u;
+  const uint32_t smem_base = smem_u32(smem);
+  uint32_t use0 = 0u, use1 = 0u, in_uses = 0u;              // completed waits on mma_done[0/1], in_full
   bool ok = true;
-  uint8_t* img_smem = smem + a.in_off;
+  const int nph = a.nphases;
   const int my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const uint32_t total_pc = static_cast<uint32_t>(my_images) * static_cast<uint32_t>(a.nphases);
-
-  auto load_params = [&](uint32_t pcx) {                    // thread 0 only
-    const FusedPhase& nx = c_fphase[pcx % static_cast<uint32_t>(a.nphases)];
-    uint64_t* bar = &par_full[pcx % kFusedParamSlots];
-    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
-    bulk_load_1d(smem + a.slot_off + (pcx % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
+  const uint32_t total_pc = static_cast<uint32_t>(my_images) * static_cast<uint32_t>(nph);
+  auto wait_bar = [&](uint64_t* bar, uint32_t parity, int code) {
+    if (ok && !mbar_wait(bar, parity)) { atomicCAS(a.err, 0, code); ok = false; }
   };
-  if (tid == 0 && my_images > 0) {
-    mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(img_smem, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
-    for (uint32_t i = 0; i + 1 < kFusedParamSlots && i < total_pc; ++i) load_params(i);
-  }
 
-  uint32_t pc = 0;
-  for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
-    int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
-    for (int p = 0; p < a.nphases; ++p, ++pc) {
-      const FusedPhase& ph = c_fphase[p];
-      if (tid == 0 && pc + kFusedParamSlots - 1 < total_pc) load_params(pc + kFusedParamSlots - 1);
-      if (ok && !mbar_wait(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1)) { atomicCAS(a.err, 0, 302); ok = false; }
-      const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
-
-      if (ph.kind == STEP_CONV1X1) {
-        if (tid == 0) {                                       // every tile of the layer, one commit
-          tc_fence_after();
-          const int ntiles = (ph.rows_out + 127) >> 7;
-          const uint32_t sA = smem_u32(smem + ph.in_off), sW = smem_u32(slot + ph.w_off);
-          const uint32_t idesc = umma_idesc_s8(128, ph.npad);
-          for (int t = 0; t < ntiles; ++t)
-            for (int k = 0; k < ph.nk; ++k)
-              mma_i8(tmem_base + t * ph.npad, umma_smem_desc(sA + t * 2048 + k * 2 * ph.in_cs, ph.in_cs, 128, 0),
-                     umma_smem_desc(sW + k * 2 * ph.npad * 16, ph.npad * 16, 128, 0), idesc, k > 0 ? 1u : 0u);
-          mma_commit(&mma_done[0]);
-        }
-        if (ok && !mbar_wait(&mma_done[0], mma_uses[0] & 1)) { atomicCAS(a.err, 0, 301); ok = false; }
-        ++mma_uses[0];
-        tc_fence_after();
-        conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
-        tc_fence_before();
-      } else if (ph.kind == STEP_CONV_IM2COL) {
-        if (p == 0) {
-          if (ok && !mbar_wait(in_full, in_uses & 1)) { atomicCAS(a.err, 0, 303); ok = false; }
-          ++in_uses;
-        }
-        // rounds of two 128-pixel tiles; round r uses A stages (2r, 2r+1) mod 4 and barrier r & 1
-        const int ntiles = (ph.rows_out + 127) >> 7, rounds = (ntiles + 1) >> 1;
-        const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
-        const int row_bytes = ph.Win * 3, rt = tid & 127, hf = tid >> 7;
-        const uint8_t* image = smem + ph.in_off;
-        const uint32_t sW = smem_u32(slot + ph.w_off);
-        const uint32_t idesc = umma_idesc_s8(128, ph.npad);
-        for (int r = 0; r < rounds; ++r) {
-          if (r >= 2) {                                       // stages of round r-2 must have been consumed
-            if (ok && !mbar_wait(&mma_done[r & 1], mma_uses[r & 1] & 1)) { atomicCAS(a.err, 0, 304); ok = false; }
-            ++mma_uses[r & 1];
-          }
-          const int t = 2 * r + hf;
-          uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
-          const int rr = t * 128 + rt;
-          if (rr < ph.rows_out) {
-            const int oy = rr / ph.Wout, ox = rr - oy * ph.Wout;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const int iy = 2 * oy - 1 + ky;
-              uint32_t a0 = zpw, a1 = zpw, a2 = zpw;
-              if (iy >= 0) {
-                const int o = iy * row_bytes + (2 * ox - 1) * 3;      // -3 for ox = 0: the image sits 16 B into smem
-                const int base = o & ~3;
-                const uint32_t sel = 0x3210u + 0x1111u * static_cast<uint32_t>(o & 3);
-                const uint32_t w0 = *reinterpret_cast<const uint32_t*>(image + base), w1 = *reinterpret_cast<const uint32_t*>(image + base + 4);
-                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(image + base + 8);
-                a0 = __byte_perm(w0, w1, sel); a1 = __byte_perm(w1, w2, sel); a2 = __byte_perm(w2, 0u, sel);
-                if (ox == 0) a0 = (a0 & 0xff000000u) | (zpw & 0x00ffffffu);
-              }
-              *reinterpret_cast<uint4*>(stage + ky * 2048 + rt * 16) = make_uint4(a0, a1, a2, 0u);
-            }
-          }
-          fence_proxy_async_smem();
-          __syncthreads();
-          if (tid == 0) {
+  if (is_ctrl) {
+    // ================= control warp: parameter / image prefetch and every tcgen05.mma =================
+    const bool lead = lane == 0;
+    int pnext = 0;                                            // phase index of parameter block pc_next
+    uint32_t pc_next = 0;
+    auto load_params = [&]() {                                // issue the bulk copy of block pc_next
+      const FusedPhase& nx = c_fphase[pnext];
+      uint64_t* bar = &par_full[pc_next % kFusedParamSlots];
+      mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
+      bulk_load_1d(smem + a.slot_off + (pc_next % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
+      ++pc_next; if (++pnext == nph) pnext = 0;
+    };
+    if (lead && my_images > 0) {
+      mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
+      bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+      while (pc_next + 1 < kFusedParamSlots && pc_next < total_pc) load_params();
+      wait_bar(&par_full[0], 0, 311);                         // weights of the very first phase
+    }
+    uint32_t pc = 0;
+    for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
+      for (int p = 0; p < nph; ++p, ++pc) {
+        const FusedPhase& ph = c_fphase[p];
+        const uint32_t sW = smem_base + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes + ph.w_off;
+        if (ph.kind == STEP_CONV1X1) {
+          if (lead) {                                         // all tiles of the layer, one commit (weights already waited for)
             tc_fence_after();
-            for (int h = 0; h < 2; ++h) {
-              const int tt = 2 * r + h;
-              if (tt >= ntiles) break;
-              const uint32_t sS = smem_u32(smem + ph.scratch_off + ((2 * r + h) & 3) * 6144);
-              for (int k = 0; k < 2; ++k)
-                mma_i8(tmem_base + tt * ph.npad, umma_smem_desc(sS + k * 4096, 2048, 128, 0),
-                       umma_smem_desc(sW + k * 2 * ph.npad * 16, ph.npad * 16, 128, 0), idesc, k > 0 ? 1u : 0u);
+            const uint32_t sA = smem_base + ph.in_off;
+            for (int t = 0; t < ph.ntiles; ++t)
+              for (int k = 0; k < ph.nk; ++k)
+                mma_i8(tmem_base + t * ph.npad, mk_desc(ph.adesc_lo, sA + t * 2048 + k * 2 * ph.in_cs),
+                       mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16), static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
+            mma_commit(&mma_done[0]);
+          }
+        } else if (ph.kind == STEP_CONV_IM2COL) {
+          const int rounds = (ph.ntiles + 1) >> 1;
+          for (int r = 0; r < rounds; ++r) {
+            __syncthreads();                                  // workers finished building round r
+            if (lead) {
+              tc_fence_after();
+              for (int h = 0; h < 2; ++h) {
+                const int tt = 2 * r + h;
+                if (tt >= ph.ntiles) break;
+                const uint32_t sS = smem_base + ph.scratch_off + ((2 * r + h) & 3) * 6144;
+                for (int k = 0; k < 2; ++k)
+                  mma_i8(tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
+                         static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
+              }
+              mma_commit(&mma_done[r & 1]);
             }
-            mma_commit(&mma_done[r & 1]);
           }
         }
-        for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
-          if (ok && !mbar_wait(&mma_done[r & 1], mma_uses[r & 1] & 1)) { atomicCAS(a.err, 0, 305); ok = false; }
-          ++mma_uses[r & 1];
+        if (lead) {
+          if (pc_next < total_pc) load_params();              // keep kFusedParamSlots - 1 blocks in flight
+          if (p == 1 && img + static_cast<int>(gridDim.x) < a.n_img) {   // image buffer is free after phase 0
+            mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
+            bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+          }
+          if (pc + 1 < total_pc)                              // next phase's weights, off the critical path
+            wait_bar(&par_full[(pc + 1) % kFusedParamSlots], ((pc + 1) / kFusedParamSlots) & 1, 312);
         }
-        tc_fence_after();
-        conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
-        tc_fence_before();
-      } else if (ph.kind == STEP_DW) {
-        dw_phase(ph, smem, slot, tid);
-      } else if (ph.kind == STEP_MAXPOOL) {
-        pool_phase(ph, smem, slot, tid);
-      }
-      fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
-      __syncthreads();
-      if (p == 0 && tid == 0 && img + static_cast<int>(gridDim.x) < a.n_img) {   // image buffer free: prefetch the next one
-        mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-        bulk_load_1d(img_smem, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+        __syncthreads();                                      // end of phase p
       }
     }
+  } else {
+    // ================= worker warps =================
+    uint32_t pc = 0;
+    for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
+      int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
+      for (int p = 0; p < nph; ++p, ++pc) {
+        const FusedPhase& ph = c_fphase[p];
+        const bool tr = a.trace && tid == 0 && blockIdx.x == 0 && pc < 2u * static_cast<uint32_t>(nph);
+        long long* sub = (tr && p == 14) ? a.trace + 80 + 8 * (pc / nph) : nullptr;
+        if (tr) a.trace[pc + pc / nph] = clock64();
+        if (sub) sub[0] = clock64();
+        wait_bar(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1, 302);
+        const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
+        if (sub) sub[1] = clock64();
+        if (ph.kind == STEP_CONV1X1) {
+          if (sub) sub[2] = clock64();
+          wait_bar(&mma_done[0], use0 & 1, 301); ++use0;
+          tc_fence_after();
+          if (sub) sub[3] = clock64();
+          conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
+          tc_fence_before();
+          if (sub) sub[4] = clock64();
+        } else if (ph.kind == STEP_CONV_IM2COL) {
+          wait_bar(in_full, in_uses & 1, 303); ++in_uses;
+          const int rounds = (ph.ntiles + 1) >> 1;
+          for (int r = 0; r < rounds; ++r) {
+            if (r >= 2) {                                     // the A stages of round r-2 must have been consumed
+              if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 304); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 304); ++use0; }
+            }
+            im2col_build(ph, smem, tid, r);
+            fence_proxy_async_smem();
+            __syncthreads();                                  // control issues round r
+          }
+          for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
+            if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 305); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 305); ++use0; }
+          }
+          tc_fence_after();
+          conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
+          tc_fence_before();
+        } else if (ph.kind == STEP_DW) {
+          dw_phase(ph, smem, slot, tid);
+        } else if (ph.kind == STEP_MAXPOOL) {
+          pool_phase(ph, smem, slot, tid);
+        }
+        fence_proxy_async_smem();          // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
+        if (sub) sub[5] = clock64();
+        __syncthreads();
+        if (sub) sub[6] = clock64();
+      }
+    }
+    if (a.trace && tid == 0 && blockIdx.x == 0) a.trace[(my_images >= 2 ? 2 : 1) * (nph + 1) - 1] = clock64();
   }
   tc_fence_before();
   __syncthreads();
@@ -424,12 +473,12 @@ cudaError_t fused_init(int smem_bytes) {
 }
 
 cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
-                         int sm_count, int* d_err, cudaStream_t s) {
+                         int sm_count, int* d_err, cudaStream_t s, long long* d_trace) {
   if (n_img <= 0) return cudaSuccess;
   FusedArgs a{};
   a.in = d_in; a.out = d_out; a.params = d_params; a.n_img = n_img; a.nphases = static_cast<int>(F.phases.size());
   a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes;
-  a.head_bytes = F.head_bytes; a.err = d_err;
+  a.head_bytes = F.head_bytes; a.err = d_err; a.trace = d_trace;
   const int per_sm = F.smem_bytes <= 113 * 1024 ? 2 : 1;
   const int grid = n_img < sm_count * per_sm ? n_img : sm_count * per_sm;
   yoloface_fused_kernel<<<grid, kFusedThreads, F.smem_bytes, s>>>(a);

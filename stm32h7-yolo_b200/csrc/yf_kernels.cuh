@@ -89,6 +89,6 @@ cudaError_t kernels_init();              // opt-in dynamic smem sizes
 cudaError_t upload_fused_tables(const EpiCh* epi, int n, const FusedPhase* phases, int nph, cudaStream_t s);
 cudaError_t fused_init(int smem_bytes);
 cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
-                         int sm_count, int* d_err, cudaStream_t s);
+                         int sm_count, int* d_err, cudaStream_t s, long long* d_trace = nullptr);
 
 }  // namespace yf

@@ -618,7 +618,14 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     if (s.add.enabled) { ph.add = s.add; ph.add_cs = ph.rows_out * 16; ph.add_off = F->arena_off + off[s.add_buf] + (s.add_coff / 16) * ph.add_cs; }
     ph.cout = s.Cout; ph.chunks_out = (s.Cout + 15) / 16; ph.epi_base = s.epi_base; ph.has_lut = s.lut_fused >= 0;
     ph.npad = s.Npad;
-    // block: [weights][table][depthwise EpiCh]
+    ph.ntiles = (ph.rows_out + 127) / 128;
+    ph.nw = (s.Cout + 3) / 4;
+    ph.per = kFusedWorkerThreads / ph.nw;
+    ph.dy = ph.per / ph.Wout; ph.dx = ph.per % ph.Wout; ph.dy1 = ph.dy; ph.dx1 = ph.dx;
+    ph.idesc = static_cast<int32_t>((2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(s.Npad >> 3) << 17) | (8u << 24));
+    ph.adesc_lo = static_cast<uint32_t>(((s.kind == STEP_CONV_IM2COL ? 2048 : ph.in_cs) >> 4) & 0x3FFF) << 16;
+    ph.bdesc_lo = static_cast<uint32_t>(((s.Npad * 16) >> 4) & 0x3FFF) << 16;
+    // block: [weights][table][depthwise constants]
     std::vector<uint8_t> blk;
     auto put = [&](const void* src, size_t n) { size_t o = blk.size(); blk.resize((o + n + 15) & ~size_t(15), 0); std::memcpy(blk.data() + o, src, n); return static_cast<int>(o); };
     if (s.kind == STEP_CONV1X1) {
@@ -638,9 +645,16 @@ bool build_fused(const Plan& P, FusedProgram* F) {
       ph.w_off = put(w64.data(), w64.size());
     } else if (s.kind == STEP_DW) {
       ph.dw_off = put(P.wblob.data() + s.w_off, s.w_bytes);             // [9][CP] one-hot words
-      std::vector<EpiCh> e(static_cast<size_t>(ph.chunks_out) * 16, EpiCh{});
-      for (int c = 0; c < s.Cout; ++c) e[c] = P.epi[s.epi_base + c];
-      ph.dwepi_off = put(e.data(), e.size() * sizeof(EpiCh));
+      // per 4-channel word: {add64 x4 | mult x4 | c2p x4 | e x4} = 80 bytes, c2p = c2 + (128 << e)
+      std::vector<uint8_t> e(static_cast<size_t>(ph.nw) * 80, 0);
+      for (int c = 0; c < s.Cout; ++c) {
+        const EpiCh& k = P.epi[s.epi_base + c];
+        uint8_t* b = e.data() + static_cast<size_t>(c / 4) * 80; const int j = c % 4;
+        const int32_t c2p = k.c2 + (128 << k.e);
+        std::memcpy(b + 8 * j, &k.add64, 8); std::memcpy(b + 32 + 4 * j, &k.mult, 4);
+        std::memcpy(b + 48 + 4 * j, &c2p, 4); std::memcpy(b + 64 + 4 * j, &k.e, 4);
+      }
+      ph.dwepi_off = put(e.data(), e.size());
     }
     if (ph.has_lut) ph.lut_off = put(P.luts.data() + static_cast<size_t>(s.lut_fused) * 256, 256);
     if (blk.empty()) blk.resize(16, 0);

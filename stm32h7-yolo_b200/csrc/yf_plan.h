@@ -164,7 +164,13 @@ struct alignas(16) FusedPhase {
   int32_t w_off, lut_off, dw_off, dwepi_off;   // offsets inside the block (bytes)
   AddParams add;
   int32_t scratch_off;          // smem scratch: im2col A stages (4 x 6 KB) / separable max-pool row maxima
-  int32_t pad_[1];
+  // loop constants precomputed on the host (no integer division on the device)
+  int32_t ntiles;               // conv: 128-pixel tiles
+  int32_t nw, per, dy, dx;      // depthwise / pool pass 2: real 4-channel words, pixels per sweep, (per / Wout, per % Wout)
+  int32_t dy1, dx1;             // pool pass 1 (row maxima): per / Wout, per % Wout (same Wout) -- kept separate for clarity
+  int32_t idesc;                // UMMA instruction descriptor (M=128, N=npad, s8 x s8 -> s32)
+  uint32_t adesc_lo, bdesc_lo;  // UMMA smem descriptor low words without the start address: LBO >> 4 << 16
+  int32_t pad_[2];
 };
 
 struct FusedProgram {
@@ -180,7 +186,8 @@ struct FusedProgram {
   int head_bytes = 0;           // bytes per image of the dense head
 };
 constexpr int kFusedMaxPhases = 32;
-constexpr int kFusedWarpgroups = 2;
+constexpr int kFusedWarpgroups = 2;   // worker warps = 4 * kFusedWarpgroups, plus one control warp
+constexpr int kFusedWorkerThreads = kFusedWarpgroups * 128;
 constexpr int kFusedParamSlots = 4;
 constexpr int kFusedTmemCols = 256;     // all accumulator tiles of one conv phase live in TMEM at once
 bool build_fused(const Plan& plan, FusedProgram* prog);

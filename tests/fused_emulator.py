@@ -60,7 +60,14 @@ def run_fused(F, img, seed=0):
             w = np.zeros((9, cp), np.int64)
             for c in range(cp):
                 w[:, c] = ((w1h[:, c] >> (8 * (c % 4))) & 0xFF).astype(np.uint8).view(np.int8)
-            epi = slot[ph["dwepi_off"]:ph["dwepi_off"] + cp * 32].view(epi_all.dtype)[:cout]
+            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + ph["nw"] * 80].reshape(ph["nw"], 80)
+            epi = np.zeros(ph["nw"] * 4, epi_all.dtype)
+            epi["add64"] = raw[:, 0:32].copy().view("<i8").reshape(-1)
+            epi["mult"] = raw[:, 32:48].copy().view("<i4").reshape(-1)
+            epi["e"] = raw[:, 64:80].copy().view("<i4").reshape(-1)
+            epi["c2"] = raw[:, 48:64].copy().view("<i4").reshape(-1) - (128 << epi["e"])
+            epi["sgn_mask"] = -1
+            epi = epi[:cout]
             H, W, Ho, Wo, st = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"]
             x = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, H * W) for c in range(chunks)], axis=1).reshape(H, W, cp).astype(np.int64)
             xp = np.full((H + 2 + st, W + 2 + st, cp), ph["in_zp"], np.int64)
