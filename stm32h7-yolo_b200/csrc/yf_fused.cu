@@ -17,6 +17,8 @@
 //   depthwise     CUDA cores: one thread = one 4-channel word, fixed per thread (weights and
 //                 requant constants in registers), dp4a against one-hot words, interior fast path
 //   max-pool      separable (row maxima to scratch, then columns), VIMNMX3.S16x2 on unpacked lanes
+#include <cstdlib>
+
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
 
@@ -71,10 +73,16 @@ __device__ __noinline__ uint32_t add_word(uint32_t skipw, uint32_t yw, const Add
 struct FusedArgs {
   const int8_t* in; int8_t* out; const uint8_t* params;
   int n_img, nphases;
-  int in_off, in_bytes, slot_off, slot_bytes, head_bytes;
+  int in_off, in_bytes, slot_off, slot_bytes, head_bytes, desc_off;
   int* err;
   long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first image
+  int trace_phase;            // phase whose inner stamps (trace[96..127]) are recorded
 };
+#ifdef YF_TRACE
+#define YF_STAMP(tp, i) do { if (tp) (tp)[i] = clock64(); } while (0)
+#else
+#define YF_STAMP(tp, i) do { } while (0)
+#endif
 
 constexpr int kWorkers = kFusedWorkerThreads;            // 8 worker warps
 constexpr int kFusedThreads = kWorkers + 32;              // + 1 control warp (parameter prefetch, MMA issue)
@@ -86,14 +94,14 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
 }
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
-__device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, uint32_t taddr, int row, int g,
-                                          int8_t* ghead) {
+__device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
+                                          int row, int g, int8_t* ghead) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   tmem_ld_wait();
   if (row >= ph.rows_out) return;
   const int nreal = ph.cout - g * 16;                        // real channels in this chunk (> 0)
-  const EpiChF* ek = &c_epif[ph.epi_base + g * 16];
+  const EpiChF* ek = epi + g * 16;                           // shared memory (broadcast reads)
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (ph.has_lut) {
 #pragma unroll
@@ -139,11 +147,12 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* sme
                                               int warp, int lane, int8_t* ghead) {
   const int q = warp & 3, chunks = ph.chunks_out, ntiles = ph.ntiles;
   const uint8_t* lut = slot + ph.lut_off;
+  const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
   int t = 0, g = warp >> 2;
   while (g >= chunks) { g -= chunks; ++t; }
   while (t < ntiles) {
     if (t * 128 + q * 32 < ph.rows_out)                      // else: this warp's 32 rows are all padding
-      conv_unit(ph, smem, lut, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+      conv_unit(ph, smem, lut, epi, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
     g += kFusedWarpgroups;
     while (g >= chunks) { g -= chunks; ++t; }
   }
@@ -153,8 +162,9 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* sme
 __device__ __forceinline__ int small_div(int x, int d) { return static_cast<int>(__fdividef(static_cast<float>(x) + 0.5f, static_cast<float>(d))); }
 
 // DEPTHWISE_CONV_2D 3x3
-__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
+__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, long long* tp) {
   const int nw = ph.nw, per = ph.per;
+  YF_STAMP(tp, 0);
   if (tid >= per * nw) return;
   int pix = small_div(tid, nw);
   const int wd = tid - pix * nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
@@ -183,10 +193,13 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
   const bool has_lut = ph.has_lut != 0;
   int oy = small_div(pix, Wout), ox = pix - oy * Wout;
+  YF_STAMP(tp, 1);
+
   for (; pix < rows; pix += per) {
     const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
     const uint8_t* p = ib + (iy0 * Win + ix0) * 16;
     uint32_t x[9];
+
     if (iy0 >= 0 && iy0 + 2 < Hin && ix0 >= 0 && ix0 + 2 < Win) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
@@ -214,6 +227,7 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
     ox += dx; oy += dy;
     if (ox >= Wout) { ox -= Wout; ++oy; }
   }
+  YF_STAMP(tp, 8);
 }
 
 // signed bytes (b0,b2) / (b1,b3) of a word as two 16-bit lanes each
@@ -319,7 +333,7 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
 
 __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.slot_off + kFusedParamSlots * a.slot_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127));
   uint64_t* in_full = bars;                 // input image landed
   uint64_t* par_full = bars + 1;            // [kFusedParamSlots] parameter slot landed
   uint64_t* mma_done = bars + 1 + kFusedParamSlots;   // [2] accumulators ready (two used by the first conv's rounds)
@@ -337,6 +351,13 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  {                                                           // phase descriptors: __constant__ -> smem, read with LDS from here on
+    const uint4* src = reinterpret_cast<const uint4*>(c_fphase);
+    uint4* dst = reinterpret_cast<uint4*>(smem + a.desc_off);
+    for (int i = tid; i < a.nphases * static_cast<int>(sizeof(FusedPhase) / 16); i += kFusedThreads) dst[i] = src[i];
+    __syncthreads();
+  }
+  const FusedPhase* s_ph = reinterpret_cast<const FusedPhase*>(smem + a.desc_off);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_base = smem_u32(smem);
   uint32_t use0 = 0u, use1 = 0u, in_uses = 0u;              // completed waits on mma_done[0/1], in_full
@@ -354,7 +375,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
     int pnext = 0;                                            // phase index of parameter block pc_next
     uint32_t pc_next = 0;
     auto load_params = [&]() {                                // issue the bulk copy of block pc_next
-      const FusedPhase& nx = c_fphase[pnext];
+      const FusedPhase& nx = s_ph[pnext];
       uint64_t* bar = &par_full[pc_next % kFusedParamSlots];
       mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
       bulk_load_1d(smem + a.slot_off + (pc_next % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
     uint32_t pc = 0;
     for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
       for (int p = 0; p < nph; ++p, ++pc) {
-        const FusedPhase& ph = c_fphase[p];
+        const FusedPhase& ph = s_ph[p];
         const uint32_t sW = smem_base + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes + ph.w_off;
         if (ph.kind == STEP_CONV1X1) {
           if (lead) {                                         // all tiles of the layer, one commit (weights already waited for)
@@ -417,10 +438,14 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
     for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
       int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
       for (int p = 0; p < nph; ++p, ++pc) {
-        const FusedPhase& ph = c_fphase[p];
+        const FusedPhase& ph = s_ph[p];
+#ifdef YF_TRACE
         const bool tr = a.trace && tid == 0 && blockIdx.x == 0 && pc < 2u * static_cast<uint32_t>(nph);
         long long* sub = (tr && p == 14) ? a.trace + 80 + 8 * (pc / nph) : nullptr;
         if (tr) a.trace[pc + pc / nph] = clock64();
+#else
+        constexpr bool tr = false; long long* const sub = nullptr;
+#endif
         if (sub) sub[0] = clock64();
         wait_bar(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1, 302);
         const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
@@ -451,17 +476,22 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
           conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
           tc_fence_before();
         } else if (ph.kind == STEP_DW) {
-          dw_phase(ph, smem, slot, tid);
+          dw_phase(ph, smem, slot, tid, (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) ? a.trace + 96 : nullptr);
+          if (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) a.trace[96 + 9] = clock64();
         } else if (ph.kind == STEP_MAXPOOL) {
           pool_phase(ph, smem, slot, tid);
         }
         fence_proxy_async_smem();          // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
         if (sub) sub[5] = clock64();
+        if (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) a.trace[96 + 10] = clock64();
         __syncthreads();
+        if (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) a.trace[96 + 11] = clock64();
         if (sub) sub[6] = clock64();
       }
     }
+#ifdef YF_TRACE
     if (a.trace && tid == 0 && blockIdx.x == 0) a.trace[(my_images >= 2 ? 2 : 1) * (nph + 1) - 1] = clock64();
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -477,8 +507,9 @@ cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_ou
   if (n_img <= 0) return cudaSuccess;
   FusedArgs a{};
   a.in = d_in; a.out = d_out; a.params = d_params; a.n_img = n_img; a.nphases = static_cast<int>(F.phases.size());
-  a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes;
+  a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes; a.desc_off = F.desc_off;
   a.head_bytes = F.head_bytes; a.err = d_err; a.trace = d_trace;
+  { const char* e = getenv("YF_B200_TRACE_PHASE"); a.trace_phase = e ? atoi(e) : 1; }
   const int per_sm = F.smem_bytes <= 113 * 1024 ? 2 : 1;
   const int grid = n_img < sm_count * per_sm ? n_img : sm_count * per_sm;
   yoloface_fused_kernel<<<grid, kFusedThreads, F.smem_bytes, s>>>(a);

@@ -628,9 +628,19 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     // block: [weights][table][depthwise constants]
     std::vector<uint8_t> blk;
     auto put = [&](const void* src, size_t n) { size_t o = blk.size(); blk.resize((o + n + 15) & ~size_t(15), 0); std::memcpy(blk.data() + o, src, n); return static_cast<int>(o); };
+    auto put_epi = [&]() {     // {add64, mult, c2p = c2 + (128 << e), e, pad} per output channel, padded to whole chunks
+      std::vector<uint8_t> e(static_cast<size_t>(ph.chunks_out) * 16 * 32, 0);
+      for (int c = 0; c < s.Cout; ++c) {
+        const EpiCh& k = P.epi[s.epi_base + c]; uint8_t* b = e.data() + static_cast<size_t>(c) * 32;
+        const int32_t c2p = k.c2 + (128 << k.e);
+        std::memcpy(b, &k.add64, 8); std::memcpy(b + 8, &k.mult, 4); std::memcpy(b + 12, &c2p, 4); std::memcpy(b + 16, &k.e, 4);
+      }
+      return put(e.data(), e.size());
+    };
     if (s.kind == STEP_CONV1X1) {
       ph.nk = s.Kpad / 32;
       ph.w_off = put(P.wblob.data() + s.w_off, s.w_bytes);
+      ph.epi_off = put_epi();
     } else if (s.kind == STEP_CONV_IM2COL) {
       // K = 64 layout for the fused builder: chunk ky holds the 9 bytes (kx, c) of input row ky,
       // bytes 9..15 and chunk 3 carry zero weights (the A bytes there are don't-care)
@@ -643,6 +653,7 @@ bool build_fused(const Plan& P, FusedProgram* F) {
         w64[(static_cast<size_t>(ky) * s.Npad + o) * 16 + j] = static_cast<uint8_t>(w32[(static_cast<size_t>(k / 16) * s.Npad + o) * 16 + k % 16]);
       }
       ph.w_off = put(w64.data(), w64.size());
+      ph.epi_off = put_epi();
     } else if (s.kind == STEP_DW) {
       ph.dw_off = put(P.wblob.data() + s.w_off, s.w_bytes);             // [9][CP] one-hot words
       // per 4-channel word: {add64 x4 | mult x4 | c2p x4 | e x4} = 80 bytes, c2p = c2 + (128 << e)
@@ -664,7 +675,8 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     F->phases.push_back(ph);
   }
   F->slot_bytes = (slot + 127) & ~127;
-  F->smem_bytes = F->slot_off + kFusedParamSlots * F->slot_bytes + 256;
+  F->desc_off = F->slot_off + kFusedParamSlots * F->slot_bytes;
+  F->smem_bytes = F->desc_off + ((static_cast<int>(F->phases.size() * sizeof(FusedPhase)) + 127) & ~127) + 256;
   F->head_bytes = P.GH * P.GW * 18;
   if (F->smem_bytes > 200 * 1024) return no("activations do not fit shared memory (" + std::to_string(F->smem_bytes) + " bytes)");
   F->ok = true;

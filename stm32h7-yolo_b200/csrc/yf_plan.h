@@ -162,6 +162,7 @@ struct alignas(16) FusedPhase {
   int32_t to_global;            // 1: last conv writes the dense int8 head to global memory
   int32_t param_off, param_bytes;       // this phase's block inside the parameter blob
   int32_t w_off, lut_off, dw_off, dwepi_off;   // offsets inside the block (bytes)
+  int32_t epi_off;              // conv: per-channel requant constants (32 B each) inside the block
   AddParams add;
   int32_t scratch_off;          // smem scratch: im2col A stages (4 x 6 KB) / separable max-pool row maxima
   // loop constants precomputed on the host (no integer division on the device)
@@ -170,8 +171,9 @@ struct alignas(16) FusedPhase {
   int32_t dy1, dx1;             // pool pass 1 (row maxima): per / Wout, per % Wout (same Wout) -- kept separate for clarity
   int32_t idesc;                // UMMA instruction descriptor (M=128, N=npad, s8 x s8 -> s32)
   uint32_t adesc_lo, bdesc_lo;  // UMMA smem descriptor low words without the start address: LBO >> 4 << 16
-  int32_t pad_[2];
+  int32_t pad_[1];
 };
+static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied to shared memory with 16-byte loads");
 
 struct FusedProgram {
   bool ok = false;              // false: this resolution/model cannot run fused (use the layered path)
@@ -182,6 +184,7 @@ struct FusedProgram {
   int in_bytes = 0;
   int arena_off = 0, arena_bytes = 0;
   int slot_off = 0, slot_bytes = 0;     // smem: kFusedParamSlots parameter slots
+  int desc_off = 0;                     // smem: copy of the phase descriptors
   int smem_bytes = 0;
   int head_bytes = 0;           // bytes per image of the dense head
 };

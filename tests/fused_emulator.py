@@ -46,7 +46,13 @@ def run_fused(F, img, seed=0):
                     for ky in range(3):
                         A[r, ky * 16:ky * 16 + 9] = flat[2 * oy + ky, (2 * ox) * 3:(2 * ox) * 3 + 9]
             acc = A @ wmat
-            epi = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
+            raw = slot[ph["epi_off"]:ph["epi_off"] + cout * 32].reshape(cout, 32)      # constants travel in the block
+            epi = np.zeros(cout, epi_all.dtype)
+            epi["add64"] = raw[:, 0:8].copy().view("<i8").reshape(-1); epi["mult"] = raw[:, 8:12].copy().view("<i4").reshape(-1)
+            epi["e"] = raw[:, 16:20].copy().view("<i4").reshape(-1)
+            epi["c2"] = raw[:, 12:16].copy().view("<i4").reshape(-1) - (128 << epi["e"]); epi["sgn_mask"] = -1
+            ref = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
+            assert all(np.array_equal(epi[f], ref[f]) for f in ("add64", "mult", "e", "c2"))
             y = np.clip(requant(acc[:, :cout], epi), -128, 127)
             if ph["add_off"] >= 0:
                 _, zp1, zp2, zpo, m1, m2, mo, s1, s2, so = ph["add"]

@@ -34,4 +34,8 @@ for im in range(2 if n > 296 else 1):
         print("  %-14s kind %d rows %4d cout %2d  %7d cyc  %5.1f%%" % (s["name"], s["kind"], F["phases"][i]["rows_out"], F["phases"][i]["cout"], d, 100.0 * d / tot))
     sub = st[80 + 8 * im:80 + 8 * im + 7]
     print("  phase 14 sub-stamps: param wait %d | mma issue %d | mma wait %d | epilogue %d | fence %d | barrier %d" % tuple(sub[i + 1] - sub[i] for i in range(6)))
+inner = st[96:108]
+print("inner stamps of phase %s (thread 0): entry->setup %d | setup->iter0 %d | iters %s | loop end->ret %s | fence %d | barrier %d" % (
+    os.environ.get("YF_B200_TRACE_PHASE", "1"), inner[1] - inner[0], inner[2] - inner[1], [inner[i + 1] - inner[i] for i in range(2, 7)],
+    inner[9] - inner[8], inner[10] - inner[9], inner[11] - inner[10]))
 net.close()
