@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
                              "sample": "each step = one 256-image batch through the C oracle on %d host threads" % cores},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, local_rank, world):
@@ -208,22 +208,37 @@ def run_ours(args, rank, local_rank, world):
     h_in = [torch.empty((BATCH, 56, 56, 3), dtype=torch.int8).pin_memory() for _ in range(RING)]
     for i, t in enumerate(h_in):
         t.copy_(d_in[i])
-    h_out = torch.empty((BATCH, 7, 7, 18), dtype=torch.int8).pin_memory()
+    h_out = [torch.empty((BATCH, 7, 7, 18), dtype=torch.int8).pin_memory() for _ in range(4)]
     for k in range(max(args.warmup, 3)):
-        net.run(h_in[k % RING], h_out, n=BATCH)
+        net.run(h_in[k % RING], h_out[0], n=BATCH)
+    # (a) blocking call per step: H2D + kernel(s) + D2H, returns when the heads are in host memory
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        net.run(h_in[k % RING], h_out, n=BATCH)          # H2D + 26 kernels + D2H, blocking
+        net.run(h_in[k % RING], h_out[0], n=BATCH)
     torch.cuda.synchronize()
+    dt_block = max_over_ranks(time.perf_counter() - t0)
+    # (b) the pipelined API: every step still copies its own inputs in and its own heads out, but the copy of
+    #     step k+1 overlaps the kernels of step k (three streams, ring of staging slots)
+    for k in range(3):
+        net.submit(h_in[k % RING], h_out[k % 4], BATCH)
+    net.wait()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        net.submit(h_in[k % RING], h_out[k % 4], BATCH)
+    net.wait()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e = {"value": world * BATCH * args.steps / dt, "unit": "images/s", "h2d_bytes_per_step": BATCH * IN_BYTES,
-           "d2h_bytes_per_step": BATCH * OUT_BYTES, "api": "yf_b200_run(host pinned in, host pinned out)", "ms_per_step": 1e3 * dt / args.steps}
+           "d2h_bytes_per_step": BATCH * OUT_BYTES, "api": "yf_b200_submit(host pinned in, host pinned out) per step + yf_b200_wait",
+           "ms_per_step": 1e3 * dt / args.steps,
+           "blocking": {"value": world * BATCH * args.steps / dt_block, "ms_per_step": 1e3 * dt_block / args.steps,
+                        "api": "yf_b200_run(host pinned in, host pinned out), one blocking call per step"}}
     # sanity: the e2e result of the last step equals the device-resident result for that input
     last = (args.steps - 1) % RING
     net.run(d_in[last], d_out[last], n=BATCH)
-    assert torch.equal(h_out, d_out[last].cpu()), "host-path and device-path heads differ"
+    assert torch.equal(h_out[(args.steps - 1) % 4], d_out[last].cpu()), "host-path and device-path heads differ"
 
     # ---------------- roofline of the dominant kernel ----------------
     roofline, per_step = None, []
@@ -269,12 +284,29 @@ def run_ours(args, rank, local_rank, world):
                 "data": "synthetic", "config": CONFIG, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu, "path": "fused single kernel" if fused else "layer-by-layer kernels",
                 "layered_kernels": per_step}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, warnings
+    from libraries) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                         # fd 1 -> stderr for the rest of the run (native libraries print there too)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)

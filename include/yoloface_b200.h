@@ -58,6 +58,14 @@ AI_API_ENTRY int32_t yf_b200_set_stream(ai_handle network, void* cuda_stream);
 AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* d_out, uint32_t n);
 AI_API_ENTRY int32_t yf_b200_sync(ai_handle network);
 
+/* Pipelined host path: yf_b200_submit queues n images from (preferably page-locked) host memory --
+ * H2D copy, kernels and D2H copy of the heads run on three streams over a ring of staging slots, so the
+ * copy of one submission overlaps the kernels of the previous one -- and returns without waiting;
+ * yf_b200_wait blocks until every submitted result is in `out_host` and reports pipeline errors.
+ * (yf_b200_run / ai_network_run use the same ring internally for batches larger than one chunk.) */
+AI_API_ENTRY int32_t yf_b200_submit(ai_handle network, const void* in_host, void* out_host, uint32_t n);
+AI_API_ENTRY int32_t yf_b200_wait(ai_handle network);
+
 /* Decode + NMS of heads already computed ([n,gh,gw,18] int8, host or device).
  * conf_thr: keep conf >= conf_thr (0.7 in yoloface.c:123); iou_thr < 0: threshold only (what the
  * firmware does), else greedy NMS keeping iou <= iou_thr (0.4 in yoloface_test.py:32).

@@ -40,8 +40,14 @@ struct PlanDev {
   uint8_t* d_wblob = nullptr;
   uint8_t* d_luts = nullptr;
   uint8_t* d_arena = nullptr;
-  int8_t* d_in = nullptr;               // staging for host inputs [cap,H,W,3]
-  int8_t* d_head = nullptr;             // staging for host outputs [cap,GH,GW,18]
+  int8_t* d_in = nullptr;               // staging for host inputs [cap,H,W,3]      (= ring slot 0)
+  int8_t* d_head = nullptr;             // staging for host outputs [cap,GH,GW,18] (= ring slot 0)
+  static constexpr int kRing = 3;       // pipelined host path: slots of (input, head) staging + events
+  int8_t* r_in[kRing] = {nullptr, nullptr, nullptr};
+  int8_t* r_head[kRing] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_h2d[kRing] = {nullptr, nullptr, nullptr}, ev_comp[kRing] = {nullptr, nullptr, nullptr}, ev_d2h[kRing] = {nullptr, nullptr, nullptr};
+  bool busy[kRing] = {false, false, false};
+  uint64_t seq = 0;
   std::vector<CUtensorMap> tmaps;       // per step (conv1x1 only)
   std::vector<float> step_ms;
   Plan fplan;                           // same steps with 16-aligned concat slots, for the fused kernel
@@ -49,6 +55,8 @@ struct PlanDev {
   uint8_t* d_fparams = nullptr;
   ~PlanDev() {
     cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams);
+    for (int i = 1; i < kRing; ++i) { cudaFree(r_in[i]); cudaFree(r_head[i]); }
+    for (int i = 0; i < kRing; ++i) { if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]); if (ev_comp[i]) cudaEventDestroy(ev_comp[i]); if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]); }
   }
 };
 
@@ -70,6 +78,7 @@ struct Network {
   uint8_t* d_frames = nullptr; size_t frames_cap = 0;
   std::map<std::pair<int, int>, std::unique_ptr<PlanDev>> plans;
   cudaStream_t own_stream = nullptr;    // created by the library; `stream` may be a caller's
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
   uint32_t last_run_n = 0;
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
@@ -303,6 +312,44 @@ bool check_device_err(Network* n) {
   return true;
 }
 
+// ---- pipelined host path: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h) over a ring of staging slots ----
+bool ring_prepare(Network* n, PlanDev* pd) {
+  if (pd->ev_h2d[0]) return true;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3 * pd->cap, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18 * pd->cap;
+  pd->r_in[0] = pd->d_in; pd->r_head[0] = pd->d_head;
+  for (int i = 0; i < PlanDev::kRing; ++i) {
+    if (i && (!cuda_ok(n, cudaMalloc(&pd->r_in[i], in_sz), "cudaMalloc ring", AI_ERROR_ALLOCATION_FAILED) ||
+              !cuda_ok(n, cudaMalloc(&pd->r_head[i], out_sz), "cudaMalloc ring", AI_ERROR_ALLOCATION_FAILED))) return false;
+    if (!cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_h2d[i], cudaEventDisableTiming), "event") ||
+        !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_comp[i], cudaEventDisableTiming), "event") ||
+        !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_d2h[i], cudaEventDisableTiming), "event")) return false;
+  }
+  return true;
+}
+// queue one chunk (nb <= cap) from host memory; returns without waiting.  out may be NULL (heads stay in the slot).
+bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_host, uint32_t nb, int8_t** slot_heads) {
+  if (!ring_prepare(n, pd)) return false;
+  const int s = static_cast<int>(pd->seq++ % PlanDev::kRing);
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  if (pd->busy[s] && !cuda_ok(n, cudaEventSynchronize(pd->ev_d2h[s]), "ring slot wait")) return false;   // slot's previous user has drained
+  if (!cuda_ok(n, cudaMemcpyAsync(pd->r_in[s], in_host, nb * in_sz, cudaMemcpyHostToDevice, n->s_h2d), "H2D input", AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
+  cudaEventRecord(pd->ev_h2d[s], n->s_h2d);
+  cudaStreamWaitEvent(n->stream, pd->ev_h2d[s], 0);
+  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb)) return false;
+  cudaEventRecord(pd->ev_comp[s], n->stream);
+  cudaStreamWaitEvent(n->s_d2h, pd->ev_comp[s], 0);
+  if (out_host && !cuda_ok(n, cudaMemcpyAsync(out_host, pd->r_head[s], nb * out_sz, cudaMemcpyDeviceToHost, n->s_d2h), "D2H output", AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
+  cudaEventRecord(pd->ev_d2h[s], n->s_d2h);
+  pd->busy[s] = true; n->last_run_n = nb;
+  if (slot_heads) *slot_heads = pd->r_head[s];
+  return true;
+}
+bool ring_wait(Network* n, PlanDev* pd) {
+  for (int i = 0; i < PlanDev::kRing; ++i)
+    if (pd->busy[i]) { if (!cuda_ok(n, cudaEventSynchronize(pd->ev_d2h[i]), "ring wait")) return false; pd->busy[i] = false; }
+  return true;
+}
+
 // inference of n images; in/out host or device
 int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool keep_heads_on_device, int8_t** dev_heads) {
   PlanDev* pd = get_plan(n, n->H, n->W);
@@ -313,6 +360,19 @@ int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool k
   const bool out_dev = out ? is_device_ptr(out) : true;
   if (in_dev && (reinterpret_cast<uintptr_t>(in) & 15)) { set_text("device input must be 16-byte aligned"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   cudaEventRecord(n->ev0, n->stream);
+  if (!in_dev && out && !out_dev && !n->step_profiling && !pd->observer) {
+    // host -> host: pipeline the chunks (copy of chunk i+1 overlaps the kernels of chunk i)
+    for (uint32_t done = 0; done < count; done += pd->cap) {
+      const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+      if (!ring_submit(n, pd, static_cast<const int8_t*>(in) + done * in_sz, static_cast<int8_t*>(out) + done * out_sz, nb, nullptr)) return -1;
+    }
+    if (!ring_wait(n, pd)) return -1;
+    cudaEventRecord(n->ev1, n->stream);
+    if (!check_device_err(n)) return -1;
+    cudaEventElapsedTime(&n->last_ms, n->ev0, n->ev1);
+    n->images += count;
+    return static_cast<int32_t>(count);
+  }
   for (uint32_t done = 0; done < count; done += pd->cap) {
     const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
     const int8_t* din = in_dev ? static_cast<const int8_t*>(in) + done * in_sz : pd->d_in;
@@ -459,7 +519,8 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr);
   }
   if (!ok) { set_text("model: " + perr); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; return err; }
-  if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&n->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&n->s_d2h, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
       cudaEventCreate(&n->ev1) != cudaSuccess || cudaMalloc(&n->d_err, sizeof(int)) != cudaSuccess ||
       cudaMemset(n->d_err, 0, sizeof(int)) != cudaSuccess || kernels_init() != cudaSuccess) {
     set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
@@ -483,7 +544,7 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   }
   n->plans.clear();
   cudaFree(n->d_trace); cudaFree(n->d_err); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
-  cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream);
+  cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream); cudaStreamDestroy(n->s_h2d); cudaStreamDestroy(n->s_d2h);
   g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end());
   delete n;
   return AI_HANDLE_NULL;
@@ -634,6 +695,27 @@ AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* 
   }
   n->images += count;
   return static_cast<int32_t>(count);
+}
+
+AI_API_ENTRY int32_t yf_b200_submit(ai_handle network, const void* in_host, void* out_host, uint32_t count) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!in_host || is_device_ptr(in_host)) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (!out_host || is_device_ptr(out_host)) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  for (uint32_t done = 0; done < count; done += pd->cap) {
+    const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+    if (!ring_submit(n, pd, static_cast<const int8_t*>(in_host) + done * in_sz, static_cast<int8_t*>(out_host) + done * out_sz, nb, nullptr)) return -1;
+  }
+  n->images += count;
+  return static_cast<int32_t>(count);
+}
+
+AI_API_ENTRY int32_t yf_b200_wait(ai_handle network) {
+  YF_NET_OR_FAIL(n, network)
+  for (auto& kv : n->plans) if (!ring_wait(n, kv.second.get())) return -1;
+  return check_device_err(n) ? 0 : -1;
 }
 
 AI_API_ENTRY int32_t yf_b200_sync(ai_handle network) {
