@@ -93,6 +93,26 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
   return (static_cast<uint64_t>(0x4008u) << 32) | static_cast<uint64_t>(lo_tmpl | ((saddr >> 4) & 0x3FFFu));
 }
 
+// requantise NW 4-channel words of one accumulator row in ONE basic block (ILP across 4*NW chains)
+template <int NW, bool LUT>
+__device__ __forceinline__ void requant_words(const uint32_t (&v)[16], const EpiChF* ek, const uint8_t* lut, uint32_t (&w)[4]) {
+  int32_t idx[NW * 4];
+#pragma unroll
+  for (int c = 0; c < NW * 4; ++c) {
+    const EpiChF k = ek[c];
+    idx[c] = requant_idx(static_cast<int32_t>(v[c]), k.add64, k.mult, k.c2p, k.e);
+  }
+#pragma unroll
+  for (int wi = 0; wi < NW; ++wi) {
+    if (LUT)
+      w[wi] = static_cast<uint32_t>(lut[idx[4 * wi]]) | (static_cast<uint32_t>(lut[idx[4 * wi + 1]]) << 8) |
+              (static_cast<uint32_t>(lut[idx[4 * wi + 2]]) << 16) | (static_cast<uint32_t>(lut[idx[4 * wi + 3]]) << 24);
+    else
+      w[wi] = (static_cast<uint32_t>(idx[4 * wi]) | (static_cast<uint32_t>(idx[4 * wi + 1]) << 8) | (static_cast<uint32_t>(idx[4 * wi + 2]) << 16) |
+               (static_cast<uint32_t>(idx[4 * wi + 3]) << 24)) ^ 0x80808080u;         // index -> int8
+  }
+}
+
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
                                           int row, int g, int8_t* ghead) {
@@ -101,29 +121,23 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
   tmem_ld_wait();
   if (row >= ph.rows_out) return;
   const int nreal = ph.cout - g * 16;                        // real channels in this chunk (> 0)
+  const int nwords = nreal >= 13 ? 4 : (nreal + 3) >> 2;     // warp-uniform
   const EpiChF* ek = epi + g * 16;                           // shared memory (broadcast reads)
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (ph.has_lut) {
-#pragma unroll
-    for (int wi = 0; wi < 4; ++wi)
-      if (wi * 4 < nreal) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const EpiChF k = ek[wi * 4 + j];
-          w[wi] |= static_cast<uint32_t>(lut[requant_idx(static_cast<int32_t>(v[wi * 4 + j]), k.add64, k.mult, k.c2p, k.e)]) << (8 * j);
-        }
-      }
+    switch (nwords) {
+      case 1: requant_words<1, true>(v, ek, lut, w); break;
+      case 2: requant_words<2, true>(v, ek, lut, w); break;
+      case 3: requant_words<3, true>(v, ek, lut, w); break;
+      default: requant_words<4, true>(v, ek, lut, w); break;
+    }
   } else {
-#pragma unroll
-    for (int wi = 0; wi < 4; ++wi)
-      if (wi * 4 < nreal) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const EpiChF k = ek[wi * 4 + j];
-          w[wi] |= static_cast<uint32_t>(requant_idx(static_cast<int32_t>(v[wi * 4 + j]), k.add64, k.mult, k.c2p, k.e)) << (8 * j);
-        }
-        w[wi] ^= 0x80808080u;                                // index -> int8
-      }
+    switch (nwords) {
+      case 1: requant_words<1, false>(v, ek, lut, w); break;
+      case 2: requant_words<2, false>(v, ek, lut, w); break;
+      case 3: requant_words<3, false>(v, ek, lut, w); break;
+      default: requant_words<4, false>(v, ek, lut, w); break;
+    }
     if (ph.add_off >= 0) {
       const uint4 sk = *reinterpret_cast<const uint4*>(smem + ph.add_off + g * ph.add_cs + row * 16);
       w[0] = add_word(sk.x, w[0], ph.add);
@@ -148,13 +162,19 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* sme
   const int q = warp & 3, chunks = ph.chunks_out, ntiles = ph.ntiles;
   const uint8_t* lut = slot + ph.lut_off;
   const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
-  int t = 0, g = warp >> 2;
-  while (g >= chunks) { g -= chunks; ++t; }
-  while (t < ntiles) {
-    if (t * 128 + q * 32 < ph.rows_out)                      // else: this warp's 32 rows are all padding
-      conv_unit(ph, smem, lut, epi, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
-    g += kFusedWarpgroups;
-    while (g >= chunks) { g -= chunks; ++t; }
+  if (ntiles >= kFusedWarpgroups) {
+    // several tiles: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
+    for (int t = warp >> 2; t < ntiles; t += kFusedWarpgroups) {
+      if (t * 128 + q * 32 >= ph.rows_out) continue;         // this warp's 32 rows are all padding
+      for (int g = 0; g < chunks; ++g)
+        conv_unit(ph, smem, lut, epi, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+    }
+  } else {
+    // a single tile: split its chunks across the warpgroups
+    for (int g = warp >> 2; g < chunks; g += kFusedWarpgroups)
+      for (int t = 0; t < ntiles; ++t)
+        if (t * 128 + q * 32 < ph.rows_out)
+          conv_unit(ph, smem, lut, epi, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
   }
 }
 
@@ -312,7 +332,7 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
   const uint8_t* image = smem + ph.in_off;
   uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
   const int rr = (2 * r + hf) * 128 + rt;
-  if (rr >= ph.rows_out) return;
+  if (hf >= 2 || rr >= ph.rows_out) return;                 // two tiles per round; further worker warps idle here
   const int oy = small_div(rr, ph.Wout), ox = rr - oy * ph.Wout;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
