@@ -278,12 +278,40 @@ def run_ours(args, rank, local_rank, world):
 
     cpu = cpu_baseline_sample() if (rank == 0 and world == 1 and not args.no_cpu) else None
     net.close()
+    # ---------------- informational: larger launches and the decode+NMS path (not the headline) ----------------
+    extra = None
+    if rank == 0 and not args.no_extra:
+        big = 8192
+        net2 = yf.Network(device=local_rank, chunk_images=big)
+        xb = torch.randint(-128, 128, (big, 56, 56, 3), dtype=torch.int8, device="cuda", generator=gen)
+        xb[::2] = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "images_56.npy"))[np.arange(big // 2) % 27]).cuda()
+        yb = torch.empty((big, 7, 7, 18), dtype=torch.int8, device="cuda")
+        net2.set_stream(stream.cuda_stream)
+        for _ in range(3):
+            net2.enqueue(xb, yb, big)
+        net2.sync()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for _ in range(20):
+            net2.enqueue(xb, yb, big)
+        b1.record(stream); b1.synchronize(); net2.sync()
+        ms_big = b0.elapsed_time(b1) / 20
+        net2.set_stream(None)
+        net2.detect(xb, 0.7, 0.4, max_det=8, n=big)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            dets, counts = net2.detect(xb, 0.7, 0.4, max_det=8, n=big)
+        dt_det = (time.perf_counter() - t0) / 5
+        extra = {"batch": big, "device_resident_images_per_s": big / (ms_big * 1e-3), "ms_per_launch": ms_big,
+                 "detect_images_per_s": big / dt_det, "detect_api": "yf_b200_detect(device in) -> decode + NMS on device, detections D2H",
+                 "detections_per_image": float(counts.mean())}
+        net2.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",
                 "data": "synthetic", "config": CONFIG, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu, "path": "fused single kernel" if fused else "layer-by-layer kernels",
-                "layered_kernels": per_step}
+                "extra": extra, "layered_kernels": per_step}
         emit(line)
     if dist:
         dist.destroy_process_group()
@@ -313,6 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational large-batch / decode leg")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

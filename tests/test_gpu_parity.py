@@ -233,3 +233,25 @@ def test_launch_counter(net):
     s1 = net.stats()
     assert s1["steps"] == 26 and s1["sm_count"] == 148
     assert s1["kernel_launches"] - s0["kernel_launches"] == (1 if s1["fused"] else 26)
+
+
+def test_config3_65536_images_with_device_decode_nms(net, oracle, golden):
+    """BASELINE config 3: 65,536 images (half of them tiled real faces so decode/NMS has survivors),
+    heads + detections computed on device; a 2,048-image random subset is checked bit-exact against the
+    oracle and all of its detections within tolerance, identical keep-set."""
+    n = 65536
+    rng = np.random.default_rng(1)
+    base = rng.integers(-128, 128, (512, 56, 56, 3), dtype=np.int8)
+    base[::2] = golden["images"][np.arange(256) % 27]
+    x = np.tile(base, (n // 512, 1, 1, 1))
+    heads = np.empty((n, 7, 7, 18), np.int8)
+    dets, counts = net.detect(x, 0.7, 0.4, max_det=8, heads_out=heads)
+    assert counts.sum() > n // 4                              # the face half does produce detections
+    sub = rng.permutation(n)[:2048]
+    ref = oracle.run_batch(np.ascontiguousarray(x[sub]), threads=os.cpu_count())
+    assert np.array_equal(heads[sub], ref)
+    for k, i in enumerate(sub[:512]):
+        r = oracle.decode_nms(ref[k], 0.7, 0.4)[:8]
+        assert counts[i] == len(r)
+        if len(r):
+            assert np.all(np.abs(dets[i, :len(r), :4] - r[:, :4]) <= COORD_TOL) and np.all(np.abs(dets[i, :len(r), 4] - r[:, 4]) <= CONF_TOL)
