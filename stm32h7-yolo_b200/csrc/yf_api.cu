@@ -984,7 +984,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
     kv("out_off", p.out_off); kv("out_cs", p.out_cs); kv("add_off", p.add_off); kv("add_cs", p.add_cs); kv("nk", p.nk); kv("npad", p.npad);
     kv("cout", p.cout); kv("chunks_out", p.chunks_out); kv("epi_base", p.epi_base); kv("has_lut", p.has_lut); kv("in_zp", p.in_zp);
     kv("to_global", p.to_global); kv("param_off", p.param_off); kv("param_bytes", p.param_bytes); kv("w_off", p.w_off); kv("lut_off", p.lut_off);
-    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("epi_off", p.epi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw);
+    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("epi_off", p.epi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw); kv("in_wp", p.in_wp); kv("out_wp", p.out_wp); kv("out_zp", p.out_zp);
     j += "\"add\":[" + std::to_string(p.add.enabled) + "," + std::to_string(p.add.zp1) + "," + std::to_string(p.add.zp2) + "," + std::to_string(p.add.zp_out) + "," +
          std::to_string(p.add.m1) + "," + std::to_string(p.add.m2) + "," + std::to_string(p.add.mo) + "," + std::to_string(p.add.s1) + "," +
          std::to_string(p.add.s2) + "," + std::to_string(p.add.so) + "]";

@@ -93,6 +93,25 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
   return (static_cast<uint64_t>(0x4008u) << 32) | static_cast<uint64_t>(lo_tmpl | ((saddr >> 4) & 0x3FFFu));
 }
 
+// x / d for small non-negative x (x < 4096), d <= 64: exact (margin 0.5/(x+0.5) >> float error)
+__device__ __forceinline__ int small_div(int x, int d) { return static_cast<int>(__fdividef(static_cast<float>(x) + 0.5f, static_cast<float>(d))); }
+
+// border cells of a padded output buffer <- the tensor's zero point (run by the workers while the MMAs are in flight)
+__device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem, int tid) {
+  const int WP = ph.out_wp, H = ph.Hout, ncell = 2 * WP + 2 * H;
+  const uint32_t z = static_cast<uint32_t>(ph.out_zp & 0xff) * 0x01010101u;
+  const uint4 zv = make_uint4(z, z, z, z);
+  for (int i = tid; i < ncell * ph.chunks_out; i += kFusedWorkerThreads) {
+    const int c = small_div(i, ncell), k = i - c * ncell;
+    int cell;
+    if (k < WP) cell = k;
+    else if (k < 2 * WP) cell = (H + 1) * WP + (k - WP);
+    else if (k < 2 * WP + H) cell = (k - 2 * WP + 1) * WP;
+    else cell = (k - 2 * WP - H + 1) * WP + WP - 1;
+    *reinterpret_cast<uint4*>(smem + ph.out_off + c * ph.out_cs + cell * 16) = zv;
+  }
+}
+
 // requantise NW 4-channel words of one accumulator row in ONE basic block (ILP across 4*NW chains)
 template <int NW, bool LUT>
 __device__ __forceinline__ void requant_words(const uint32_t (&v)[16], const EpiChF* ek, const uint8_t* lut, uint32_t (&w)[4]) {
@@ -152,7 +171,12 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
     for (int j = 0; j < 8; ++j)
       if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
   } else {
-    *reinterpret_cast<uint4*>(smem + ph.out_off + g * ph.out_cs + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    int cell = row;
+    if (ph.out_wp) {                                         // zero-point-bordered layout for depthwise / pool consumers
+      const int y = small_div(row, ph.Wout);
+      cell = (y + 1) * ph.out_wp + (row - y * ph.Wout) + 1;
+    }
+    *reinterpret_cast<uint4*>(smem + ph.out_off + g * ph.out_cs + cell * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -178,8 +202,6 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* sme
   }
 }
 
-// x / d for small x (x < 4096) with a host-free magic: exact for d <= 64
-__device__ __forceinline__ int small_div(int x, int d) { return static_cast<int>(__fdividef(static_cast<float>(x) + 0.5f, static_cast<float>(d))); }
 
 // DEPTHWISE_CONV_2D 3x3
 __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, long long* tp) {
@@ -206,34 +228,22 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
     k_c2p[0] = c.x; k_c2p[1] = c.y; k_c2p[2] = c.z; k_c2p[3] = c.w;
     k_e[0] = e.x; k_e[1] = e.y; k_e[2] = e.z; k_e[3] = e.w;
   }
-  const int Hin = ph.Hin, Win = ph.Win, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out, pad_t = ph.pad_t, pad_l = ph.pad_l;
-  const int row16 = Win * 16, dy = ph.dy, dx = ph.dx;
-  const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4;
+  const int WP = ph.in_wp, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out;
+  const int row16 = WP * 16, dy = ph.dy, dx = ph.dx;
+  // input is stored with a one-cell zero-point border: tap (ky,kx) of output (oy,ox) is padded cell
+  // (oy*stride - pad_t + 1 + ky, ox*stride - pad_l + 1 + kx), always inside the buffer -> no bounds checks
+  const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4 + ((1 - ph.pad_t) * WP + (1 - ph.pad_l)) * 16;
   uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
-  const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
   const bool has_lut = ph.has_lut != 0;
   int oy = small_div(pix, Wout), ox = pix - oy * Wout;
   YF_STAMP(tp, 1);
-
   for (; pix < rows; pix += per) {
-    const int iy0 = oy * stride - pad_t, ix0 = ox * stride - pad_l;
-    const uint8_t* p = ib + (iy0 * Win + ix0) * 16;
+    const uint8_t* p = ib + (oy * stride * WP + ox * stride) * 16;
     uint32_t x[9];
-
-    if (iy0 >= 0 && iy0 + 2 < Hin && ix0 >= 0 && ix0 + 2 < Win) {
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) x[ky * 3 + kx] = *reinterpret_cast<const uint32_t*>(p + ky * row16 + kx * 16);
-    } else {
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const bool in = (iy0 + ky >= 0) && (iy0 + ky < Hin) && (ix0 + kx >= 0) && (ix0 + kx < Win);
-          x[ky * 3 + kx] = in ? *reinterpret_cast<const uint32_t*>(p + ky * row16 + kx * 16) : zpw;
-        }
-    }
+      for (int kx = 0; kx < 3; ++kx) x[ky * 3 + kx] = *reinterpret_cast<const uint32_t*>(p + ky * row16 + kx * 16);
     uint32_t ow = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -273,7 +283,7 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
     for (; it < total; it += per) {
       const int x0 = max(0, ox * stride - ph.pad_l), x1 = min(Win, ox * stride - ph.pad_l + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
-      const uint8_t* p = ib + (y * Win + x0) * 16;
+      const uint8_t* p = ib + ((y + 1) * ph.in_wp + x0 + 1) * 16;
       int n = x1 - x0;
       for (; n >= 2; n -= 2, p += 32) {
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 16);
@@ -472,6 +482,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
         if (sub) sub[1] = clock64();
         if (ph.kind == STEP_CONV1X1) {
           if (sub) sub[2] = clock64();
+          if (ph.out_wp) fill_border(ph, smem, tid);
           wait_bar(&mma_done[0], use0 & 1, 301); ++use0;
           tc_fence_after();
           if (sub) sub[3] = clock64();
@@ -479,6 +490,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
           tc_fence_before();
           if (sub) sub[4] = clock64();
         } else if (ph.kind == STEP_CONV_IM2COL) {
+          if (ph.out_wp) fill_border(ph, smem, tid);
           wait_bar(in_full, in_uses & 1, 303); ++in_uses;
           const int rounds = (ph.ntiles + 1) >> 1;
           for (int r = 0; r < rounds; ++r) {

@@ -561,7 +561,19 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     if (s.add_buf >= 0) death[s.add_buf] = std::max(death[s.add_buf], i);
     birth[s.out_buf] = std::min(birth[s.out_buf], i); death[s.out_buf] = std::max(death[s.out_buf], i);
   }
-  auto bytes_of = [&](int b) { const PBuffer& B = P.buffers[b]; return (B.H * B.W * B.CP + 127) & ~127; };
+  // padded buffers: produced by a conv step, consumed only by depthwise / pool steps
+  std::vector<char> padded(nb, 0), has_prod_conv(nb, 0), bad_cons(nb, 0), has_cons(nb, 0);
+  for (int i = 0; i < ns; ++i) {
+    const Step& s = P.steps[i];
+    if (s.kind == STEP_DW || s.kind == STEP_MAXPOOL) has_cons[s.in_buf] = 1; else bad_cons[s.in_buf] = 1;
+    if (s.add_buf >= 0) bad_cons[s.add_buf] = 1;
+    if ((s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && s.out_coff == 0) has_prod_conv[s.out_buf] = 1; else bad_cons[s.out_buf] = 1;
+  }
+  for (int b = 0; b < nb; ++b) padded[b] = has_prod_conv[b] && has_cons[b] && !bad_cons[b] && !P.buffers[b].is_input && !P.buffers[b].is_output;
+  for (int i = 0; i < ns; ++i) if ((P.steps[i].kind == STEP_DW || P.steps[i].kind == STEP_MAXPOOL) && !padded[P.steps[i].in_buf])
+    return no("depthwise/pool input " + P.steps[i].name + " is not a conv-produced, dw/pool-only buffer");
+  auto cells_of = [&](int b) { const PBuffer& B = P.buffers[b]; return padded[b] ? (B.H + 2) * (B.W + 2) : B.H * B.W; };
+  auto bytes_of = [&](int b) { const PBuffer& B = P.buffers[b]; return (cells_of(b) * B.CP + 127) & ~127; };
   // scratch regions live for exactly one phase: the first conv's A stages, the pools' row maxima
   std::vector<int> scratch_size(ns, 0);
   for (int i = 0; i < ns; ++i) {
@@ -610,9 +622,13 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     ph.Hin = s.Hin; ph.Win = s.Win; ph.Hout = s.Hout; ph.Wout = s.Wout; ph.rows_in = s.Hin * s.Win; ph.rows_out = s.Hout * s.Wout;
     ph.stride = s.stride; ph.pad_t = s.pad_t; ph.pad_l = s.pad_l; ph.ksize = s.kh; ph.in_zp = s.in_zp;
     const PBuffer& ib = P.buffers[s.in_buf]; const PBuffer& ob = P.buffers[s.out_buf];
-    ph.in_off = ib.is_input ? F->in_off : F->arena_off + off[s.in_buf]; ph.in_cs = ph.rows_in * 16;
+    ph.in_off = ib.is_input ? F->in_off : F->arena_off + off[s.in_buf];
+    ph.in_cs = (ib.is_input ? ph.rows_in : cells_of(s.in_buf)) * 16;
+    ph.in_wp = (!ib.is_input && padded[s.in_buf]) ? s.Win + 2 : 0;
     ph.to_global = ob.is_output ? 1 : 0;
-    ph.out_cs = ph.rows_out * 16;
+    ph.out_cs = (ob.is_output ? ph.rows_out : cells_of(s.out_buf)) * 16;
+    ph.out_wp = (!ob.is_output && padded[s.out_buf]) ? s.Wout + 2 : 0;
+    if (ph.out_wp) { for (int j = i + 1; j < ns; ++j) if (P.steps[j].in_buf == s.out_buf) { ph.out_zp = P.steps[j].in_zp; break; } }
     ph.out_off = ob.is_output ? 0 : F->arena_off + off[s.out_buf] + (s.out_coff / 16) * ph.out_cs;
     ph.add_off = -1; ph.scratch_off = scratch_off[i] >= 0 ? F->arena_off + scratch_off[i] : -1;
     if (s.add.enabled) { ph.add = s.add; ph.add_cs = ph.rows_out * 16; ph.add_off = F->arena_off + off[s.add_buf] + (s.add_coff / 16) * ph.add_cs; }

@@ -171,7 +171,10 @@ struct alignas(16) FusedPhase {
   int32_t dy1, dx1;             // pool pass 1 (row maxima): per / Wout, per % Wout (same Wout) -- kept separate for clarity
   int32_t idesc;                // UMMA instruction descriptor (M=128, N=npad, s8 x s8 -> s32)
   uint32_t adesc_lo, bdesc_lo;  // UMMA smem descriptor low words without the start address: LBO >> 4 << 16
-  int32_t pad_[1];
+  // zero-point border: buffers read only by depthwise / pool steps are stored as (H+2) x (W+2) cells
+  int32_t in_wp, out_wp;        // padded row width in cells of the input / output buffer (0 = not padded)
+  int32_t out_zp;               // border value of a padded output buffer (its tensor's zero point)
+  int32_t pad_[2];
 };
 static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied to shared memory with 16-byte loads");
 

@@ -21,6 +21,11 @@ def run_fused(F, img, seed=0):
         a = off + chunk * cs
         return smem[a:a + rows * 16].view(np.int8).reshape(rows, 16)
 
+    def padded_input(ph, chunks):                  # zero-point-bordered (H+2)x(W+2) buffer -> [H+2, W+2, chunks*16] int64
+        H, W = ph["Hin"], ph["Win"]
+        assert ph["in_wp"] == W + 2 and ph["in_cs"] == (H + 2) * (W + 2) * 16
+        return np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, (H + 2) * (W + 2)) for c in range(chunks)], axis=1).reshape(H + 2, W + 2, chunks * 16).astype(np.int64)
+
     for ph in F["phases"]:
         slot = params[ph["param_off"]:ph["param_off"] + ph["param_bytes"]]
         kind, rows_o, cout, npad = ph["kind"], ph["rows_out"], ph["cout"], ph["npad"]
@@ -75,20 +80,20 @@ def run_fused(F, img, seed=0):
             epi["sgn_mask"] = -1
             epi = epi[:cout]
             H, W, Ho, Wo, st = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"]
-            x = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, H * W) for c in range(chunks)], axis=1).reshape(H, W, cp).astype(np.int64)
-            xp = np.full((H + 2 + st, W + 2 + st, cp), ph["in_zp"], np.int64)
-            xp[ph["pad_t"]:ph["pad_t"] + H, ph["pad_l"]:ph["pad_l"] + W] = x
+            xp = padded_input(ph, chunks)           # the border must already hold the zero point (written by the producer)
+            assert np.all(xp[0, :, :cout] == ph["in_zp"]) and np.all(xp[:, 0, :cout] == ph["in_zp"]) and np.all(xp[-1, :, :cout] == ph["in_zp"]) and np.all(xp[:, -1, :cout] == ph["in_zp"])
+            oy0, ox0 = 1 - ph["pad_t"], 1 - ph["pad_l"]
             acc = np.zeros((Ho, Wo, cp), np.int64)
             for ky in range(3):
                 for kx in range(3):
-                    acc += xp[ky:ky + st * Ho:st, kx:kx + st * Wo:st] * w[ky * 3 + kx]
+                    acc += xp[oy0 + ky:oy0 + ky + st * Ho:st, ox0 + kx:ox0 + kx + st * Wo:st] * w[ky * 3 + kx]
             y = np.clip(requant(acc.reshape(Ho * Wo, cp)[:, :cout], epi), -128, 127)
             if lut is not None:
                 y = lut_apply(y, lut)
         elif kind == 3:
             chunks = ph["chunks_out"]; cp = chunks * 16
             H, W, Ho, Wo, st, k = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"], ph["ksize"]
-            x = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, H * W) for c in range(chunks)], axis=1).reshape(H, W, cp).astype(np.int64)
+            x = padded_input(ph, chunks)[1:-1, 1:-1]
             y = np.zeros((Ho * Wo, cout), np.int64)
             for oy in range(Ho):
                 for ox in range(Wo):
@@ -103,7 +108,13 @@ def run_fused(F, img, seed=0):
             continue
         out = np.zeros((rows_o, ph["chunks_out"] * 16), np.int8)
         out[:, :cout] = y
+        if ph["out_wp"]:                            # producer writes the interior of a bordered buffer and fills the border
+            Ho, Wo = ph["Hout"], ph["Wout"]
+            full = np.full((Ho + 2, Wo + 2, ph["chunks_out"] * 16), ph["out_zp"], np.int8)
+            full[1:-1, 1:-1] = out.reshape(Ho, Wo, -1)
+            assert ph["out_cs"] == (Ho + 2) * (Wo + 2) * 16 and ph["out_wp"] == Wo + 2
+            out = full.reshape(-1, ph["chunks_out"] * 16)
         for g in range(ph["chunks_out"]):
             a = ph["out_off"] + g * ph["out_cs"]
-            smem[a:a + rows_o * 16] = out[:, g * 16:(g + 1) * 16].reshape(-1).view(np.uint8)
+            smem[a:a + out.shape[0] * 16] = out[:, g * 16:(g + 1) * 16].reshape(-1).view(np.uint8)
     return head

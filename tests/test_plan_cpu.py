@@ -135,7 +135,7 @@ def test_fused_program_reproduces_oracle(yf, oracle, golden):
 
 def test_fused_program_limits(yf):
     F = yf.fused_program(64, 64)                  # still fits shared memory and TMEM
-    assert F["smem_bytes"] < 113 * 1024
+    assert F["smem_bytes"] < 200 * 1024
     for hw in ((64, 96), (224, 224)):             # a layer's accumulator tiles exceed TMEM / smem -> layered path
         with pytest.raises(RuntimeError):
             yf.fused_program(*hw)
