@@ -36,6 +36,8 @@ typedef struct yf_b200_config_ {
 
 #define YF_B200_FLAG_OBSERVER 0x1u   /* keep every operator's tensor (slower, more memory) */
 #define YF_B200_FLAG_LAYERED 0x2u    /* always run the layer-by-layer kernels (one launch per fused step) */
+#define YF_B200_FLAG_ST_ACTIVATIONS 0x8u /* LeakyReLU tables as ST's code generator rounds them (network.c:2218..2902)
+                                          * instead of TFLite's fixed-point rule; also env YF_B200_ST_ACTIVATIONS=1 */
 #define YF_B200_FLAG_FUSED_ONLY 0x4u /* fail instead of falling back when the single-kernel path cannot be used */
 
 typedef struct yf_b200_det_ {

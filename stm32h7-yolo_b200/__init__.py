@@ -28,6 +28,7 @@ YF_B200_CONFIG_MAGIC = 0x32424659
 YF_B200_FLAG_OBSERVER = 1
 YF_B200_FLAG_LAYERED = 2
 YF_B200_FLAG_FUSED_ONLY = 4
+YF_B200_FLAG_ST_ACTIVATIONS = 8
 YF_B200_NMS_PLUS_ONE = 1
 
 
@@ -233,11 +234,12 @@ def fused_program(height=56, width=56, blob=None):
 class Network:
     """aiInit()/aiRun() of stm32/X-CUBE-AI/App/yoloface.c:188-240, batch-capable."""
 
-    def __init__(self, device=-1, chunk_images=0, observer=False, tflite_path=None, weights=None, mode="auto"):
+    def __init__(self, device=-1, chunk_images=0, observer=False, tflite_path=None, weights=None, mode="auto", st_activations=False):
         L = self.L = lib()
         self.handle = C.c_void_p()
         flags = (YF_B200_FLAG_OBSERVER if observer else 0) | {"auto": 0, "layered": YF_B200_FLAG_LAYERED,
                                                               "fused": YF_B200_FLAG_FUSED_ONLY}[mode]
+        flags |= YF_B200_FLAG_ST_ACTIVATIONS if st_activations else 0
         self._cfg = Config(YF_B200_CONFIG_MAGIC, device, chunk_images, flags,
                            tflite_path.encode() if tflite_path else None)
         cfgbuf = AiBuffer(AI_BUFFER_FORMAT_U8, 1, 1, 1, C.sizeof(Config), C.cast(C.pointer(self._cfg), C.c_void_p), None)

@@ -69,6 +69,7 @@ struct Network {
   uint32_t chunk = 1024;
   bool observer = false, step_profiling = false;
   int mode = 0;                         // 0 auto (fused when possible), 1 layer-by-layer, 2 fused only
+  bool st_act = false;                  // ST-style LeakyReLU tables instead of TFLite's
   int H = 56, W = 56;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -135,7 +136,7 @@ PlanDev* get_plan(Network* n, int H, int W) {
   }
   std::unique_ptr<PlanDev> pd(new PlanDev);
   std::string perr;
-  if (!build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->plan, &perr)) {
+  if (!build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->plan, &perr, 4, n->st_act)) {
     set_text("plan: " + perr); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr;
   }
   Plan& P = pd->plan;
@@ -173,7 +174,7 @@ PlanDev* get_plan(Network* n, int H, int W) {
   pd->step_ms.assign(P.steps.size(), -1.f);
   // fused single-kernel program (falls back to the layered path when it cannot be built)
   std::string ferr;
-  if (build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->fplan, &ferr, 16) &&
+  if (build_plan(n->model, H, W, n->blob.empty() ? nullptr : n->blob.data(), n->blob.size(), &pd->fplan, &ferr, 16, n->st_act) &&
       build_fused(pd->fplan, &pd->fprog) && pd->fprog.ok) {
     if (!cuda_ok(n, cudaMalloc(&pd->d_fparams, pd->fprog.params.size()), "cudaMalloc fused params", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
     if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fparams, pd->fprog.params.data(), pd->fprog.params.size(), cudaMemcpyHostToDevice, n->stream), "upload fused params")) return nullptr;
@@ -503,6 +504,7 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
   if (cfg && cfg->chunk_images) n->chunk = cfg->chunk_images;
   else if (const char* e = std::getenv("YF_B200_CHUNK")) n->chunk = static_cast<uint32_t>(std::max(1, std::atoi(e)));
   n->observer = cfg && (cfg->flags & YF_B200_FLAG_OBSERVER);
+  n->st_act = (cfg && (cfg->flags & YF_B200_FLAG_ST_ACTIVATIONS)) || (std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS")));
   if (cfg && (cfg->flags & YF_B200_FLAG_LAYERED)) n->mode = 1;
   else if (cfg && (cfg->flags & YF_B200_FLAG_FUSED_ONLY)) n->mode = 2;
   else if (const char* e = std::getenv("YF_B200_MODE")) n->mode = !std::strcmp(e, "layered") ? 1 : (!std::strcmp(e, "fused") ? 2 : 0);
@@ -906,7 +908,8 @@ static bool host_plan(int32_t H, int32_t W, const void* blob, Plan* P) {
   if (!ok) return false;
   size_t need = 0; st_blob_layout(model, &need);
   std::string perr;
-  if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr)) { set_text("plan: " + perr); return false; }
+  const bool st = std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS"));
+  if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr, 4, st)) { set_text("plan: " + perr); return false; }
   return true;
 }
 
@@ -961,7 +964,8 @@ static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedPro
   if (!ok) return false;
   size_t need = 0; st_blob_layout(model, &need);
   std::string perr;
-  if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr, 16)) { set_text("plan: " + perr); return false; }
+  const bool st = std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS"));
+  if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr, 16, st)) { set_text("plan: " + perr); return false; }
   build_fused(*P, F);
   if (!F->ok) { set_text("fused: " + F->why); return false; }
   return true;

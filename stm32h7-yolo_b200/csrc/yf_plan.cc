@@ -158,7 +158,7 @@ namespace {
 
 struct Builder {
   const TflModel& m; Plan& P; std::string& err;
-  const uint8_t* blob; size_t blob_len; int slot_align;
+  const uint8_t* blob; size_t blob_len; int slot_align; bool st_act;
   std::vector<std::vector<int>> consumers;           // tensor -> ops
   std::vector<int> th, tw, tc;                       // propagated tensor shapes
   std::vector<char> done;                            // op already folded
@@ -227,8 +227,16 @@ struct Builder {
     int32_t zin = static_cast<int32_t>(m.tensors[O.in[0]].zp[0]), zout = static_cast<int32_t>(m.tensors[O.out].zp[0]);
     int8_t tab[256];
     for (int q = -128; q < 128; ++q) {
-      int32_t v = q - zin;
-      int32_t u = zout + (v >= 0 ? mbqm_host(v, mi, si) : mbqm_host(v, ma, sa));
+      int32_t u;
+      if (st_act) {   // ST: float32 de-quantise, leak, re-quantise with round-half-even (nl_func_array_integer tables)
+        volatile float v = (static_cast<float>(q) - static_cast<float>(zin)) * s_in;
+        if (q < zin) v = v * 0.1f;
+        v = v / s_out;
+        u = static_cast<int32_t>(std::nearbyintf(v)) + zout;
+      } else {
+        int32_t v = q - zin;
+        u = zout + (v >= 0 ? mbqm_host(v, mi, si) : mbqm_host(v, ma, sa));
+      }
       tab[q + 128] = static_cast<int8_t>(std::min(127, std::max(-128, u)));
     }
     return add_lut(tab);
@@ -527,10 +535,10 @@ struct Builder {
 }  // namespace
 
 bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err,
-                int slot_align) {
+                int slot_align, bool st_activations) {
   *plan = Plan{}; plan->H = H; plan->W = W;
   std::string e;
-  Builder b{m, *plan, e, blob, blob_len, slot_align};
+  Builder b{m, *plan, e, blob, blob_len, slot_align, st_activations};
   bool ok = b.run();
   if (!ok && err) *err = e;
   return ok;

@@ -137,8 +137,10 @@ std::vector<uint8_t> st_blob_from_model(const TflModel& m);
 // flatbuffer's weight/bias bytes -- this is how ai_network_init(params) feeds weights.
 // slot_align: alignment (in channels) of concat slots inside their buffer: 4 for the layer-by-layer
 // path (word stores), 16 for the fused kernel (every producer writes whole 16-byte chunks).
+// st_activations: build the LEAKY_RELU tables the way ST's code generator does (float32, round half to even;
+// network.c:2218..2902) instead of TFLite's fixed-point rule -- 271 of 4,352 entries differ by 1 LSB.
 bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blob_len, Plan* plan, std::string* err,
-                int slot_align = 4);
+                int slot_align = 4, bool st_activations = false);
 
 // ------------------------------------------------------------------------------------------------
 // Fused single-kernel program: the same steps executed by one persistent CTA per image with every

@@ -255,3 +255,20 @@ def test_config3_65536_images_with_device_decode_nms(net, oracle, golden):
         assert counts[i] == len(r)
         if len(r):
             assert np.all(np.abs(dets[i, :len(r), :4] - r[:, :4]) <= COORD_TOL) and np.all(np.abs(dets[i, :len(r), 4] - r[:, 4]) <= CONF_TOL)
+
+
+def test_st_activation_mode_on_device(yf, golden, monkeypatch):
+    """ST-style tables on the GPU give exactly what the plan emulator predicts for that plan (both paths)."""
+    from plan_emulator import Emulator
+    monkeypatch.setenv("YF_B200_ST_ACTIVATIONS", "1")
+    P = yf.plan(56, 56)
+    monkeypatch.delenv("YF_B200_ST_ACTIVATIONS")
+    imgs = golden["images"][:6]
+    exp = np.stack([Emulator(P).run(i, observer=False)[1] for i in imgs])
+    for mode in ("fused", "layered"):
+        n = yf.Network(chunk_images=16, mode=mode, st_activations=True)
+        try:
+            assert np.array_equal(n.run(imgs), exp)
+        finally:
+            n.close()
+    assert not np.array_equal(exp, golden["heads_images"][:6])

@@ -139,3 +139,30 @@ def test_fused_program_limits(yf):
     for hw in ((64, 96), (224, 224)):             # a layer's accumulator tiles exceed TMEM / smem -> layered path
         with pytest.raises(RuntimeError):
             yf.fused_program(*hw)
+
+
+def test_st_activation_mode_reproduces_st_tables(yf, oracle, golden, monkeypatch):
+    """SURVEY.md 8f n4: with ST-style activations the 17 LeakyReLU tables equal network.c:2218..2902 exactly;
+    the default (TFLite) tables differ from them in 271 entries."""
+    def leaky_tables(P):
+        out = {}
+        for s in P["steps"]:
+            for op in s["ops"]:
+                if oracle.op(op)["opcode"] == 98:
+                    out[op] = P["luts"][s["lut1"]]
+        return out
+    st = dict(zip(golden["st_lut_ops"].tolist(), golden["st_luts"]))
+    tfl = leaky_tables(yf.plan(56, 56))
+    assert sum(int((tfl[op] != st[op]).sum()) for op in st) == 271
+    monkeypatch.setenv("YF_B200_ST_ACTIVATIONS", "1")
+    stm = leaky_tables(yf.plan(56, 56))
+    assert sorted(stm) == sorted(st)
+    for op in st:
+        assert np.array_equal(stm[op], st[op]), op
+    # and the plan still executes: heads move by a few LSB at most relative to TFLite mode
+    img = golden["images"][2]
+    a = Emulator(yf.plan(56, 56)).run(img, observer=False)
+    monkeypatch.delenv("YF_B200_ST_ACTIVATIONS")
+    b = Emulator(yf.plan(56, 56)).run(img, observer=False)
+    d = np.abs(a[1].astype(int) - b[1].astype(int))
+    assert 0 < d.max() <= 16
