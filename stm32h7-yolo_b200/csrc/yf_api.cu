@@ -480,27 +480,7 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     cfg = static_cast<const yf_b200_config*>(network_config->data);
     if (cfg->magic != YF_B200_CONFIG_MAGIC) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; set_text("network_config is not a yf_b200_config"); return err; }
   }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    set_text("no CUDA device: libyoloface_b200 has no CPU path");
-    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
-  }
-  int dev = -1;
-  if (cfg && cfg->device >= 0) dev = cfg->device;
-  else if (const char* e = std::getenv("YF_B200_DEVICE")) dev = std::atoi(e);
-  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
-  if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return err; }
-  cudaDeviceProp prop{};
-  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-    set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
-  }
-  if (prop.major != 10) {
-    set_text("libyoloface_b200 carries sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
-    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
-  }
   std::unique_ptr<Network> n(new Network);
-  n->device = dev; n->sm_count = prop.multiProcessorCount;
   if (cfg && cfg->chunk_images) n->chunk = cfg->chunk_images;
   else if (const char* e = std::getenv("YF_B200_CHUNK")) n->chunk = static_cast<uint32_t>(std::max(1, std::atoi(e)));
   n->observer = cfg && (cfg->flags & YF_B200_FLAG_OBSERVER);
@@ -521,6 +501,26 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr);
   }
   if (!ok) { set_text("model: " + perr); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; return err; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_text("no CUDA device: libyoloface_b200 has no CPU path");
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  int dev = -1;
+  if (cfg && cfg->device >= 0) dev = cfg->device;
+  else if (const char* e = std::getenv("YF_B200_DEVICE")) dev = std::atoi(e);
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return err; }
+  cudaDeviceProp prop{};
+  if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  if (prop.major != 10) {
+    set_text("libyoloface_b200 carries sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+  }
+  n->device = dev; n->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&n->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&n->s_d2h, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
       cudaEventCreate(&n->ev1) != cudaSuccess || cudaMalloc(&n->d_err, sizeof(int)) != cudaSuccess ||

@@ -31,6 +31,16 @@ __device__ __forceinline__ int32_t requant(int32_t acc, const EpiCh& k) {
   return (t + k.c2 + ((t >> 31) & k.sgn_mask)) >> k.e;     // includes +zp_out, not yet clamped
 }
 __device__ __forceinline__ int32_t clamp_s8(int32_t v) { return max(-128, min(127, v)); }
+// the 32-byte record with two 128-bit loads (shared memory, broadcast)
+__device__ __forceinline__ int32_t requant_smem(int32_t acc, const EpiCh* kp) {
+  const uint4 a = reinterpret_cast<const uint4*>(kp)[0], b = reinterpret_cast<const uint4*>(kp)[1];
+  const long long add64 = static_cast<long long>((static_cast<unsigned long long>(a.y) << 32) | a.x);
+  const int32_t mult = static_cast<int32_t>(a.z), c2 = static_cast<int32_t>(a.w), e = static_cast<int32_t>(b.x), ls = static_cast<int32_t>(b.y),
+                sgn = static_cast<int32_t>(b.z);
+  const long long p = static_cast<long long>(acc << ls) * static_cast<long long>(mult) + add64;
+  const int32_t t = static_cast<int32_t>(p >> 31);
+  return (t + c2 + ((t >> 31) & sgn)) >> e;
+}
 // MultiplyByQuantizedMultiplier for shift <= 0 (used by the fused ADD only)
 __device__ __forceinline__ int32_t mbqm_dev(int32_t x, int32_t m, int s) {
   const long long ab = static_cast<long long>(x) * static_cast<long long>(m);
@@ -82,7 +92,7 @@ __device__ __forceinline__ void store_row(int8_t* dst, const uint32_t (&w)[NW], 
 // sLut: smem copy of table 1 at [0,256) and table 2 at [256,512).
 template <int NPAD>
 __device__ __forceinline__ void epilogue_row(const uint32_t (&acc)[NPAD], const EpiOut& eo, long long row,
-                                             const uint8_t* sLut) {
+                                             const uint8_t* sLut, const EpiCh* sEpi) {
   uint32_t outw[NPAD / 4], raww[NPAD / 4], midw[NPAD / 4];
 #pragma unroll
   for (int i = 0; i < NPAD / 4; ++i) { outw[i] = 0; raww[i] = 0; midw[i] = 0; }
@@ -90,7 +100,7 @@ __device__ __forceinline__ void epilogue_row(const uint32_t (&acc)[NPAD], const 
 #pragma unroll
   for (int c = 0; c < NPAD; ++c) {
     if (c < eo.cout) {
-      int32_t y = clamp_s8(requant(static_cast<int32_t>(acc[c]), c_epi[eo.epi_base + c]));
+      int32_t y = clamp_s8(requant_smem(static_cast<int32_t>(acc[c]), sEpi + c));   // broadcast LDS.128 x2 (runtime-indexed LDC is slow)
       raww[c / 4] |= static_cast<uint32_t>(y & 0xff) << (8 * (c % 4));
       if (eo.add.enabled) y = add_dev(static_cast<int32_t>(addp[c]), y, eo.add);
       if (eo.lut1) y = static_cast<int8_t>(sLut[y + 128]);
@@ -105,6 +115,10 @@ __device__ __forceinline__ void epilogue_row(const uint32_t (&acc)[NPAD], const 
   if (eo.mid) store_row<NPAD / 4>(eo.mid + row * eo.mid_pitch, midw, eo.cout);
 }
 
+template <int NPAD>
+__device__ __forceinline__ void load_epi(EpiCh* sEpi, const EpiOut& eo, int tid, int nthreads) {
+  for (int i = tid; i < NPAD; i += nthreads) sEpi[i] = c_epi[eo.epi_base + (i < eo.cout ? i : 0)];
+}
 __device__ __forceinline__ void load_luts(uint8_t* sLut, const EpiOut& eo, int tid, int nthreads) {
   for (int i = tid; i < 128; i += nthreads) {
     reinterpret_cast<uint32_t*>(sLut)[i] =
@@ -132,7 +146,7 @@ constexpr int kStageBytes = 8192;       // 4 K-chunks x 128 rows x 16 B
 constexpr int kGemmThreads = 192;
 
 template <int NPAD>
-constexpr int gemm_smem_bytes() { return kGemmStages * kStageBytes + 4 * NPAD * 16 + 512 + 16 * 8 + 16; }
+constexpr int gemm_smem_bytes() { return kGemmStages * kStageBytes + 4 * NPAD * 16 + 512 + 16 * 8 + 16 + NPAD * 32 + 16; }
 template <int NPAD>
 __host__ __device__ constexpr uint32_t tmem_cols() { return 2 * NPAD <= 32 ? 32 : (2 * NPAD <= 64 ? 64 : (2 * NPAD <= 128 ? 128 : 256)); }
 
@@ -146,7 +160,9 @@ conv1x1_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const Conv1x1A
   uint64_t* bars = reinterpret_cast<uint64_t*>(sLut + 512);
   uint64_t* full = bars; uint64_t* empty = bars + 4; uint64_t* tfull = bars + 8; uint64_t* tempty = bars + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  EpiCh* sEpi = reinterpret_cast<EpiCh*>(reinterpret_cast<uint8_t*>(bars + 16) + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_epi<NPAD>(sEpi, p.eo, threadIdx.x, kGemmThreads);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmapA);
@@ -215,7 +231,7 @@ conv1x1_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const Conv1x1A
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       const long long row = static_cast<long long>(tile) * 128 + q * 32 + lane;
-      if (row < p.M) epilogue_row<NPAD>(acc, p.eo, row, sLut);
+      if (row < p.M) epilogue_row<NPAD>(acc, p.eo, row, sLut, sEpi);
     }
   }
   tc_fence_before();
@@ -234,7 +250,7 @@ constexpr int kBandSlotBytes = 16384 + 2048;
 constexpr int kIm2colStages = 4;
 constexpr int kIm2colThreads = 320;
 template <int NPAD>
-constexpr int im2col_smem_bytes() { return 2 * kBandSlotBytes + kIm2colStages * 4096 + 2 * NPAD * 16 + 512 + 24 * 8 + 16; }
+constexpr int im2col_smem_bytes() { return 2 * kBandSlotBytes + kIm2colStages * 4096 + 2 * NPAD * 16 + 512 + 24 * 8 + 16 + NPAD * 32 + 16; }
 
 template <int NPAD>
 __global__ void __launch_bounds__(kIm2colThreads)
@@ -248,7 +264,9 @@ conv_im2col_tcgen05_kernel(const ConvIm2colArgs p) {
   uint64_t* bfull = bars; uint64_t* bempty = bars + 2;
   uint64_t* afull = bars + 4; uint64_t* aempty = bars + 8; uint64_t* tfull = bars + 12; uint64_t* tempty = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  EpiCh* sEpi = reinterpret_cast<EpiCh*>(reinterpret_cast<uint8_t*>(bars + 24) + 16);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_epi<NPAD>(sEpi, p.eo, threadIdx.x, kIm2colThreads);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 4); mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
@@ -336,7 +354,7 @@ conv_im2col_tcgen05_kernel(const ConvIm2colArgs p) {
         const int r = t * 128 + q * 32 + lane;
         if (r < npix) {
           const long long row = (static_cast<long long>(img) * p.Hout + oy0) * p.Wout + r;
-          epilogue_row<NPAD>(acc, p.eo, row, sLut);
+          epilogue_row<NPAD>(acc, p.eo, row, sLut, sEpi);
         }
       }
     }
@@ -479,10 +497,23 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
     const int8_t* base = p.in + img * p.Hin * p.Win * p.in_pitch + wq * 4;
     const int y0 = max(0, oy * p.stride - p.pad_t), y1 = min(p.Hin, oy * p.stride - p.pad_t + p.k);
     const int x0 = max(0, ox * p.stride - p.pad_l), x1 = min(p.Win, ox * p.stride - p.pad_l + p.k);
-    uint32_t m = 0x80808080u;
-    for (int iy = y0; iy < y1; ++iy)
-      for (int ix = x0; ix < x1; ++ix)
-        m = __vmaxs4(m, __ldg(reinterpret_cast<const uint32_t*>(base + (static_cast<long long>(iy) * p.Win + ix) * p.in_pitch)));
+    // max on sign-unpacked 16-bit lanes (VIMNMX.S16x2 is native; __vmaxs4 is a 6-instruction emulation on sm_100)
+    uint32_t ev = __byte_perm(0x80808080u, 0u, 0xA280u), od = __byte_perm(0x80808080u, 0u, 0xB391u);
+    for (int iy = y0; iy < y1; ++iy) {
+      const int8_t* rowp = base + static_cast<long long>(iy) * p.Win * p.in_pitch;
+      int ix = x0;
+      for (; ix + 1 < x1; ix += 2) {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(rowp + static_cast<long long>(ix) * p.in_pitch));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(rowp + static_cast<long long>(ix + 1) * p.in_pitch));
+        ev = __vimax3_s16x2(ev, __byte_perm(a, 0u, 0xA280u), __byte_perm(b, 0u, 0xA280u));
+        od = __vimax3_s16x2(od, __byte_perm(a, 0u, 0xB391u), __byte_perm(b, 0u, 0xB391u));
+      }
+      if (ix < x1) {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(rowp + static_cast<long long>(ix) * p.in_pitch));
+        ev = __vmaxs2(ev, __byte_perm(a, 0u, 0xA280u)); od = __vmaxs2(od, __byte_perm(a, 0u, 0xB391u));
+      }
+    }
+    const uint32_t m = __byte_perm(ev, od, 0x6240u);
     int32_t y[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) y[j] = static_cast<int8_t>((m >> (8 * j)) & 0xff);
@@ -628,7 +659,8 @@ __global__ void __launch_bounds__(256) prep_rgb565_kernel(const PrepArgs p) {
 // ------------------------------------------------------------------------------------------
 template <int NPAD>
 static cudaError_t launch_conv1x1_t(const CUtensorMap& tmapA, const Conv1x1Args& a, int sm_count, cudaStream_t s) {
-  const int grid = a.num_tiles < sm_count * 4 ? a.num_tiles : sm_count * 4;
+  const int per_sm = 4;                                      // 6 CTAs/SM (possible for N <= 32) measured slower
+  const int grid = a.num_tiles < sm_count * per_sm ? a.num_tiles : sm_count * per_sm;
   conv1x1_tcgen05_kernel<NPAD><<<grid, kGemmThreads, gemm_smem_bytes<NPAD>(), s>>>(tmapA, a);
   return cudaGetLastError();
 }

@@ -52,11 +52,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // callers record the failure in a global error word and drain.
 static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
+  unsigned ns = 32;
 #pragma unroll 1
   for (;;) {
 #pragma unroll 1
-    for (int i = 0; i < 64; ++i)
+    for (int i = 0; i < 32; ++i) {
       if (mbar_try_wait(bar, parity)) return true;
+      __nanosleep(ns);                       // long waits (layer kernels' producer / MMA lanes) must not steal issue slots
+    }
+    if (ns < 256) ns <<= 1;
     if (clock64() - t0 > (1ll << 32)) return false;
   }
 }

@@ -72,13 +72,15 @@ int main(int argc, char** argv) {
   if (aiRun(in_data, out_data, n)) return 1;
   if (yf_b200_decode(network, out_data, n, conf, iou, 0, dets, counts, max_det) < 0) { printf("E: decode: %s\r\n", yf_b200_last_error_text()); return 1; }
 
-  for (unsigned f = 0; f < n; ++f) {
-    printf("=== Frame %u ===\r\n", f);
+  for (unsigned f = 0; f < n; ++f) {                          /* main.c:46,53 + yoloface.c:143-148: clamp to the frame, double */
+    printf("=== Frame %u ===\r\n----------------------------------------\r\n", f);
     for (int k = 0; k < counts[f]; ++k) {
       const yf_b200_det* d = &dets[(size_t)f * max_det + k];
-      printf("[Face %d] BBox: [%d, %d, %d, %d], Conf: %.2f\r\n", k + 1, (int)(d->x1 * 2), (int)(d->y1 * 2), (int)(d->x2 * 2), (int)(d->y2 * 2), d->conf);
+      int c[4] = {(int)d->x1, (int)d->y1, (int)d->x2, (int)d->y2};
+      for (int j = 0; j < 4; ++j) c[j] = (c[j] < 0 ? 0 : (c[j] > 55 ? 55 : c[j])) * 2;
+      printf("[Face %d] BBox: [%d, %d, %d, %d], Conf: %.2f\r\n", k + 1, c[0], c[1], c[2], c[3], d->conf);
     }
-    printf("[INFO] Total faces detected: %d\r\n", counts[f]);
+    printf("----------------------------------------\r\n[INFO] Total faces detected: %d\r\n", counts[f]);
   }
   yf_b200_stats st;
   yf_b200_get_stats(network, &st);
