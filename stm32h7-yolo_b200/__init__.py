@@ -73,7 +73,7 @@ EXPORTS = [
     "ai_network_data_params_get", "yf_b200_set_input_size", "yf_b200_run", "yf_b200_decode", "yf_b200_detect",
     "yf_b200_preprocess_rgb565", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
     "yf_b200_get_stats", "yf_b200_step_count", "yf_b200_step_info_get", "yf_b200_set_step_profiling",
-    "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
+    "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_enqueue_batches", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
 ]
 
 _lib = None
@@ -120,6 +120,8 @@ def lib():
     L.yf_b200_set_stream.argtypes = [vp, vp]
     L.yf_b200_enqueue.restype = i32
     L.yf_b200_enqueue.argtypes = [vp, vp, vp, u32]
+    L.yf_b200_enqueue_batches.restype = i32
+    L.yf_b200_enqueue_batches.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32), u32]
     L.yf_b200_submit.restype = i32
     L.yf_b200_submit.argtypes = [vp, vp, vp, u32]
     L.yf_b200_wait.restype = i32
@@ -320,6 +322,15 @@ class Network:
         """Queue n device-resident images without synchronising (torch CUDA tensors or addresses)."""
         if self.L.yf_b200_enqueue(self.handle, _ptr(d_in)[0], _ptr(d_out)[0], n) != n:
             self._raise("yf_b200_enqueue")
+
+    def enqueue_batches(self, d_ins, d_outs, counts):
+        """Queue several independent device-resident batches; they may overlap each other on the GPU."""
+        k = len(counts)
+        ins = (C.c_void_p * k)(*[_ptr(x)[0] for x in d_ins])
+        outs = (C.c_void_p * k)(*[_ptr(x)[0] for x in d_outs])
+        cnt = (C.c_uint32 * k)(*[int(c) for c in counts])
+        if self.L.yf_b200_enqueue_batches(self.handle, ins, outs, cnt, k) != sum(int(c) for c in counts):
+            self._raise("yf_b200_enqueue_batches")
 
     def submit(self, in_host, out_host, n):
         """Queue n images from host memory (H2D, kernels, D2H pipelined over a ring); pair with wait()."""

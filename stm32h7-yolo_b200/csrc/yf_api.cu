@@ -80,6 +80,12 @@ struct Network {
   std::map<std::pair<int, int>, std::unique_ptr<PlanDev>> plans;
   cudaStream_t own_stream = nullptr;    // created by the library; `stream` may be a caller's
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
+  // Kernel lanes: one fused launch covers 256 of the GPU's 296 CTA slots for one image latency, so
+  // independent chunks alternate over two streams and the head of one overlaps the tail of the other.
+  static constexpr int kLanes = 2;
+  cudaStream_t lane[kLanes] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {nullptr, nullptr};
+  uint64_t lane_seq = 0;
   uint32_t last_run_n = 0;
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
@@ -184,6 +190,7 @@ PlanDev* get_plan(Network* n, int H, int W) {
     if (pd->fprog.why.empty()) pd->fprog.why = ferr;
   }
   if (n->mode == 2 && !pd->fprog.ok) { set_text("fused path unavailable: " + pd->fprog.why); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr; }
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "plan upload")) return nullptr;   // lanes read these buffers too
   PlanDev* raw = pd.get();
   n->plans[key] = std::move(pd);
   return raw;
@@ -224,16 +231,22 @@ EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* 
 }
 
 // run the fused steps for nb images whose input is at d_in (device) writing heads to d_head (device)
-bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb) {
+// true when chunks of this plan go through the single fused kernel (no shared activation arena:
+// independent chunks may then run concurrently)
+bool uses_fused(const Network* n, const PlanDev* pd) { return !pd->observer && !n->step_profiling && n->mode != 1 && pd->fprog.ok; }
+
+bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb, cudaStream_t st = nullptr) {
   const Plan& P = pd->plan;
-  if (!pd->observer && !n->step_profiling && n->mode != 1 && pd->fprog.ok) {
+  if (!st) st = n->stream;
+  if (uses_fused(n, pd)) {
     if (g_active_fused[n->device & 63] != pd) {
       if (!cuda_ok(n, cudaDeviceSynchronize(), "synchronize before table switch")) return false;
       if (!cuda_ok(n, upload_fused_tables(pd->fplan.epi.data(), static_cast<int>(pd->fplan.epi.size()), pd->fprog.phases.data(),
                                           static_cast<int>(pd->fprog.phases.size()), n->stream), "upload fused tables")) return false;
+      if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "upload fused tables")) return false;   // visible to every lane
       g_active_fused[n->device & 63] = pd;
     }
-    if (!cuda_ok(n, launch_fused(pd->fprog, d_in, d_head, pd->d_fparams, static_cast<int>(nb), n->sm_count, n->d_err, n->stream,
+    if (!cuda_ok(n, launch_fused(pd->fprog, d_in, d_head, pd->d_fparams, static_cast<int>(nb), n->sm_count, n->d_err, st,
                                  n->trace_on ? n->d_trace : nullptr), "fused kernel")) return false;
     ++n->launches;
     return true;
@@ -241,7 +254,7 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
   if (g_active_epi[n->device & 63] != pd) {
     // the table is shared by every context on this device: order the overwrite after prior work
     if (!cuda_ok(n, cudaDeviceSynchronize(), "synchronize before table switch")) return false;
-    if (!cuda_ok(n, upload_epi_table(P.epi.data(), static_cast<int>(P.epi.size()), n->stream), "upload epilogue table")) return false;
+    if (!cuda_ok(n, upload_epi_table(P.epi.data(), static_cast<int>(P.epi.size()), st), "upload epilogue table")) return false;
     g_active_epi[n->device & 63] = pd;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -250,7 +263,7 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
     const Step& s = P.steps[i];
     const EpiOut eo = make_epi_out(pd, s, d_in, d_head);
     cudaError_t e = cudaSuccess;
-    if (n->step_profiling) cudaEventRecord(e0, n->stream);
+    if (n->step_profiling) cudaEventRecord(e0, st);
     switch (s.kind) {
       case STEP_CONV1X1: {
         Conv1x1Args a{};
@@ -258,14 +271,14 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
         a.nchunk = P.buffers[s.in_buf].CP / 16; a.nk = s.Kpad / 32;
         a.M = static_cast<long long>(nb) * s.Hout * s.Wout; a.num_tiles = static_cast<int>((a.M + 127) / 128);
         a.eo = eo; a.err = n->d_err;
-        e = launch_conv1x1(pd->tmaps[i], a, s.Npad, n->sm_count, n->stream);
+        e = launch_conv1x1(pd->tmaps[i], a, s.Npad, n->sm_count, st);
         break; }
       case STEP_CONV_IM2COL: {
         ConvIm2colArgs a{};
         a.in = d_in; a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
         a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
         a.band_rows = s.band_rows; a.bands = s.bands; a.in_zp = s.in_zp; a.eo = eo; a.err = n->d_err;
-        e = launch_conv_im2col(a, s.Npad, n->sm_count, n->stream);
+        e = launch_conv_im2col(a, s.Npad, n->sm_count, st);
         break; }
       case STEP_DW: {
         DwArgs a{};
@@ -273,26 +286,26 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
         a.w1h = reinterpret_cast<const uint32_t*>(pd->d_wblob + s.w_off);
         a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
         a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.in_zp = s.in_zp; a.words = (s.Cout + 3) / 4; a.eo = eo;
-        e = launch_dw(a, n->stream);
+        e = launch_dw(a, st);
         break; }
       case STEP_MAXPOOL: {
         PoolArgs a{};
         a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP;
         a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
         a.k = s.kh; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.words = (s.Cout + 3) / 4; a.eo = eo;
-        e = launch_pool(a, n->stream);
+        e = launch_pool(a, st);
         break; }
       case STEP_LUT: {
         LutArgs a{};
         a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP; a.in_coff = s.in_coff;
         a.rows = static_cast<long long>(nb) * s.Hout * s.Wout; a.words = (s.Cout + 3) / 4; a.eo = eo;
-        e = launch_lut(a, n->stream);
+        e = launch_lut(a, st);
         break; }
     }
     if (!cuda_ok(n, e, s.name.c_str())) return false;
     ++n->launches;
     if (n->step_profiling) {
-      cudaEventRecord(e1, n->stream); cudaEventSynchronize(e1);
+      cudaEventRecord(e1, st); cudaEventSynchronize(e1);
       float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); pd->step_ms[i] = ms;
     }
   }
@@ -313,7 +326,27 @@ bool check_device_err(Network* n) {
   return true;
 }
 
-// ---- pipelined host path: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h) over a ring of staging slots ----
+// ---- independent device-resident chunks: fork from n->stream over the kernel lanes, join back ----
+struct DevChunk { const int8_t* in; int8_t* out; uint32_t nb; };
+bool run_chunks(Network* n, PlanDev* pd, const std::vector<DevChunk>& ch) {
+  if (ch.size() < 2 || !uses_fused(n, pd)) {
+    for (const DevChunk& c : ch) { if (!run_steps(n, pd, c.in, c.out, c.nb)) return false; n->last_run_n = c.nb; }
+    return true;
+  }
+  if (!cuda_ok(n, cudaEventRecord(n->ev_fork, n->stream), "fork")) return false;
+  for (int l = 0; l < Network::kLanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
+  for (size_t i = 0; i < ch.size(); ++i) {
+    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[i % Network::kLanes])) return false;
+    n->last_run_n = ch[i].nb;
+  }
+  for (int l = 0; l < Network::kLanes; ++l) {
+    cudaEventRecord(n->ev_join[l], n->lane[l]);
+    if (!cuda_ok(n, cudaStreamWaitEvent(n->stream, n->ev_join[l], 0), "join")) return false;
+  }
+  return true;
+}
+
+// ---- pipelined host path: H2D (s_h2d) -> kernels (lanes) -> D2H (s_d2h) over a ring of staging slots ----
 bool ring_prepare(Network* n, PlanDev* pd) {
   if (pd->ev_h2d[0]) return true;
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3 * pd->cap, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18 * pd->cap;
@@ -335,9 +368,10 @@ bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_hos
   if (pd->busy[s] && !cuda_ok(n, cudaEventSynchronize(pd->ev_d2h[s]), "ring slot wait")) return false;   // slot's previous user has drained
   if (!cuda_ok(n, cudaMemcpyAsync(pd->r_in[s], in_host, nb * in_sz, cudaMemcpyHostToDevice, n->s_h2d), "H2D input", AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
   cudaEventRecord(pd->ev_h2d[s], n->s_h2d);
-  cudaStreamWaitEvent(n->stream, pd->ev_h2d[s], 0);
-  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb)) return false;
-  cudaEventRecord(pd->ev_comp[s], n->stream);
+  cudaStream_t ks = uses_fused(n, pd) ? n->lane[n->lane_seq++ % Network::kLanes] : n->stream;
+  cudaStreamWaitEvent(ks, pd->ev_h2d[s], 0);
+  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb, ks)) return false;
+  cudaEventRecord(pd->ev_comp[s], ks);
   cudaStreamWaitEvent(n->s_d2h, pd->ev_comp[s], 0);
   if (out_host && !cuda_ok(n, cudaMemcpyAsync(out_host, pd->r_head[s], nb * out_sz, cudaMemcpyDeviceToHost, n->s_d2h), "D2H output", AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
   cudaEventRecord(pd->ev_d2h[s], n->s_d2h);
@@ -524,6 +558,9 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
   if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&n->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&n->s_d2h, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
       cudaEventCreate(&n->ev1) != cudaSuccess || cudaMalloc(&n->d_err, sizeof(int)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&n->lane[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&n->lane[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&n->ev_join[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_join[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaMemset(n->d_err, 0, sizeof(int)) != cudaSuccess || kernels_init() != cudaSuccess) {
     set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
     err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
@@ -540,6 +577,8 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   if (!n) return network;
   cudaSetDevice(n->device);
   cudaStreamSynchronize(n->stream);
+  for (int l = 0; l < Network::kLanes; ++l) cudaStreamSynchronize(n->lane[l]);
+  cudaStreamSynchronize(n->s_d2h);
   for (auto& kv : n->plans) {
     if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
     if (g_active_fused[n->device & 63] == kv.second.get()) g_active_fused[n->device & 63] = nullptr;
@@ -547,6 +586,8 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   n->plans.clear();
   cudaFree(n->d_trace); cudaFree(n->d_err); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
   cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream); cudaStreamDestroy(n->s_h2d); cudaStreamDestroy(n->s_d2h);
+  for (int l = 0; l < Network::kLanes; ++l) { cudaStreamDestroy(n->lane[l]); cudaEventDestroy(n->ev_join[l]); }
+  cudaEventDestroy(n->ev_fork);
   g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end());
   delete n;
   return AI_HANDLE_NULL;
@@ -690,13 +731,33 @@ AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* 
   if (!d_out) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
-  for (uint32_t done = 0; done < count; done += pd->cap) {
-    const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
-    if (!run_steps(n, pd, static_cast<const int8_t*>(d_in) + done * in_sz, static_cast<int8_t*>(d_out) + done * out_sz, nb)) return -1;
-    n->last_run_n = nb;
-  }
+  std::vector<DevChunk> ch;
+  for (uint32_t done = 0; done < count; done += pd->cap)
+    ch.push_back({static_cast<const int8_t*>(d_in) + done * in_sz, static_cast<int8_t*>(d_out) + done * out_sz, std::min<uint32_t>(pd->cap, count - done)});
+  if (!run_chunks(n, pd, ch)) return -1;
   n->images += count;
   return static_cast<int32_t>(count);
+}
+
+AI_API_ENTRY int32_t yf_b200_enqueue_batches(ai_handle network, const void* const* d_in, void* const* d_out, const uint32_t* counts, uint32_t n_batches) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!d_in || !d_out || !counts) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  std::vector<DevChunk> ch;
+  uint64_t total = 0;
+  for (uint32_t b = 0; b < n_batches; ++b) {
+    if (!d_in[b] || (reinterpret_cast<uintptr_t>(d_in[b]) & 15)) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+    if (!d_out[b]) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+    for (uint32_t done = 0; done < counts[b]; done += pd->cap)
+      ch.push_back({static_cast<const int8_t*>(d_in[b]) + done * in_sz, static_cast<int8_t*>(d_out[b]) + done * out_sz, std::min<uint32_t>(pd->cap, counts[b] - done)});
+    total += counts[b];
+  }
+  if (total > 0x7fffffffull) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_OUT_OF_RANGE); return -1; }
+  if (!run_chunks(n, pd, ch)) return -1;
+  n->images += total;
+  return static_cast<int32_t>(total);
 }
 
 AI_API_ENTRY int32_t yf_b200_submit(ai_handle network, const void* in_host, void* out_host, uint32_t count) {

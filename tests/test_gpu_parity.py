@@ -31,6 +31,10 @@ def net(yf, request):
     n.close()
 
 
+def net_mode(net):
+    return "fused" if net.stats()["fused"] else "layered"
+
+
 def real_batch(golden, n, seed):
     rng = np.random.default_rng(seed)
     x = rng.integers(-128, 128, (n, 56, 56, 3), dtype=np.int8)
@@ -131,6 +135,41 @@ def test_device_pointers(yf, net, oracle, golden):
     # pinned host input
     xp = torch.from_numpy(x).pin_memory()
     assert np.array_equal(net.run(xp, n=300), od.cpu().numpy())
+
+
+def test_enqueue_batches_overlapping_lanes(yf, net, oracle, golden):
+    """Independent batches queued in one call may overlap on the GPU (two kernel lanes); each must
+    still equal the oracle, and work queued on the stream afterwards must see all of them finished."""
+    torch = pytest.importorskip("torch")
+    sizes = [256, 1, 600, 17, 256, 64, 129]                 # 600 > the fixture's 512-image chunk: split too
+    xs = [real_batch(golden, n, 40 + i) for i, n in enumerate(sizes)]
+    stream = torch.cuda.Stream()
+    net.set_stream(stream.cuda_stream)
+    try:
+        with torch.cuda.stream(stream):
+            d_in = [torch.from_numpy(x).cuda() for x in xs]
+            d_out = [torch.full((n, 7, 7, 18), 99, dtype=torch.int8, device="cuda") for n in sizes]
+            stream.synchronize()
+            for rep in range(3):                            # back-to-back groups on the same stream
+                net.enqueue_batches(d_in, d_out, sizes)
+            gathered = torch.cat([o.reshape(-1) for o in d_out])      # torch kernel queued behind the join
+        net.sync()
+        stream.synchronize()
+    finally:
+        net.set_stream(None)
+    want = np.concatenate([oracle.run_batch(x, threads=os.cpu_count()).reshape(-1) for x in xs])
+    assert np.array_equal(gathered.cpu().numpy(), want)
+    # one big batch over several chunks takes the same route through yf_b200_enqueue
+    small = yf.Network(chunk_images=64, mode=net_mode(net))
+    try:
+        x = real_batch(golden, 333, 77)
+        xd = torch.from_numpy(x).cuda(); od = torch.empty((333, 7, 7, 18), dtype=torch.int8, device="cuda")
+        torch.cuda.synchronize()
+        small.enqueue(xd, od, 333); small.sync()
+        assert np.array_equal(od.cpu().numpy(), oracle.run_batch(x, threads=os.cpu_count()))
+        assert small.stats()["kernel_launches"] == (6 if small.stats()["fused"] else 6 * 26)
+    finally:
+        small.close()
 
 
 def test_decode_and_nms_match_oracle(net, oracle, golden):
