@@ -182,7 +182,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---------------- device-resident throughput (`value`) ----------------
     # The K steps are K independent batches: they go to the stream in ONE yf_b200_enqueue_batches call, which
-    # spreads them over the library's two kernel lanes (one 256-image launch fills 256 of the 296 CTA slots, so
+    # spreads them over the library's four kernel lanes (one 256-image launch fills 256 of the 444 CTA slots, so
     # the head of step k+1 runs in the slots step k leaves idle).  `serial` below is the same K steps queued one
     # yf_b200_enqueue at a time on a single stream (no overlap between steps).
     def step_lists(k0, k):
@@ -234,7 +234,7 @@ def run_ours(args, rank, local_rank, world):
     h_in = [torch.empty((BATCH, 56, 56, 3), dtype=torch.int8).pin_memory() for _ in range(RING)]
     for i, t in enumerate(h_in):
         t.copy_(d_in[i])
-    h_out = [torch.empty((BATCH, 7, 7, 18), dtype=torch.int8).pin_memory() for _ in range(4)]
+    h_out = [torch.empty((BATCH, 7, 7, 18), dtype=torch.int8).pin_memory() for _ in range(8)]
     for k in range(max(args.warmup, 3)):
         net.run(h_in[k % RING], h_out[0], n=BATCH)
     # (a) blocking call per step: H2D + kernel(s) + D2H, returns when the heads are in host memory
@@ -245,14 +245,14 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     dt_block = max_over_ranks(time.perf_counter() - t0)
     # (b) the pipelined API: every step still copies its own inputs in and its own heads out, but the copy of
-    #     step k+1 overlaps the kernels of step k (three streams, ring of staging slots)
+    #     step k+1 overlaps the kernels of step k (copy streams + four kernel lanes, ring of six staging slots)
     for k in range(3):
-        net.submit(h_in[k % RING], h_out[k % 4], BATCH)
+        net.submit(h_in[k % RING], h_out[k % 8], BATCH)
     net.wait()
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        net.submit(h_in[k % RING], h_out[k % 4], BATCH)
+        net.submit(h_in[k % RING], h_out[k % 8], BATCH)
     net.wait()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -264,7 +264,7 @@ def run_ours(args, rank, local_rank, world):
     # sanity: the e2e result of the last step equals the device-resident result for that input
     last = (args.steps - 1) % RING
     net.run(d_in[last], d_out[last], n=BATCH)
-    assert torch.equal(h_out[(args.steps - 1) % 4], d_out[last].cpu()), "host-path and device-path heads differ"
+    assert torch.equal(h_out[(args.steps - 1) % 8], d_out[last].cpu()), "host-path and device-path heads differ"
 
     # ---------------- roofline of the dominant kernel ----------------
     roofline, per_step = None, []

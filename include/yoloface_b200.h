@@ -61,15 +61,15 @@ AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* 
 AI_API_ENTRY int32_t yf_b200_sync(ai_handle network);
 /* Several independent device-resident batches in one call (batch b: counts[b] images at d_in[b] ->
  * d_out[b]).  The batches are ordered after earlier work on the stream and before later work, but not
- * among themselves: the library spreads them over two internal kernel lanes, so the first CTAs of one
- * batch fill the SM slots the previous batch leaves idle (one 256-image launch occupies 256 of the 296
+ * among themselves: the library spreads them over four internal kernel lanes, so the first CTAs of one
+ * batch fill the SM slots the previous batches leave idle (one 256-image launch occupies 256 of the 444
  * resident-CTA slots).  yf_b200_enqueue does the same for the chunks of one large batch.  Returns the
  * number of images queued. */
 AI_API_ENTRY int32_t yf_b200_enqueue_batches(ai_handle network, const void* const* d_in, void* const* d_out,
                                              const uint32_t* counts, uint32_t n_batches);
 
 /* Pipelined host path: yf_b200_submit queues n images from (preferably page-locked) host memory --
- * H2D copy, kernels (alternating over two lanes) and D2H copy of the heads run on separate streams over a
+ * H2D copy, kernels (alternating over four lanes) and D2H copy of the heads run on separate streams over a
  * ring of staging slots, so the copies of one submission overlap the kernels of its neighbours -- and
  * returns without waiting;
  * yf_b200_wait blocks until every submitted result is in `out_host` and reports pipeline errors.

@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libyoloface_b200.so")
+LIB_PATH = os.environ.get("YF_B200_LIB") or os.path.join(PKG_DIR, "libyoloface_b200.so")   # YF_B200_LIB: e.g. the TRACE=1 twin
 
 # ---- ABI structs (include/ai_platform.h) ------------------------------------------------------
 AI_BUFFER_FORMAT_S8 = (1 << 23) | (2 << 17) | (8 << 7) | 64

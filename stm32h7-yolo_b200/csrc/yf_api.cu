@@ -42,11 +42,11 @@ struct PlanDev {
   uint8_t* d_arena = nullptr;
   int8_t* d_in = nullptr;               // staging for host inputs [cap,H,W,3]      (= ring slot 0)
   int8_t* d_head = nullptr;             // staging for host outputs [cap,GH,GW,18] (= ring slot 0)
-  static constexpr int kRing = 3;       // pipelined host path: slots of (input, head) staging + events
-  int8_t* r_in[kRing] = {nullptr, nullptr, nullptr};
-  int8_t* r_head[kRing] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_h2d[kRing] = {nullptr, nullptr, nullptr}, ev_comp[kRing] = {nullptr, nullptr, nullptr}, ev_d2h[kRing] = {nullptr, nullptr, nullptr};
-  bool busy[kRing] = {false, false, false};
+  static constexpr int kRing = 6;       // pipelined host path: slots of (input, head) staging + events
+  int8_t* r_in[kRing] = {};
+  int8_t* r_head[kRing] = {};
+  cudaEvent_t ev_h2d[kRing] = {}, ev_comp[kRing] = {}, ev_d2h[kRing] = {};
+  bool busy[kRing] = {};
   uint64_t seq = 0;
   std::vector<CUtensorMap> tmaps;       // per step (conv1x1 only)
   std::vector<float> step_ms;
@@ -82,15 +82,22 @@ struct Network {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
   // Kernel lanes: one fused launch covers 256 of the GPU's 296 CTA slots for one image latency, so
   // independent chunks alternate over two streams and the head of one overlaps the tail of the other.
-  static constexpr int kLanes = 2;
-  cudaStream_t lane[kLanes] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {nullptr, nullptr};
+  static constexpr int kLanes = 4;      // 4 x 256 queued CTAs keep the 444 resident-CTA slots busy
+  cudaStream_t lane[kLanes] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {};
   uint64_t lane_seq = 0;
   uint32_t last_run_n = 0;
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
   void latch(int type, int code) { if (err.type == AI_ERROR_NONE) { err.type = type; err.code = code; } }
 };
+
+bool make_lanes(Network* n) {
+  for (int l = 0; l < Network::kLanes; ++l)
+    if (cudaStreamCreateWithFlags(&n->lane[l], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n->ev_join[l], cudaEventDisableTiming) != cudaSuccess) return false;
+  return cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+}
 
 std::mutex g_mu;
 // ST's runtime has one static context (g_network, network.c:36); a GPU process may want one per
@@ -558,9 +565,7 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
   if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&n->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&n->s_d2h, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&n->ev0) != cudaSuccess ||
       cudaEventCreate(&n->ev1) != cudaSuccess || cudaMalloc(&n->d_err, sizeof(int)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&n->lane[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&n->lane[1], cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&n->ev_join[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&n->ev_join[1], cudaEventDisableTiming) != cudaSuccess ||
+      !make_lanes(n.get()) ||
       cudaMemset(n->d_err, 0, sizeof(int)) != cudaSuccess || kernels_init() != cudaSuccess) {
     set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
     err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
@@ -1039,7 +1044,8 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
   auto kv = [&](const char* k, long long v, bool comma = true) { j += std::string("\"") + k + "\":" + std::to_string(v) + (comma ? "," : ""); };
   kv("in_off", F.in_off); kv("in_bytes", F.in_bytes); kv("arena_off", F.arena_off); kv("arena_bytes", F.arena_bytes);
   kv("slot_off", F.slot_off); kv("slot_bytes", F.slot_bytes); kv("smem_bytes", F.smem_bytes); kv("head_bytes", F.head_bytes);
-  kv("warpgroups", kFusedWarpgroups);
+  kv("warpgroups", kFusedWarpgroups); kv("tmem_cols", kFusedTmemCols); kv("param_slots", kFusedParamSlots); kv("desc_off", F.desc_off);
+  kv("in_pf_phase", F.in_pf_phase);
   j += "\"phases\":[";
   for (size_t i = 0; i < F.phases.size(); ++i) {
     const FusedPhase& p = F.phases[i];
@@ -1050,6 +1056,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
     kv("cout", p.cout); kv("chunks_out", p.chunks_out); kv("epi_base", p.epi_base); kv("has_lut", p.has_lut); kv("in_zp", p.in_zp);
     kv("to_global", p.to_global); kv("param_off", p.param_off); kv("param_bytes", p.param_bytes); kv("w_off", p.w_off); kv("lut_off", p.lut_off);
     kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("epi_off", p.epi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw); kv("in_wp", p.in_wp); kv("out_wp", p.out_wp); kv("out_zp", p.out_zp);
+    kv("in_ws", p.in_ws); kv("out_ws", p.out_ws); kv("scratch_ws", p.scratch_ws); kv("tpg", p.tpg); kv("ntiles", p.ntiles);
     j += "\"add\":[" + std::to_string(p.add.enabled) + "," + std::to_string(p.add.zp1) + "," + std::to_string(p.add.zp2) + "," + std::to_string(p.add.zp_out) + "," +
          std::to_string(p.add.m1) + "," + std::to_string(p.add.m2) + "," + std::to_string(p.add.mo) + "," + std::to_string(p.add.s1) + "," +
          std::to_string(p.add.s2) + "," + std::to_string(p.add.so) + "]";

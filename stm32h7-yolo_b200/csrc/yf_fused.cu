@@ -1,17 +1,19 @@
 // yf_fused.cu -- the whole yoloface int8 network as ONE persistent sm_100a kernel.
 //
-// One CTA (256 threads) takes one image at a time through all 26 fused steps (SURVEY.md 8a rows
-// a2-a11).  Activations never leave the SM: they sit in shared memory in chunk-planar form
-// [C/16][H*W][16 B], which is directly the canonical no-swizzle K-major UMMA operand layout, so every
-// CONV_2D is  tcgen05.mma.kind::i8 (smem x smem -> TMEM)  on the data where the previous epilogue
-// left it.  Per-phase parameters (packed weights, 256-entry tables, depthwise words) stream through
-// four smem slots with cp.async.bulk (TMA engine), three phases ahead; the next image is prefetched
-// the same way.  HBM traffic per image is the I/O floor: 9,408 B in + 882 B out.
+// One CTA (256 threads, three CTAs per SM) takes one image at a time through all 26 fused steps
+// (SURVEY.md 8a rows a2-a11).  Activations never leave the SM: MMA operands sit in shared memory in
+// chunk-planar form [C/16][H*W][16 B], which is directly the canonical no-swizzle K-major UMMA operand
+// layout, so every CONV_2D is  tcgen05.mma.kind::i8 (smem x smem -> TMEM)  on the data where the
+// previous phase left it; tensors only the depthwise / pool phases read are word-planar
+// [C/4][cells][4 B] with a zero-point border.  Per-phase parameters (packed weights, 256-entry
+// tables, requant constants) stream through four smem slots with cp.async.bulk (TMA engine), up to
+// three phases ahead; the next image is prefetched the same way.  HBM traffic per image is the I/O
+// floor: 9,408 B in + 882 B out.  75 KB smem, 80 registers, 128 TMEM columns per CTA.
 //
-//   conv phases   one thread issues the MMAs of ALL 128-pixel tiles of the layer (they fit TMEM
-//                 together: <= 224 of the 256 allocated columns) and commits once; then the 8 warps
-//                 split the (tile, 16-channel) units evenly: tcgen05.ld -> TFLite requant ->
-//                 table / ADD -> one 16-byte st.shared per unit row.  No intra-phase barriers.
+//   conv phases   thread 0 issues the MMAs of a tile group (all 128-pixel tiles whose accumulators fit
+//                 the CTA's 128 TMEM columns; the 28x28x18 layer takes two groups) and commits once;
+//                 then the 8 warps split the (tile, 16-channel) units: tcgen05.ld -> TFLite requant
+//                 -> table / ADD -> st.shared.  Thread 0 refills the parameter slots meanwhile.
 //   first conv    implicit GEMM: all threads build A tiles (3 x 16-B chunks per pixel, K laid out
 //                 as [ky][9 taps + 7 don't-care bytes] against zero weights), two tiles per round
 //   depthwise     CUDA cores: one thread = one 4-channel word, fixed per thread (weights and
@@ -24,30 +26,22 @@
 
 namespace yf {
 
-struct alignas(16) EpiChF { long long add64; int32_t mult; int32_t c2p; int32_t e; int32_t pad_[3]; };
-static_assert(sizeof(EpiChF) == 32, "EpiChF layout");
-__constant__ EpiChF c_epif[kMaxEpiCh];
+// per-channel requant constants as they travel in the parameter blocks (yf_plan.cc::build_fused)
+struct alignas(16) EpiChF { int32_t bias; int32_t mult; int32_t c2p; int32_t e; };
+static_assert(sizeof(EpiChF) == 16, "EpiChF layout");
 __constant__ FusedPhase c_fphase[kFusedMaxPhases];
 
-cudaError_t upload_fused_tables(const EpiCh* epi, int n, const FusedPhase* phases, int nph, cudaStream_t s) {
-  if (n + 16 > kMaxEpiCh || nph > kFusedMaxPhases) return cudaErrorInvalidValue;
-  static EpiChF host[kMaxEpiCh];
-  for (int i = 0; i < kMaxEpiCh; ++i) host[i] = EpiChF{};
-  for (int i = 0; i < n; ++i) {
-    // fold "+128" (table index / int8 bias) into the post-shift constant
-    host[i].add64 = epi[i].add64; host[i].mult = epi[i].mult; host[i].c2p = epi[i].c2 + (128 << epi[i].e); host[i].e = epi[i].e;
-  }
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_epif, host, sizeof(EpiChF) * kMaxEpiCh, 0, cudaMemcpyHostToDevice, s);
+cudaError_t upload_fused_tables(const EpiCh*, int, const FusedPhase* phases, int nph, cudaStream_t s) {
+  if (nph > kFusedMaxPhases) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_fphase, phases, sizeof(FusedPhase) * static_cast<size_t>(nph), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
-  e = cudaMemcpyToSymbolAsync(c_fphase, phases, sizeof(FusedPhase) * static_cast<size_t>(nph), 0, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(s);      // `host` is static scratch
+  return cudaStreamSynchronize(s);
 }
 
 // ---- fixed-point pieces -------------------------------------------------------------------------
-// returns the int8 result + 128 clamped to [0,255]; c2p = half + (zp_out + 128) << e; needs e >= 1
-__device__ __forceinline__ int32_t requant_idx(int32_t acc, long long add64, int32_t mult, int32_t c2p, int32_t e) {
-  const long long p = static_cast<long long>(acc) * static_cast<long long>(mult) + add64;
+// returns the int8 result + 128 clamped to [0,255]; acc already holds the folded bias; c2p = half + (zp_out + 128) << e; needs e >= 1
+__device__ __forceinline__ int32_t requant_idx(int32_t acc, int32_t mult, int32_t c2p, int32_t e) {
+  const long long p = static_cast<long long>(acc) * static_cast<long long>(mult) + (1ll << 30);
   const int32_t t = static_cast<int32_t>(p >> 31);
   return __vimin_s32_relu((t + c2p + (t >> 31)) >> e, 255);
 }
@@ -73,7 +67,7 @@ __device__ __noinline__ uint32_t add_word(uint32_t skipw, uint32_t yw, const Add
 struct FusedArgs {
   const int8_t* in; int8_t* out; const uint8_t* params;
   int n_img, nphases;
-  int in_off, in_bytes, slot_off, slot_bytes, head_bytes, desc_off;
+  int in_off, in_bytes, slot_off, slot_bytes, head_bytes, desc_off, bars_off, in_pf_phase;
   int* err;
   long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first image
   int trace_phase;            // phase whose inner stamps (trace[96..127]) are recorded
@@ -84,10 +78,9 @@ struct FusedArgs {
 #define YF_STAMP(tp, i) do { } while (0)
 #endif
 
-constexpr int kWorkers = kFusedWorkerThreads;            // 8 worker warps
-constexpr int kFusedThreads = kWorkers + 32;              // + 1 control warp (parameter prefetch, MMA issue)
+constexpr int kFusedThreads = kFusedWorkerThreads;       // 8 warps; thread 0 doubles as MMA issuer / prefetcher
+constexpr int kFusedCtasPerSm = 3;
 
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
 // UMMA smem descriptor: template low word (LBO) + start address; high word: SBO = 128 B, version 1, no swizzle
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
   return (static_cast<uint64_t>(0x4008u) << 32) | static_cast<uint64_t>(lo_tmpl | ((saddr >> 4) & 0x3FFFu));
@@ -100,15 +93,14 @@ __device__ __forceinline__ int small_div(int x, int d) { return static_cast<int>
 __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem, int tid) {
   const int WP = ph.out_wp, H = ph.Hout, ncell = 2 * WP + 2 * H;
   const uint32_t z = static_cast<uint32_t>(ph.out_zp & 0xff) * 0x01010101u;
-  const uint4 zv = make_uint4(z, z, z, z);
-  for (int i = tid; i < ncell * ph.chunks_out; i += kFusedWorkerThreads) {
+  for (int i = tid; i < ncell * ph.nw; i += kFusedThreads) {
     const int c = small_div(i, ncell), k = i - c * ncell;
     int cell;
     if (k < WP) cell = k;
     else if (k < 2 * WP) cell = (H + 1) * WP + (k - WP);
     else if (k < 2 * WP + H) cell = (k - 2 * WP + 1) * WP;
     else cell = (k - 2 * WP - H + 1) * WP + WP - 1;
-    *reinterpret_cast<uint4*>(smem + ph.out_off + c * ph.out_cs + cell * 16) = zv;
+    *reinterpret_cast<uint32_t*>(smem + ph.out_off + c * ph.out_ws + cell * 4) = z;
   }
 }
 
@@ -119,7 +111,7 @@ __device__ __forceinline__ void requant_words(const uint32_t (&v)[16], const Epi
 #pragma unroll
   for (int c = 0; c < NW * 4; ++c) {
     const EpiChF k = ek[c];
-    idx[c] = requant_idx(static_cast<int32_t>(v[c]), k.add64, k.mult, k.c2p, k.e);
+    idx[c] = requant_idx(static_cast<int32_t>(v[c]) + k.bias, k.mult, k.c2p, k.e);
   }
 #pragma unroll
   for (int wi = 0; wi < NW; ++wi) {
@@ -170,35 +162,37 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
+  } else if (ph.out_wp) {                                    // word-planar, zero-point-bordered: depthwise / pool consumers
+    const int y = small_div(row, ph.Wout);
+    uint8_t* o = smem + ph.out_off + g * 4 * ph.out_ws + ((y + 1) * ph.out_wp + (row - y * ph.Wout) + 1) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nwords) *reinterpret_cast<uint32_t*>(o + j * ph.out_ws) = w[j];
   } else {
-    int cell = row;
-    if (ph.out_wp) {                                         // zero-point-bordered layout for depthwise / pool consumers
-      const int y = small_div(row, ph.Wout);
-      cell = (y + 1) * ph.out_wp + (row - y * ph.Wout) + 1;
-    }
-    *reinterpret_cast<uint4*>(smem + ph.out_off + g * ph.out_cs + cell * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(smem + ph.out_off + g * ph.out_cs + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
 // all (tile, chunk) units of a conv phase, split across the worker warps (no divisions)
+// (tiles t0 .. t0+nt-1 are the group whose accumulators sit in TMEM, tile t at column (t - t0) * npad)
 __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, uint32_t tmem_base,
-                                              int warp, int lane, int8_t* ghead) {
-  const int q = warp & 3, chunks = ph.chunks_out, ntiles = ph.ntiles;
+                                              int warp, int lane, int8_t* ghead, int t0, int nt) {
+  const int q = warp & 3, chunks = ph.chunks_out;
   const uint8_t* lut = slot + ph.lut_off;
   const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
-  if (ntiles >= kFusedWarpgroups) {
+  const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  if (nt >= kFusedWarpgroups) {
     // several tiles: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
-    for (int t = warp >> 2; t < ntiles; t += kFusedWarpgroups) {
-      if (t * 128 + q * 32 >= ph.rows_out) continue;         // this warp's 32 rows are all padding
-      for (int g = 0; g < chunks; ++g)
-        conv_unit(ph, smem, lut, epi, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+    for (int t = warp >> 2; t < nt; t += kFusedWarpgroups) {
+      const int row0 = (t0 + t) * 128 + q * 32;
+      if (row0 >= ph.rows_out) continue;                     // this warp's 32 rows are all padding
+      for (int g = 0; g < chunks; ++g) conv_unit(ph, smem, lut, epi, tq + t * ph.npad + g * 16, row0 + lane, g, ghead);
     }
   } else {
     // a single tile: split its chunks across the warpgroups
-    for (int g = warp >> 2; g < chunks; g += kFusedWarpgroups)
-      for (int t = 0; t < ntiles; ++t)
-        if (t * 128 + q * 32 < ph.rows_out)
-          conv_unit(ph, smem, lut, epi, tmem_base + t * ph.npad + g * 16 + (static_cast<uint32_t>(q * 32) << 16), t * 128 + q * 32 + lane, g, ghead);
+    const int row0 = t0 * 128 + q * 32;
+    if (row0 < ph.rows_out)
+      for (int g = warp >> 2; g < chunks; g += kFusedWarpgroups) conv_unit(ph, smem, lut, epi, tq + g * 16, row0 + lane, g, ghead);
   }
 }
 
@@ -211,51 +205,60 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   int pix = small_div(tid, nw);
   const int wd = tid - pix * nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
   const uint32_t* w1h = reinterpret_cast<const uint32_t*>(slot + ph.dw_off);
-  const uint8_t* kb = slot + ph.dwepi_off + wd * 80;
+  const uint8_t* kb = slot + ph.dwepi_off + wd * 64;
   const uint8_t* lut = slot + ph.lut_off;
-  uint32_t w[9][4];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const uint4 v = *reinterpret_cast<const uint4*>(w1h + t * cp + ch0);
-    w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
-  }
-  long long k_add[4]; int32_t k_mult[4], k_c2p[4], k_e[4];
+  // The nine one-hot weight vectors are re-read from the slot for every pixel (one broadcast LDS.128 per tap)
+  // rather than held in 36 registers: the kernel runs three CTAs per SM on 80 registers per thread.
+  const uint4* wv = reinterpret_cast<const uint4*>(w1h + ch0);
+  const int wstep = cp >> 2;                                  // uint4 elements between taps
+  int32_t k_bias[4], k_mult[4], k_c2p[4], k_e[4];
   {
-    const longlong2 a01 = *reinterpret_cast<const longlong2*>(kb), a23 = *reinterpret_cast<const longlong2*>(kb + 16);
-    const int4 m = *reinterpret_cast<const int4*>(kb + 32), c = *reinterpret_cast<const int4*>(kb + 48), e = *reinterpret_cast<const int4*>(kb + 64);
-    k_add[0] = a01.x; k_add[1] = a01.y; k_add[2] = a23.x; k_add[3] = a23.y;
+    const int4 b = *reinterpret_cast<const int4*>(kb), m = *reinterpret_cast<const int4*>(kb + 16);
+    const int4 c = *reinterpret_cast<const int4*>(kb + 32), e = *reinterpret_cast<const int4*>(kb + 48);
+    k_bias[0] = b.x; k_bias[1] = b.y; k_bias[2] = b.z; k_bias[3] = b.w;
     k_mult[0] = m.x; k_mult[1] = m.y; k_mult[2] = m.z; k_mult[3] = m.w;
     k_c2p[0] = c.x; k_c2p[1] = c.y; k_c2p[2] = c.z; k_c2p[3] = c.w;
     k_e[0] = e.x; k_e[1] = e.y; k_e[2] = e.z; k_e[3] = e.w;
   }
   const int WP = ph.in_wp, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out;
-  const int row16 = WP * 16, dy = ph.dy, dx = ph.dx;
+  const int row4 = WP * 4, dy = ph.dy, dx = ph.dx;
   // input is stored with a one-cell zero-point border: tap (ky,kx) of output (oy,ox) is padded cell
   // (oy*stride - pad_t + 1 + ky, ox*stride - pad_l + 1 + kx), always inside the buffer -> no bounds checks
-  const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4 + ((1 - ph.pad_t) * WP + (1 - ph.pad_l)) * 16;
+  const uint8_t* ib = smem + ph.in_off + wd * ph.in_ws + ((1 - ph.pad_t) * WP + (1 - ph.pad_l)) * 4;
   uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
   const bool has_lut = ph.has_lut != 0;
-  int oy = small_div(pix, Wout), ox = pix - oy * Wout;
+  const int oy = small_div(pix, Wout);
+  int ox = pix - oy * Wout;
+  // pointer-incremental sweep: +per pixels = +dy rows +dx columns, wrapping once at most
+  const uint8_t* p = ib + (oy * stride * WP + ox * stride) * 4;
+  uint8_t* o = ob + pix * 16;
+  const int dP = (dy * stride * WP + dx * stride) * 4, dWrap = (stride * WP - Wout * stride) * 4, dO = per * 16;
+  int n_it = pix < rows ? small_div(rows - 1 - pix, per) + 1 : 0;
   YF_STAMP(tp, 1);
-  for (; pix < rows; pix += per) {
-    const uint8_t* p = ib + (oy * stride * WP + ox * stride) * 16;
+  for (; n_it > 0; --n_it) {
     uint32_t x[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) x[ky * 3 + kx] = *reinterpret_cast<const uint32_t*>(p + ky * row16 + kx * 16);
+      for (int kx = 0; kx < 3; ++kx) x[ky * 3 + kx] = *reinterpret_cast<const uint32_t*>(p + ky * row4 + kx * 4);
+    int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const uint4 w = wv[t * wstep];
+      acc[0] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.x), acc[0]);
+      acc[1] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.y), acc[1]);
+      acc[2] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.z), acc[2]);
+      acc[3] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.w), acc[3]);
+    }
     uint32_t ow = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int32_t acc = 0;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) acc = __dp4a(static_cast<int>(x[t]), static_cast<int>(w[t][j]), acc);
-      const int32_t idx = requant_idx(acc, k_add[j], k_mult[j], k_c2p[j], k_e[j]);
+      const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
       ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(lut[idx]) : (idx ^ 0x80)) << (8 * j);
     }
-    *reinterpret_cast<uint32_t*>(ob + pix * 16) = ow;
-    ox += dx; oy += dy;
-    if (ox >= Wout) { ox -= Wout; ++oy; }
+    *reinterpret_cast<uint32_t*>(o) = ow;
+    o += dO; p += dP; ox += dx;
+    if (ox >= Wout) { ox -= Wout; p += dWrap; }
   }
   YF_STAMP(tp, 8);
 }
@@ -265,28 +268,28 @@ __device__ __forceinline__ uint32_t unpack_even(uint32_t x) { return __byte_perm
 __device__ __forceinline__ uint32_t unpack_odd(uint32_t x) { return __byte_perm(x, 0u, 0xB391u); }
 __device__ __forceinline__ uint32_t repack(uint32_t ev, uint32_t od) { return __byte_perm(ev, od, 0x6240u); }
 
-// MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only (worker threads only)
+// MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only
 __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
   const int nw = ph.nw, per = ph.per;
   const bool active = tid < per * nw;
   const int it0 = small_div(tid, nw), wd = tid - it0 * nw;
   const int Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout, k = ph.ksize, stride = ph.stride;
-  const int scs = Hin * Wout * 16;                            // chunk stride of the row-maxima scratch
+  const int sws = ph.scratch_ws;                              // word-plane stride of the row-maxima scratch
   const uint32_t neg = 0x80808080u;
   const int dy = ph.dy, dx = ph.dx;
   if (active) {                                               // pass 1: horizontal window of every input row
-    const uint8_t* ib = smem + ph.in_off + (wd >> 2) * ph.in_cs + (wd & 3) * 4;
-    uint8_t* sb = smem + ph.scratch_off + (wd >> 2) * scs + (wd & 3) * 4;
+    const uint8_t* ib = smem + ph.in_off + wd * ph.in_ws;
+    uint8_t* sb = smem + ph.scratch_off + wd * sws;
     const int total = Hin * Wout;
     int it = it0;
     int y = small_div(it, Wout), ox = it - y * Wout;
     for (; it < total; it += per) {
       const int x0 = max(0, ox * stride - ph.pad_l), x1 = min(Win, ox * stride - ph.pad_l + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
-      const uint8_t* p = ib + ((y + 1) * ph.in_wp + x0 + 1) * 16;
+      const uint8_t* p = ib + ((y + 1) * ph.in_wp + x0 + 1) * 4;
       int n = x1 - x0;
-      for (; n >= 2; n -= 2, p += 32) {
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 16);
+      for (; n >= 2; n -= 2, p += 8) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 4);
         ev = __vimax3_s16x2(ev, unpack_even(a), unpack_even(b));
         od = __vimax3_s16x2(od, unpack_odd(a), unpack_odd(b));
       }
@@ -294,14 +297,14 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p);
         ev = __vmaxs2(ev, unpack_even(a)); od = __vmaxs2(od, unpack_odd(a));
       }
-      *reinterpret_cast<uint32_t*>(sb + it * 16) = repack(ev, od);
+      *reinterpret_cast<uint32_t*>(sb + it * 4) = repack(ev, od);
       ox += dx; y += dy;
       if (ox >= Wout) { ox -= Wout; ++y; }
     }
   }
-  workers_sync();
+  __syncthreads();
   if (active) {                                               // pass 2: vertical window over the row maxima
-    const uint8_t* sb = smem + ph.scratch_off + (wd >> 2) * scs + (wd & 3) * 4;
+    const uint8_t* sb = smem + ph.scratch_off + wd * sws;
     uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
     const uint8_t* lut = slot + ph.lut_off;
     const int total = Hout * Wout;
@@ -310,8 +313,8 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
     for (; it < total; it += per) {
       const int y0 = max(0, oy * stride - ph.pad_t), y1 = min(Hin, oy * stride - ph.pad_t + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
-      const uint8_t* p = sb + (y0 * Wout + ox) * 16;
-      const int step = Wout * 16;
+      const uint8_t* p = sb + (y0 * Wout + ox) * 4;
+      const int step = Wout * 4;
       int n = y1 - y0;
       for (; n >= 2; n -= 2, p += 2 * step) {
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + step);
@@ -335,14 +338,14 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
   }
 }
 
-// first conv: every worker thread builds one A row (3 x 16-byte chunks) of tile 2r + (tid >> 7)
+// first conv: every thread builds one A row (3 x 16-byte chunks) of tile 2r + (tid >> 7)
 __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem, int tid, int r) {
   const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
   const int row_bytes = ph.Win * 3, rt = tid & 127, hf = tid >> 7;
   const uint8_t* image = smem + ph.in_off;
   uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
   const int rr = (2 * r + hf) * 128 + rt;
-  if (hf >= 2 || rr >= ph.rows_out) return;                 // two tiles per round; further worker warps idle here
+  if (rr >= ph.rows_out) return;
   const int oy = small_div(rr, ph.Wout), ox = rr - oy * ph.Wout;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
@@ -361,15 +364,20 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
   }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const FusedArgs a) {
+constexpr int kCtrlWarp = kFusedThreads / 32 - 1;        // TMEM lane quarter 3 of warpgroup 1: no rows in the 7x7 and 14x14 epilogues
+
+__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bars_off);
   uint64_t* in_full = bars;                 // input image landed
   uint64_t* par_full = bars + 1;            // [kFusedParamSlots] parameter slot landed
   uint64_t* mma_done = bars + 1 + kFusedParamSlots;   // [2] accumulators ready (two used by the first conv's rounds)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + kFusedParamSlots);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_ctrl = warp == kWorkers / 32;
+  // The last warp doubles as the control warp: it runs the MMA-issue loops convergently (one elected lane issues,
+  // operands stay warp-uniform) and its lane 0 issues every bulk copy.
+  const bool ctrl = warp == kCtrlWarp;
+  const bool lead = tid == kCtrlWarp * 32;
 
   if (tid == 0) {
     mbar_init(in_full, 1);
@@ -398,133 +406,139 @@ __global__ void __launch_bounds__(kFusedThreads, 2) yoloface_fused_kernel(const 
   auto wait_bar = [&](uint64_t* bar, uint32_t parity, int code) {
     if (ok && !mbar_wait(bar, parity)) { atomicCAS(a.err, 0, code); ok = false; }
   };
-
-  if (is_ctrl) {
-    // ================= control warp: parameter / image prefetch and every tcgen05.mma =================
-    const bool lead = lane == 0;
-    int pnext = 0;                                            // phase index of parameter block pc_next
-    uint32_t pc_next = 0;
-    auto load_params = [&]() {                                // issue the bulk copy of block pc_next
+  // ---- lead thread: parameter blocks go round the slots; block j may be requested once block j - kFusedParamSlots
+  //      (the slot's previous tenant) belongs to a finished phase, i.e. j < pc + kFusedParamSlots
+  int pnext = 0;                                              // phase index of parameter block pc_next
+  uint32_t pc_next = 0;
+  auto refill = [&](uint32_t pc_now) {
+#pragma unroll 1
+    while (pc_next < total_pc && pc_next < pc_now + kFusedParamSlots) {
       const FusedPhase& nx = s_ph[pnext];
       uint64_t* bar = &par_full[pc_next % kFusedParamSlots];
       mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
       bulk_load_1d(smem + a.slot_off + (pc_next % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
       ++pc_next; if (++pnext == nph) pnext = 0;
-    };
-    if (lead && my_images > 0) {
-      mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-      bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
-      while (pc_next + 1 < kFusedParamSlots && pc_next < total_pc) load_params();
-      wait_bar(&par_full[0], 0, 311);                         // weights of the very first phase
     }
-    uint32_t pc = 0;
-    for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
-      for (int p = 0; p < nph; ++p, ++pc) {
-        const FusedPhase& ph = s_ph[p];
-        const uint32_t sW = smem_base + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes + ph.w_off;
-        if (ph.kind == STEP_CONV1X1) {
-          if (lead) {                                         // all tiles of the layer, one commit (weights already waited for)
-            tc_fence_after();
-            const uint32_t sA = smem_base + ph.in_off;
-            for (int t = 0; t < ph.ntiles; ++t)
-              for (int k = 0; k < ph.nk; ++k)
-                mma_i8(tmem_base + t * ph.npad, mk_desc(ph.adesc_lo, sA + t * 2048 + k * 2 * ph.in_cs),
-                       mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16), static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
-            mma_commit(&mma_done[0]);
-          }
-        } else if (ph.kind == STEP_CONV_IM2COL) {
-          const int rounds = (ph.ntiles + 1) >> 1;
-          for (int r = 0; r < rounds; ++r) {
-            __syncthreads();                                  // workers finished building round r
-            if (lead) {
-              tc_fence_after();
-              for (int h = 0; h < 2; ++h) {
-                const int tt = 2 * r + h;
-                if (tt >= ph.ntiles) break;
-                const uint32_t sS = smem_base + ph.scratch_off + ((2 * r + h) & 3) * 6144;
-                for (int k = 0; k < 2; ++k)
-                  mma_i8(tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
-                         static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
-              }
-              mma_commit(&mma_done[r & 1]);
-            }
-          }
-        }
-        if (lead) {
-          if (pc_next < total_pc) load_params();              // keep kFusedParamSlots - 1 blocks in flight
-          if (p == 1 && img + static_cast<int>(gridDim.x) < a.n_img) {   // image buffer is free after phase 0
-            mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-            bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
-          }
-          if (pc + 1 < total_pc)                              // next phase's weights, off the critical path
-            wait_bar(&par_full[(pc + 1) % kFusedParamSlots], ((pc + 1) / kFusedParamSlots) & 1, 312);
-        }
-        __syncthreads();                                      // end of phase p
-      }
-    }
-  } else {
-    // ================= worker warps =================
-    uint32_t pc = 0;
-    for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
-      int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
-      for (int p = 0; p < nph; ++p, ++pc) {
-        const FusedPhase& ph = s_ph[p];
-#ifdef YF_TRACE
-        const bool tr = a.trace && tid == 0 && blockIdx.x == 0 && pc < 2u * static_cast<uint32_t>(nph);
-        long long* sub = (tr && p == 14) ? a.trace + 80 + 8 * (pc / nph) : nullptr;
-        if (tr) a.trace[pc + pc / nph] = clock64();
-#else
-        constexpr bool tr = false; long long* const sub = nullptr;
-#endif
-        if (sub) sub[0] = clock64();
-        wait_bar(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1, 302);
-        const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
-        if (sub) sub[1] = clock64();
-        if (ph.kind == STEP_CONV1X1) {
-          if (sub) sub[2] = clock64();
-          if (ph.out_wp) fill_border(ph, smem, tid);
-          wait_bar(&mma_done[0], use0 & 1, 301); ++use0;
-          tc_fence_after();
-          if (sub) sub[3] = clock64();
-          conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
-          tc_fence_before();
-          if (sub) sub[4] = clock64();
-        } else if (ph.kind == STEP_CONV_IM2COL) {
-          if (ph.out_wp) fill_border(ph, smem, tid);
-          wait_bar(in_full, in_uses & 1, 303); ++in_uses;
-          const int rounds = (ph.ntiles + 1) >> 1;
-          for (int r = 0; r < rounds; ++r) {
-            if (r >= 2) {                                     // the A stages of round r-2 must have been consumed
-              if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 304); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 304); ++use0; }
-            }
-            im2col_build(ph, smem, tid, r);
-            fence_proxy_async_smem();
-            __syncthreads();                                  // control issues round r
-          }
-          for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
-            if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 305); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 305); ++use0; }
-          }
-          tc_fence_after();
-          conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead);
-          tc_fence_before();
-        } else if (ph.kind == STEP_DW) {
-          dw_phase(ph, smem, slot, tid, (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) ? a.trace + 96 : nullptr);
-          if (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) a.trace[96 + 9] = clock64();
-        } else if (ph.kind == STEP_MAXPOOL) {
-          pool_phase(ph, smem, slot, tid);
-        }
-        fence_proxy_async_smem();          // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
-        if (sub) sub[5] = clock64();
-        if (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) a.trace[96 + 10] = clock64();
-        __syncthreads();
-        if (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) a.trace[96 + 11] = clock64();
-        if (sub) sub[6] = clock64();
-      }
-    }
-#ifdef YF_TRACE
-    if (a.trace && tid == 0 && blockIdx.x == 0) a.trace[(my_images >= 2 ? 2 : 1) * (nph + 1) - 1] = clock64();
-#endif
+  };
+  if (lead && my_images > 0) {
+    mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
+    bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+    refill(0);
   }
+
+  uint32_t pc = 0;
+  for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
+    int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
+    for (int p = 0; p < nph; ++p, ++pc) {
+      const FusedPhase& ph = s_ph[p];
+      const int kind = ph.kind, ntiles = ph.ntiles, tpg = ph.tpg, rows_out = ph.rows_out;
+      // the fields the issue path needs, fetched by the control warp in one burst before the barrier wait below
+      int nk = 0, npad = 0, in_cs = 0;
+      uint32_t adesc_lo = 0, bdesc_lo = 0, idesc = 0, sW = 0, sA = 0;
+      if (ctrl) {
+        nk = ph.nk; npad = ph.npad; in_cs = ph.in_cs; adesc_lo = ph.adesc_lo; bdesc_lo = ph.bdesc_lo; idesc = static_cast<uint32_t>(ph.idesc);
+        sW = smem_base + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes + ph.w_off;
+        sA = smem_base + ph.in_off;
+      }
+      const bool ctrl_busy = rows_out > 224;                  // the control warp owns epilogue rows only in the 28x28 layers
+#ifdef YF_TRACE
+      const bool tr = a.trace && tid == 0 && blockIdx.x == 0 && pc < 2u * static_cast<uint32_t>(nph);
+      if (tr) a.trace[pc + pc / nph] = clock64();
+      long long* const tp = (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) ? a.trace + 96 : nullptr;
+#else
+      long long* const tp = nullptr;
+#endif
+      wait_bar(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1, 302);
+      const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
+      // lead thread, off the critical path: refill the slot the previous phase released, prefetch the next image
+      auto housekeeping = [&]() {
+        refill(pc);
+        if (p == a.in_pf_phase && img + static_cast<int>(gridDim.x) < a.n_img) {     // the image buffer is free after phase 0
+          mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
+          bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+        }
+      };
+      if (kind == STEP_CONV1X1) {
+        for (int t0 = 0; t0 < ntiles; t0 += tpg) {
+          const int nt = min(tpg, ntiles - t0);
+          if (ctrl) {                                         // every tile of the group, one commit
+            tc_fence_after();
+            const bool el = elect_one();
+            for (int t = 0; t < nt; ++t)
+              for (int k = 0; k < nk; ++k)
+                if (el) mma_i8(tmem_base + t * npad, mk_desc(adesc_lo, sA + (t0 + t) * 2048 + k * 2 * in_cs),
+                               mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
+            if (el) mma_commit(&mma_done[0]);
+            __syncwarp();
+            if (lead && t0 == 0 && !ctrl_busy) housekeeping();
+            __syncwarp();
+          }
+          if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
+          // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 7x7 and 14x14 layers)
+          // neither poll the barrier nor touch TMEM: they go straight to the end-of-phase barrier
+          const int wg = warp >> 2;
+          const bool has_rows = nt >= kFusedWarpgroups ? (t0 + wg) * 128 + (warp & 3) * 32 < rows_out
+                                                       : (t0 * 128 + (warp & 3) * 32 < rows_out && wg < ph.chunks_out);
+          if (has_rows) {
+            wait_bar(&mma_done[0], use0 & 1, 301);
+            tc_fence_after();
+            conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, t0, nt);
+            tc_fence_before();
+          }
+          ++use0;
+          if (t0 + tpg < ntiles) __syncthreads();             // the next group overwrites these TMEM columns
+        }
+        if (lead && ctrl_busy) housekeeping();
+      } else if (kind == STEP_CONV_IM2COL) {
+        if (ph.out_wp) fill_border(ph, smem, tid);
+        wait_bar(in_full, in_uses & 1, 303); ++in_uses;
+        const int rounds = (ntiles + 1) >> 1;
+        for (int r = 0; r < rounds; ++r) {
+          if (r >= 2) {                                       // the A stages of round r-2 must have been consumed
+            if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 304); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 304); ++use0; }
+          }
+          im2col_build(ph, smem, tid, r);
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (ctrl) {
+            tc_fence_after();
+            const bool el = elect_one();
+            for (int h = 0; h < 2; ++h) {
+              const int tt = 2 * r + h;
+              if (tt >= ntiles) break;
+              const uint32_t sS = smem_base + ph.scratch_off + (tt & 3) * 6144;
+              for (int k = 0; k < 2; ++k)
+                if (el) mma_i8(tmem_base + tt * npad, mk_desc(adesc_lo, sS + k * 4096), mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
+            }
+            if (el) mma_commit(&mma_done[r & 1]);
+            __syncwarp();
+          }
+        }
+        for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
+          if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 305); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 305); ++use0; }
+        }
+        tc_fence_after();
+        conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, 0, ntiles);
+        tc_fence_before();
+        if (lead) housekeeping();
+      } else {
+        if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, tp);
+        else if (kind == STEP_MAXPOOL) pool_phase(ph, smem, slot, tid);
+        if (lead && pc_next <= pc + 1) housekeeping();        // only when the next phase's block is not even requested yet
+      }
+      fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
+#ifdef YF_TRACE
+      if (tp) tp[10] = clock64();
+#endif
+      __syncthreads();
+#ifdef YF_TRACE
+      if (tp) tp[11] = clock64();
+#endif
+    }
+  }
+#ifdef YF_TRACE
+  if (a.trace && tid == 0 && blockIdx.x == 0) a.trace[(my_images >= 2 ? 2 : 1) * (nph + 1) - 1] = clock64();
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, kFusedTmemCols);
@@ -540,9 +554,10 @@ cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_ou
   FusedArgs a{};
   a.in = d_in; a.out = d_out; a.params = d_params; a.n_img = n_img; a.nphases = static_cast<int>(F.phases.size());
   a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes; a.desc_off = F.desc_off;
-  a.head_bytes = F.head_bytes; a.err = d_err; a.trace = d_trace;
+  a.head_bytes = F.head_bytes; a.err = d_err; a.trace = d_trace; a.in_pf_phase = F.in_pf_phase;
+  a.bars_off = F.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127);
   { const char* e = getenv("YF_B200_TRACE_PHASE"); a.trace_phase = e ? atoi(e) : 1; }
-  const int per_sm = F.smem_bytes <= 113 * 1024 ? 2 : 1;
+  const int per_sm = F.smem_bytes <= 75 * 1024 ? kFusedCtasPerSm : F.smem_bytes <= 113 * 1024 ? 2 : 1;
   const int grid = n_img < sm_count * per_sm ? n_img : sm_count * per_sm;
   yoloface_fused_kernel<<<grid, kFusedThreads, F.smem_bytes, s>>>(a);
   return cudaGetLastError();

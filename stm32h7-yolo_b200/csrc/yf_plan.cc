@@ -552,7 +552,10 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   auto no = [&](const std::string& w) { F->ok = false; F->why = w; return false; };
   const int ns = static_cast<int>(P.steps.size());
   if (ns > kFusedMaxPhases) return no("too many steps");
-  for (const EpiCh& e : P.epi) if (e.e < 1 || e.ls != 0) return no("requant shift outside the fused epilogue's range");
+  for (const EpiCh& e : P.epi) {
+    if (e.e < 1 || e.ls != 0) return no("requant shift outside the fused epilogue's range");
+    if (e.mult == 0 || (e.add64 - (1LL << 30)) % e.mult != 0) return no("requant addend is not bias * multiplier + 2^30");
+  }
   // live range of every buffer: first writer .. last reader (in step order)
   const int nb = static_cast<int>(P.buffers.size());
   std::vector<int> birth(nb, 1 << 30), death(nb, -1);
@@ -581,15 +584,22 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   for (int i = 0; i < ns; ++i) if ((P.steps[i].kind == STEP_DW || P.steps[i].kind == STEP_MAXPOOL) && !padded[P.steps[i].in_buf])
     return no("depthwise/pool input " + P.steps[i].name + " is not a conv-produced, dw/pool-only buffer");
   auto cells_of = [&](int b) { const PBuffer& B = P.buffers[b]; return padded[b] ? (B.H + 2) * (B.W + 2) : B.H * B.W; };
-  auto bytes_of = [&](int b) { const PBuffer& B = P.buffers[b]; return (cells_of(b) * B.CP + 127) & ~127; };
+  // word-plane stride: cells * 4 bytes, skewed so that the planes of the words one warp touches start
+  // 32 / nw banks apart (a warp of the depthwise / pool phases covers ~32 / nw cells of each of its nw words)
+  auto plane_stride = [](int cells, int nw) { int w = cells; while (w % 32 != (32 / std::max(nw, 1)) % 32) ++w; return w * 4; };
+  auto words_of = [&](int b) { return (P.buffers[b].C + 3) / 4; };
+  auto bytes_of = [&](int b) {
+    const PBuffer& B = P.buffers[b];
+    return ((padded[b] ? plane_stride(cells_of(b), words_of(b)) * words_of(b) : cells_of(b) * B.CP) + 127) & ~127;
+  };
   // scratch regions live for exactly one phase: the first conv's A stages, the pools' row maxima
   std::vector<int> scratch_size(ns, 0);
   for (int i = 0; i < ns; ++i) {
     const Step& s = P.steps[i];
     if (s.kind == STEP_CONV_IM2COL) scratch_size[i] = 4 * 6144 + 2048;
-    if (s.kind == STEP_MAXPOOL) scratch_size[i] = ((s.Cout + 15) / 16) * s.Hin * s.Wout * 16;
-    if ((s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && ((s.Hout * s.Wout + 127) / 128) * s.Npad > kFusedTmemCols)
-      return no("accumulator tiles of step " + s.name + " exceed TMEM");
+    if (s.kind == STEP_MAXPOOL) scratch_size[i] = ((s.Cout + 3) / 4) * plane_stride(s.Hin * s.Wout, (s.Cout + 3) / 4);
+    if (s.kind == STEP_CONV_IM2COL && ((s.Hout * s.Wout + 127) / 128) * s.Npad > kFusedTmemCols)
+      return no("accumulator tiles of the first conv exceed TMEM");
   }
   // first-fit placement in birth order (scratch of phase i is born with the buffers written at i)
   struct Item { int id, birth, death, size; };          // id >= 0: buffer, id < 0: scratch of phase -id-1
@@ -614,14 +624,15 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     if (it.id >= 0) off[it.id] = best; else scratch_off[-it.id - 1] = best;
     live.push_back(Live{best, it.size, it.death}); arena = std::max(arena, best + it.size);
   }
-  // smem map: [input image][arena + over-read guard][parameter slots]
+  // smem map: [input image][arena][parameter slots][phase descriptors][barriers]
   const Step& s0 = P.steps[0];
   F->in_off = 16;                                // the im2col builder reads up to 4 bytes before the image
   F->in_bytes = s0.Hin * s0.Win * s0.Cin;
   if (F->in_bytes % 16) return no("input image size is not a multiple of 16 bytes");
-  F->arena_off = (F->in_off + F->in_bytes + 16 + 1023) & ~1023;
-  F->arena_bytes = arena + 8192;                 // a 128-row MMA tile may read past the last rows
+  F->arena_off = (F->in_off + F->in_bytes + 16 + 127) & ~127;
+  F->arena_bytes = (arena + 127) & ~127;
   F->slot_off = F->arena_off + F->arena_bytes;
+  int overread_end = 0;                          // a 128-row MMA tile reads past the rows (and the K chunks) its buffer holds
   // parameter blocks
   int slot = 0;
   for (int i = 0; i < ns; ++i) {
@@ -633,9 +644,11 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     ph.in_off = ib.is_input ? F->in_off : F->arena_off + off[s.in_buf];
     ph.in_cs = (ib.is_input ? ph.rows_in : cells_of(s.in_buf)) * 16;
     ph.in_wp = (!ib.is_input && padded[s.in_buf]) ? s.Win + 2 : 0;
+    ph.in_ws = ph.in_wp ? plane_stride(cells_of(s.in_buf), words_of(s.in_buf)) : 0;
     ph.to_global = ob.is_output ? 1 : 0;
     ph.out_cs = (ob.is_output ? ph.rows_out : cells_of(s.out_buf)) * 16;
     ph.out_wp = (!ob.is_output && padded[s.out_buf]) ? s.Wout + 2 : 0;
+    ph.out_ws = ph.out_wp ? plane_stride(cells_of(s.out_buf), words_of(s.out_buf)) : 0;
     if (ph.out_wp) { for (int j = i + 1; j < ns; ++j) if (P.steps[j].in_buf == s.out_buf) { ph.out_zp = P.steps[j].in_zp; break; } }
     ph.out_off = ob.is_output ? 0 : F->arena_off + off[s.out_buf] + (s.out_coff / 16) * ph.out_cs;
     ph.add_off = -1; ph.scratch_off = scratch_off[i] >= 0 ? F->arena_off + scratch_off[i] : -1;
@@ -645,24 +658,34 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     ph.ntiles = (ph.rows_out + 127) / 128;
     ph.nw = (s.Cout + 3) / 4;
     ph.per = kFusedWorkerThreads / ph.nw;
-    ph.dy = ph.per / ph.Wout; ph.dx = ph.per % ph.Wout; ph.dy1 = ph.dy; ph.dx1 = ph.dx;
+    ph.dy = ph.per / ph.Wout; ph.dx = ph.per % ph.Wout;
+    ph.tpg = s.Npad ? std::max(1, std::min(ph.ntiles, kFusedTmemCols / s.Npad)) : 0;
+    if (ph.tpg && ph.ntiles > ph.tpg) {              // balance the groups (7 tiles: 4 + 3, not 4 + 3 -> same; 9: 3 x 3)
+      const int groups = (ph.ntiles + ph.tpg - 1) / ph.tpg;
+      ph.tpg = (ph.ntiles + groups - 1) / groups;
+    }
+    ph.scratch_ws = s.kind == STEP_MAXPOOL ? plane_stride(s.Hin * s.Wout, ph.nw) : 0;
     ph.idesc = static_cast<int32_t>((2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(s.Npad >> 3) << 17) | (8u << 24));
     ph.adesc_lo = static_cast<uint32_t>(((s.kind == STEP_CONV_IM2COL ? 2048 : ph.in_cs) >> 4) & 0x3FFF) << 16;
     ph.bdesc_lo = static_cast<uint32_t>(((s.Npad * 16) >> 4) & 0x3FFF) << 16;
     // block: [weights][table][depthwise constants]
     std::vector<uint8_t> blk;
     auto put = [&](const void* src, size_t n) { size_t o = blk.size(); blk.resize((o + n + 15) & ~size_t(15), 0); std::memcpy(blk.data() + o, src, n); return static_cast<int>(o); };
-    auto put_epi = [&]() {     // {add64, mult, c2p = c2 + (128 << e), e, pad} per output channel, padded to whole chunks
-      std::vector<uint8_t> e(static_cast<size_t>(ph.chunks_out) * 16 * 32, 0);
+    // The 64-bit addend of the folded requant is bias' * mult + 2^30 (no left shift on this path), so the
+    // kernel adds the int32 bias' to the accumulator instead and keeps 16 bytes per channel.
+    auto bias_of = [&](const EpiCh& k) { return static_cast<int32_t>((k.add64 - (1LL << 30)) / k.mult); };
+    auto put_epi = [&]() {     // {bias', mult, c2p = c2 + (128 << e), e} per output channel, padded to whole chunks
+      std::vector<uint8_t> e(static_cast<size_t>(ph.chunks_out) * 16 * 16, 0);
       for (int c = 0; c < s.Cout; ++c) {
-        const EpiCh& k = P.epi[s.epi_base + c]; uint8_t* b = e.data() + static_cast<size_t>(c) * 32;
-        const int32_t c2p = k.c2 + (128 << k.e);
-        std::memcpy(b, &k.add64, 8); std::memcpy(b + 8, &k.mult, 4); std::memcpy(b + 12, &c2p, 4); std::memcpy(b + 16, &k.e, 4);
+        const EpiCh& k = P.epi[s.epi_base + c]; uint8_t* b = e.data() + static_cast<size_t>(c) * 16;
+        const int32_t c2p = k.c2 + (128 << k.e), bf = bias_of(k);
+        std::memcpy(b, &bf, 4); std::memcpy(b + 4, &k.mult, 4); std::memcpy(b + 8, &c2p, 4); std::memcpy(b + 12, &k.e, 4);
       }
       return put(e.data(), e.size());
     };
     if (s.kind == STEP_CONV1X1) {
       ph.nk = s.Kpad / 32;
+      overread_end = std::max(overread_end, ph.in_off + (2 * ph.nk - 1) * ph.in_cs + ph.ntiles * 2048);
       ph.w_off = put(P.wblob.data() + s.w_off, s.w_bytes);
       ph.epi_off = put_epi();
     } else if (s.kind == STEP_CONV_IM2COL) {
@@ -680,14 +703,14 @@ bool build_fused(const Plan& P, FusedProgram* F) {
       ph.epi_off = put_epi();
     } else if (s.kind == STEP_DW) {
       ph.dw_off = put(P.wblob.data() + s.w_off, s.w_bytes);             // [9][CP] one-hot words
-      // per 4-channel word: {add64 x4 | mult x4 | c2p x4 | e x4} = 80 bytes, c2p = c2 + (128 << e)
-      std::vector<uint8_t> e(static_cast<size_t>(ph.nw) * 80, 0);
+      // per 4-channel word: {bias' x4 | mult x4 | c2p x4 | e x4} = 64 bytes, c2p = c2 + (128 << e)
+      std::vector<uint8_t> e(static_cast<size_t>(ph.nw) * 64, 0);
       for (int c = 0; c < s.Cout; ++c) {
         const EpiCh& k = P.epi[s.epi_base + c];
-        uint8_t* b = e.data() + static_cast<size_t>(c / 4) * 80; const int j = c % 4;
-        const int32_t c2p = k.c2 + (128 << k.e);
-        std::memcpy(b + 8 * j, &k.add64, 8); std::memcpy(b + 32 + 4 * j, &k.mult, 4);
-        std::memcpy(b + 48 + 4 * j, &c2p, 4); std::memcpy(b + 64 + 4 * j, &k.e, 4);
+        uint8_t* b = e.data() + static_cast<size_t>(c / 4) * 64; const int j = c % 4;
+        const int32_t c2p = k.c2 + (128 << k.e), bf = bias_of(k);
+        std::memcpy(b + 4 * j, &bf, 4); std::memcpy(b + 16 + 4 * j, &k.mult, 4);
+        std::memcpy(b + 32 + 4 * j, &c2p, 4); std::memcpy(b + 48 + 4 * j, &k.e, 4);
       }
       ph.dwepi_off = put(e.data(), e.size());
     }
@@ -701,6 +724,9 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   F->slot_bytes = (slot + 127) & ~127;
   F->desc_off = F->slot_off + kFusedParamSlots * F->slot_bytes;
   F->smem_bytes = F->desc_off + ((static_cast<int>(F->phases.size() * sizeof(FusedPhase)) + 127) & ~127) + 256;
+  F->smem_bytes = std::max(F->smem_bytes, overread_end);      // the over-read bytes meet zero weights; they only have to exist
+  F->in_pf_phase = 1;                                         // prefetch of the next image rides on the first 1x1 conv phase
+  for (int i = 1; i < ns; ++i) if (P.steps[i].kind == STEP_CONV1X1) { F->in_pf_phase = i; break; }
   F->head_bytes = P.GH * P.GW * 18;
   if (F->smem_bytes > 200 * 1024) return no("activations do not fit shared memory (" + std::to_string(F->smem_bytes) + " bytes)");
   F->ok = true;

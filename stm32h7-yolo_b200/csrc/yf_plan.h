@@ -148,6 +148,10 @@ bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blo
 // which is at the same time (a) the canonical no-swizzle K-major UMMA operand layout (8-row x 16-B
 // core matrices are contiguous: SBO = 128 B, LBO = rows*16 B) and (b) conflict-free for the
 // CUDA-core phases (a warp touches 8 pixels x 16 B = 128 contiguous bytes).
+// Buffers that no MMA reads -- conv outputs consumed only by depthwise / pool steps, and the pools'
+// row-maxima scratch -- are "word-planar" instead: [ceil(C/4) words][cells][4 bytes] with a
+// one-cell zero-point border, which costs C rounded up to 4 channels per cell rather than to 16
+// (the 18-channel 28x28 tensor: 18 KB instead of 28.8 KB).
 // ------------------------------------------------------------------------------------------------
 struct alignas(16) FusedPhase {
   int32_t kind;                 // StepKind (0 im2col conv, 1 conv1x1, 2 depthwise, 3 maxpool)
@@ -170,13 +174,14 @@ struct alignas(16) FusedPhase {
   // loop constants precomputed on the host (no integer division on the device)
   int32_t ntiles;               // conv: 128-pixel tiles
   int32_t nw, per, dy, dx;      // depthwise / pool pass 2: real 4-channel words, pixels per sweep, (per / Wout, per % Wout)
-  int32_t dy1, dx1;             // pool pass 1 (row maxima): per / Wout, per % Wout (same Wout) -- kept separate for clarity
+  int32_t tpg;                  // conv: tiles whose accumulators share TMEM (tile groups run one after the other)
+  int32_t scratch_ws;           // pool: bytes between the word planes of the row-maxima scratch
   int32_t idesc;                // UMMA instruction descriptor (M=128, N=npad, s8 x s8 -> s32)
   uint32_t adesc_lo, bdesc_lo;  // UMMA smem descriptor low words without the start address: LBO >> 4 << 16
-  // zero-point border: buffers read only by depthwise / pool steps are stored as (H+2) x (W+2) cells
+  // zero-point border: buffers read only by depthwise / pool steps are stored word-planar as (H+2) x (W+2) cells
   int32_t in_wp, out_wp;        // padded row width in cells of the input / output buffer (0 = not padded)
   int32_t out_zp;               // border value of a padded output buffer (its tensor's zero point)
-  int32_t pad_[2];
+  int32_t in_ws, out_ws;        // bytes between the word planes of a padded input / output buffer
 };
 static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied to shared memory with 16-byte loads");
 
@@ -190,14 +195,15 @@ struct FusedProgram {
   int arena_off = 0, arena_bytes = 0;
   int slot_off = 0, slot_bytes = 0;     // smem: kFusedParamSlots parameter slots
   int desc_off = 0;                     // smem: copy of the phase descriptors
+  int in_pf_phase = 1;                  // phase at which the next image's input is prefetched (input buffer free)
   int smem_bytes = 0;
   int head_bytes = 0;           // bytes per image of the dense head
 };
 constexpr int kFusedMaxPhases = 32;
-constexpr int kFusedWarpgroups = 2;   // worker warps = 4 * kFusedWarpgroups, plus one control warp
+constexpr int kFusedWarpgroups = 2;   // warps = 4 * kFusedWarpgroups (a warp reads the TMEM lane quarter warp % 4)
 constexpr int kFusedWorkerThreads = kFusedWarpgroups * 128;
 constexpr int kFusedParamSlots = 4;
-constexpr int kFusedTmemCols = 256;     // all accumulator tiles of one conv phase live in TMEM at once
+constexpr int kFusedTmemCols = 128;     // per CTA (three CTAs share an SM's 512 columns); larger layers run in tile groups
 bool build_fused(const Plan& plan, FusedProgram* prog);
 
 }  // namespace yf

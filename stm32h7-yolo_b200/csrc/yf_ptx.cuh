@@ -48,6 +48,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// same, but the hardware may keep the thread suspended for up to `hint_ns` before it reports "not yet":
+// a waiting warp then costs (almost) no issue slots
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must never hang the GPU box.  Gives up after ~2^32 SM cycles (~2 s);
 // callers record the failure in a global error word and drain.
 static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity) {
@@ -65,9 +78,10 @@ static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parit
   }
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;                 // the common case: already complete
 #pragma unroll 1
   for (int i = 0; i < 16; ++i)
-    if (mbar_try_wait(bar, parity)) return true;
+    if (mbar_try_wait_suspend(bar, parity, 4000u)) return true;
   return mbar_wait_slow(bar, parity);
 }
 

@@ -1,9 +1,11 @@
 """numpy emulation of the fused single-kernel program (yf_b200_fused_json + parameter blob).
 
 Shared memory is one flat byte array pre-filled with random garbage and addressed with the very
-offsets / chunk strides the kernel uses (UMMA operand rows at in_off + chunk*in_cs + row*16, weight
-images [K/16][N][16] in the parameter slot, 16-byte epilogue stores, aliasing by liveness), so that
-layout, aliasing or parameter-block mistakes in csrc/yf_plan.cc::build_fused surface on CPU.
+offsets / strides the kernel uses (UMMA operand rows at in_off + chunk*in_cs + row*16 -- including the
+rows and K chunks an MMA tile reads past its buffer, which must meet zero weights --, word-planar
+bordered buffers at off + word*ws + cell*4, weight images [K/16][N][16] in the parameter slot,
+aliasing by liveness), so that layout, aliasing or parameter-block mistakes in
+csrc/yf_plan.cc::build_fused surface on CPU.
 Test infrastructure only."""
 import numpy as np
 
@@ -21,24 +23,33 @@ def run_fused(F, img, seed=0):
         a = off + chunk * cs
         return smem[a:a + rows * 16].view(np.int8).reshape(rows, 16)
 
-    def padded_input(ph, chunks):                  # zero-point-bordered (H+2)x(W+2) buffer -> [H+2, W+2, chunks*16] int64
-        H, W = ph["Hin"], ph["Win"]
-        assert ph["in_wp"] == W + 2 and ph["in_cs"] == (H + 2) * (W + 2) * 16
-        return np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, (H + 2) * (W + 2)) for c in range(chunks)], axis=1).reshape(H + 2, W + 2, chunks * 16).astype(np.int64)
+    def word_plane(off, ws, word, cells):          # -> int8 [cells,4] view of one word plane
+        a = off + word * ws
+        return smem[a:a + cells * 4].view(np.int8).reshape(cells, 4)
+
+    def padded_input(ph, chunks):                  # word-planar zero-point-bordered (H+2)x(W+2) buffer -> [H+2, W+2, nw*4] int64
+        H, W, nw = ph["Hin"], ph["Win"], ph["nw"]
+        cells = (H + 2) * (W + 2)
+        assert ph["in_wp"] == W + 2 and ph["in_ws"] >= cells * 4 and ph["in_ws"] % 4 == 0
+        return np.concatenate([word_plane(ph["in_off"], ph["in_ws"], w, cells) for w in range(nw)], axis=1).reshape(H + 2, W + 2, nw * 4).astype(np.int64)
 
     for ph in F["phases"]:
         slot = params[ph["param_off"]:ph["param_off"] + ph["param_bytes"]]
         kind, rows_o, cout, npad = ph["kind"], ph["rows_out"], ph["cout"], ph["npad"]
         lut = slot[ph["lut_off"]:ph["lut_off"] + 256].view(np.int8) if ph["has_lut"] else None
         if ph["scratch_off"] >= 0:      # the kernel scribbles here during this phase: must not alias anything live
-            size = 4 * 6144 + 2048 if kind == 0 else ph["chunks_out"] * ph["Hin"] * ph["Wout"] * 16
+            size = 4 * 6144 + 2048 if kind == 0 else ph["nw"] * ph["scratch_ws"]
+            assert kind == 0 or ph["scratch_ws"] >= ph["Hin"] * ph["Wout"] * 4
             smem[ph["scratch_off"]:ph["scratch_off"] + size] = rng.integers(0, 256, size, dtype=np.uint8)
         if kind in (0, 1):
             K = ph["nk"] * 32
             wimg = slot[ph["w_off"]:ph["w_off"] + (K // 16) * npad * 16].view(np.int8).reshape(K // 16, npad, 16)
             wmat = wimg.transpose(0, 2, 1).reshape(K, npad).astype(np.int64)
             if kind == 1:
-                A = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, rows_o) for c in range(K // 16)], axis=1).astype(np.int64)
+                tile_rows = ph["ntiles"] * 128                  # what the MMAs really read: whole 128-row tiles of every K chunk
+                assert ph["in_off"] + (K // 16 - 1) * ph["in_cs"] + tile_rows * 16 <= F["smem_bytes"], "MMA operand read leaves the allocation"
+                assert 1 <= ph["tpg"] and ph["tpg"] * npad <= F["tmem_cols"]
+                A = np.concatenate([chunk_rows(ph["in_off"], ph["in_cs"], c, tile_rows) for c in range(K // 16)], axis=1).astype(np.int64)[:rows_o]
             else:
                 H, W = ph["Hin"], ph["Win"]
                 x = smem[F["in_off"]:F["in_off"] + H * W * 3].view(np.int8).reshape(H, W, 3).astype(np.int64)
@@ -51,11 +62,12 @@ def run_fused(F, img, seed=0):
                     for ky in range(3):
                         A[r, ky * 16:ky * 16 + 9] = flat[2 * oy + ky, (2 * ox) * 3:(2 * ox) * 3 + 9]
             acc = A @ wmat
-            raw = slot[ph["epi_off"]:ph["epi_off"] + cout * 32].reshape(cout, 32)      # constants travel in the block
+            raw = slot[ph["epi_off"]:ph["epi_off"] + cout * 16].reshape(cout, 16)      # constants travel in the block: {bias', mult, c2p, e}
             epi = np.zeros(cout, epi_all.dtype)
-            epi["add64"] = raw[:, 0:8].copy().view("<i8").reshape(-1); epi["mult"] = raw[:, 8:12].copy().view("<i4").reshape(-1)
-            epi["e"] = raw[:, 16:20].copy().view("<i4").reshape(-1)
-            epi["c2"] = raw[:, 12:16].copy().view("<i4").reshape(-1) - (128 << epi["e"]); epi["sgn_mask"] = -1
+            epi["mult"] = raw[:, 4:8].copy().view("<i4").reshape(-1)
+            epi["add64"] = raw[:, 0:4].copy().view("<i4").reshape(-1).astype(np.int64) * epi["mult"].astype(np.int64) + (1 << 30)
+            epi["e"] = raw[:, 12:16].copy().view("<i4").reshape(-1)
+            epi["c2"] = raw[:, 8:12].copy().view("<i4").reshape(-1) - (128 << epi["e"]); epi["sgn_mask"] = -1
             ref = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
             assert all(np.array_equal(epi[f], ref[f]) for f in ("add64", "mult", "e", "c2"))
             y = np.clip(requant(acc[:, :cout], epi), -128, 127)
@@ -71,23 +83,26 @@ def run_fused(F, img, seed=0):
             w = np.zeros((9, cp), np.int64)
             for c in range(cp):
                 w[:, c] = ((w1h[:, c] >> (8 * (c % 4))) & 0xFF).astype(np.uint8).view(np.int8)
-            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + ph["nw"] * 80].reshape(ph["nw"], 80)
+            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + ph["nw"] * 64].reshape(ph["nw"], 64)   # {bias' x4 | mult x4 | c2p x4 | e x4}
             epi = np.zeros(ph["nw"] * 4, epi_all.dtype)
-            epi["add64"] = raw[:, 0:32].copy().view("<i8").reshape(-1)
-            epi["mult"] = raw[:, 32:48].copy().view("<i4").reshape(-1)
-            epi["e"] = raw[:, 64:80].copy().view("<i4").reshape(-1)
-            epi["c2"] = raw[:, 48:64].copy().view("<i4").reshape(-1) - (128 << epi["e"])
+            epi["mult"] = raw[:, 16:32].copy().view("<i4").reshape(-1)
+            epi["add64"] = raw[:, 0:16].copy().view("<i4").reshape(-1).astype(np.int64) * epi["mult"].astype(np.int64) + (1 << 30)
+            epi["e"] = raw[:, 48:64].copy().view("<i4").reshape(-1)
+            epi["c2"] = raw[:, 32:48].copy().view("<i4").reshape(-1) - (128 << epi["e"])
             epi["sgn_mask"] = -1
             epi = epi[:cout]
+            ref = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
+            assert all(np.array_equal(epi[f], ref[f]) for f in ("add64", "mult", "e", "c2"))
             H, W, Ho, Wo, st = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"]
             xp = padded_input(ph, chunks)           # the border must already hold the zero point (written by the producer)
+            w = w[:, :xp.shape[2]]
             assert np.all(xp[0, :, :cout] == ph["in_zp"]) and np.all(xp[:, 0, :cout] == ph["in_zp"]) and np.all(xp[-1, :, :cout] == ph["in_zp"]) and np.all(xp[:, -1, :cout] == ph["in_zp"])
             oy0, ox0 = 1 - ph["pad_t"], 1 - ph["pad_l"]
-            acc = np.zeros((Ho, Wo, cp), np.int64)
+            acc = np.zeros((Ho, Wo, xp.shape[2]), np.int64)
             for ky in range(3):
                 for kx in range(3):
                     acc += xp[oy0 + ky:oy0 + ky + st * Ho:st, ox0 + kx:ox0 + kx + st * Wo:st] * w[ky * 3 + kx]
-            y = np.clip(requant(acc.reshape(Ho * Wo, cp)[:, :cout], epi), -128, 127)
+            y = np.clip(requant(acc.reshape(Ho * Wo, -1)[:, :cout], epi), -128, 127)
             if lut is not None:
                 y = lut_apply(y, lut)
         elif kind == 3:
@@ -106,14 +121,19 @@ def run_fused(F, img, seed=0):
         if ph["to_global"]:
             head = y.astype(np.int8)
             continue
-        out = np.zeros((rows_o, ph["chunks_out"] * 16), np.int8)
+        out = rng.integers(-128, 128, (rows_o, ph["chunks_out"] * 16)).astype(np.int8)   # pad channels: garbage (must meet zero weights)
         out[:, :cout] = y
-        if ph["out_wp"]:                            # producer writes the interior of a bordered buffer and fills the border
-            Ho, Wo = ph["Hout"], ph["Wout"]
-            full = np.full((Ho + 2, Wo + 2, ph["chunks_out"] * 16), ph["out_zp"], np.int8)
-            full[1:-1, 1:-1] = out.reshape(Ho, Wo, -1)
-            assert ph["out_cs"] == (Ho + 2) * (Wo + 2) * 16 and ph["out_wp"] == Wo + 2
-            out = full.reshape(-1, ph["chunks_out"] * 16)
+        if ph["out_wp"]:                            # producer writes the interior of a word-planar bordered buffer and fills the border
+            Ho, Wo, nw = ph["Hout"], ph["Wout"], ph["nw"]
+            full = np.full((Ho + 2, Wo + 2, nw * 4), ph["out_zp"], np.int8)
+            full[1:-1, 1:-1] = out.reshape(Ho, Wo, -1)[:, :, :nw * 4]
+            cells = (Ho + 2) * (Wo + 2)
+            assert ph["out_ws"] >= cells * 4 and ph["out_wp"] == Wo + 2
+            full = full.reshape(cells, nw * 4)
+            for w in range(nw):
+                a = ph["out_off"] + w * ph["out_ws"]
+                smem[a:a + cells * 4] = full[:, w * 4:(w + 1) * 4].reshape(-1).view(np.uint8)
+            continue
         for g in range(ph["chunks_out"]):
             a = ph["out_off"] + g * ph["out_cs"]
             smem[a:a + out.shape[0] * 16] = out[:, g * 16:(g + 1) * 16].reshape(-1).view(np.uint8)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase SM-cycle trace of the fused kernel (CTA 0, first image). usage: fused_trace.py [n_images]"""
+"""Per-phase SM-cycle trace of the fused kernel (CTA 0, first image).
+usage: make -C stm32h7-yolo_b200/csrc TRACE=1 && YF_B200_LIB=stm32h7-yolo_b200/libyoloface_b200_trace.so python tools/fused_trace.py [n_images]"""
 import os
 import sys
 
@@ -32,10 +33,11 @@ for im in range(2 if n > 296 else 1):
     for i, s in enumerate(steps):
         d = st[base + i + 1] - st[base + i]
         print("  %-14s kind %d rows %4d cout %2d  %7d cyc  %5.1f%%" % (s["name"], s["kind"], F["phases"][i]["rows_out"], F["phases"][i]["cout"], d, 100.0 * d / tot))
-    sub = st[80 + 8 * im:80 + 8 * im + 7]
-    print("  phase 14 sub-stamps: param wait %d | mma issue %d | mma wait %d | epilogue %d | fence %d | barrier %d" % tuple(sub[i + 1] - sub[i] for i in range(6)))
 inner = st[96:108]
-print("inner stamps of phase %s (thread 0): entry->setup %d | setup->iter0 %d | iters %s | loop end->ret %s | fence %d | barrier %d" % (
-    os.environ.get("YF_B200_TRACE_PHASE", "1"), inner[1] - inner[0], inner[2] - inner[1], [inner[i + 1] - inner[i] for i in range(2, 7)],
-    inner[9] - inner[8], inner[10] - inner[9], inner[11] - inner[10]))
+tph = int(os.environ.get("YF_B200_TRACE_PHASE", "1"))
+if F["phases"][tph]["kind"] == 1:
+    print("phase %d (conv) thread 0: params there -> MMAs committed %d | housekeeping %d | -> accumulators ready %d | epilogue %d | fence %d | barrier %d" % (
+        tph, inner[1] - inner[0], inner[2] - inner[1], inner[3] - inner[2], inner[4] - inner[3], inner[10] - inner[4], inner[11] - inner[10]))
+elif F["phases"][tph]["kind"] == 2:
+    print("phase %d (depthwise) thread 0: entry->setup %d | loop %d | fence %d | barrier %d" % (tph, inner[1] - inner[0], inner[8] - inner[1], inner[10] - inner[8], inner[11] - inner[10]))
 net.close()
