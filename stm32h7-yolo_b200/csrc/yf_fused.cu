@@ -86,15 +86,15 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
   return (static_cast<uint64_t>(0x4008u) << 32) | static_cast<uint64_t>(lo_tmpl | ((saddr >> 4) & 0x3FFFu));
 }
 
-// x / d for small non-negative x (x < 4096), d <= 64: exact (margin 0.5/(x+0.5) >> float error)
-__device__ __forceinline__ int small_div(int x, int d) { return static_cast<int>(__fdividef(static_cast<float>(x) + 0.5f, static_cast<float>(d))); }
+// x / d for the small non-negative x of this kernel: rcp = ceil(2^20 / d), exactness checked on the host (build_fused)
+__device__ __forceinline__ int small_div(int x, uint32_t rcp) { return static_cast<int>((static_cast<uint32_t>(x) * rcp) >> 20); }
 
 // border cells of a padded output buffer <- the tensor's zero point (run by the workers while the MMAs are in flight)
 __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem, int tid) {
   const int WP = ph.out_wp, H = ph.Hout, ncell = 2 * WP + 2 * H;
   const uint32_t z = static_cast<uint32_t>(ph.out_zp & 0xff) * 0x01010101u;
   for (int i = tid; i < ncell * ph.nw; i += kFusedThreads) {
-    const int c = small_div(i, ncell), k = i - c * ncell;
+    const int c = small_div(i, ph.rcp_ncell), k = i - c * ncell;
     int cell;
     if (k < WP) cell = k;
     else if (k < 2 * WP) cell = (H + 1) * WP + (k - WP);
@@ -163,7 +163,7 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
     for (int j = 0; j < 8; ++j)
       if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
   } else if (ph.out_wp) {                                    // word-planar, zero-point-bordered: depthwise / pool consumers
-    const int y = small_div(row, ph.Wout);
+    const int y = small_div(row, ph.rcp_wout);
     uint8_t* o = smem + ph.out_off + g * 4 * ph.out_ws + ((y + 1) * ph.out_wp + (row - y * ph.Wout) + 1) * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -202,7 +202,7 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   const int nw = ph.nw, per = ph.per;
   YF_STAMP(tp, 0);
   if (tid >= per * nw) return;
-  int pix = small_div(tid, nw);
+  int pix = small_div(tid, ph.rcp_nw);
   const int wd = tid - pix * nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
   const uint32_t* w1h = reinterpret_cast<const uint32_t*>(slot + ph.dw_off);
   const uint8_t* kb = slot + ph.dwepi_off + wd * 64;
@@ -227,13 +227,13 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   const uint8_t* ib = smem + ph.in_off + wd * ph.in_ws + ((1 - ph.pad_t) * WP + (1 - ph.pad_l)) * 4;
   uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
   const bool has_lut = ph.has_lut != 0;
-  const int oy = small_div(pix, Wout);
+  const int oy = small_div(pix, ph.rcp_wout);
   int ox = pix - oy * Wout;
   // pointer-incremental sweep: +per pixels = +dy rows +dx columns, wrapping once at most
   const uint8_t* p = ib + (oy * stride * WP + ox * stride) * 4;
   uint8_t* o = ob + pix * 16;
   const int dP = (dy * stride * WP + dx * stride) * 4, dWrap = (stride * WP - Wout * stride) * 4, dO = per * 16;
-  int n_it = pix < rows ? small_div(rows - 1 - pix, per) + 1 : 0;
+  int n_it = pix < rows ? small_div(rows - 1 - pix, ph.rcp_per) + 1 : 0;
   YF_STAMP(tp, 1);
   for (; n_it > 0; --n_it) {
     uint32_t x[9];
@@ -272,7 +272,7 @@ __device__ __forceinline__ uint32_t repack(uint32_t ev, uint32_t od) { return __
 __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
   const int nw = ph.nw, per = ph.per;
   const bool active = tid < per * nw;
-  const int it0 = small_div(tid, nw), wd = tid - it0 * nw;
+  const int it0 = small_div(tid, ph.rcp_nw), wd = tid - it0 * nw;
   const int Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout, k = ph.ksize, stride = ph.stride;
   const int sws = ph.scratch_ws;                              // word-plane stride of the row-maxima scratch
   const uint32_t neg = 0x80808080u;
@@ -282,7 +282,7 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
     uint8_t* sb = smem + ph.scratch_off + wd * sws;
     const int total = Hin * Wout;
     int it = it0;
-    int y = small_div(it, Wout), ox = it - y * Wout;
+    int y = small_div(it, ph.rcp_wout), ox = it - y * Wout;
     for (; it < total; it += per) {
       const int x0 = max(0, ox * stride - ph.pad_l), x1 = min(Win, ox * stride - ph.pad_l + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
@@ -309,7 +309,7 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
     const uint8_t* lut = slot + ph.lut_off;
     const int total = Hout * Wout;
     int it = it0;
-    int oy = small_div(it, Wout), ox = it - oy * Wout;
+    int oy = small_div(it, ph.rcp_wout), ox = it - oy * Wout;
     for (; it < total; it += per) {
       const int y0 = max(0, oy * stride - ph.pad_t), y1 = min(Hin, oy * stride - ph.pad_t + k);
       uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
@@ -346,7 +346,7 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
   uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
   const int rr = (2 * r + hf) * 128 + rt;
   if (rr >= ph.rows_out) return;
-  const int oy = small_div(rr, ph.Wout), ox = rr - oy * ph.Wout;
+  const int oy = small_div(rr, ph.rcp_wout), ox = rr - oy * ph.Wout;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = 2 * oy - 1 + ky;
@@ -368,11 +368,11 @@ constexpr int kCtrlWarp = kFusedThreads / 32 - 1;        // TMEM lane quarter 3 
 
 __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.bars_off);
-  uint64_t* in_full = bars;                 // input image landed
-  uint64_t* par_full = bars + 1;            // [kFusedParamSlots] parameter slot landed
-  uint64_t* mma_done = bars + 1 + kFusedParamSlots;   // [2] accumulators ready (two used by the first conv's rounds)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + kFusedParamSlots);
+  // mbarriers, as 32-bit shared-space addresses (8 bytes each): input image landed | [kFusedParamSlots] parameter slot
+  // landed | [2] accumulators ready (two used by the first conv's rounds)
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t in_full = smem_base + a.bars_off, par_full = in_full + 8, mma_done = par_full + 8 * kFusedParamSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // The last warp doubles as the control warp: it runs the MMA-issue loops convergently (one elected lane issues,
   // operands stay warp-uniform) and its lane 0 issues every bulk copy.
@@ -380,9 +380,7 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
   const bool lead = tid == kCtrlWarp * 32;
 
   if (tid == 0) {
-    mbar_init(in_full, 1);
-    for (int i = 0; i < kFusedParamSlots; ++i) mbar_init(&par_full[i], 1);
-    mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+    for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
@@ -397,13 +395,12 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
   }
   const FusedPhase* s_ph = reinterpret_cast<const FusedPhase*>(smem + a.desc_off);
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t smem_base = smem_u32(smem);
   uint32_t use0 = 0u, use1 = 0u, in_uses = 0u;              // completed waits on mma_done[0/1], in_full
   bool ok = true;
   const int nph = a.nphases;
   const int my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const uint32_t total_pc = static_cast<uint32_t>(my_images) * static_cast<uint32_t>(nph);
-  auto wait_bar = [&](uint64_t* bar, uint32_t parity, int code) {
+  auto wait_bar = [&](uint32_t bar, uint32_t parity, int code) {
     if (ok && !mbar_wait(bar, parity)) { atomicCAS(a.err, 0, code); ok = false; }
   };
   // ---- lead thread: parameter blocks go round the slots; block j may be requested once block j - kFusedParamSlots
@@ -414,15 +411,15 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
 #pragma unroll 1
     while (pc_next < total_pc && pc_next < pc_now + kFusedParamSlots) {
       const FusedPhase& nx = s_ph[pnext];
-      uint64_t* bar = &par_full[pc_next % kFusedParamSlots];
+      const uint32_t bar = par_full + 8 * (pc_next % kFusedParamSlots);
       mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
-      bulk_load_1d(smem + a.slot_off + (pc_next % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
+      bulk_load_1d(smem_base + a.slot_off + (pc_next % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
       ++pc_next; if (++pnext == nph) pnext = 0;
     }
   };
   if (lead && my_images > 0) {
     mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+    bulk_load_1d(smem_base + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
     refill(0);
   }
 
@@ -448,27 +445,28 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
 #else
       long long* const tp = nullptr;
 #endif
-      wait_bar(&par_full[pc % kFusedParamSlots], (pc / kFusedParamSlots) & 1, 302);
+      const uint32_t par_bar = par_full + 8 * (pc % kFusedParamSlots), par_parity = (pc / kFusedParamSlots) & 1;
       const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
       // lead thread, off the critical path: refill the slot the previous phase released, prefetch the next image
       auto housekeeping = [&]() {
         refill(pc);
         if (p == a.in_pf_phase && img + static_cast<int>(gridDim.x) < a.n_img) {     // the image buffer is free after phase 0
           mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-          bulk_load_1d(smem + a.in_off, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
+          bulk_load_1d(smem_base + a.in_off, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
         }
       };
       if (kind == STEP_CONV1X1) {
         for (int t0 = 0; t0 < ntiles; t0 += tpg) {
           const int nt = min(tpg, ntiles - t0);
           if (ctrl) {                                         // every tile of the group, one commit
+            if (t0 == 0) wait_bar(par_bar, par_parity, 302);  // the weights
             tc_fence_after();
             const bool el = elect_one();
             for (int t = 0; t < nt; ++t)
               for (int k = 0; k < nk; ++k)
                 if (el) mma_i8(tmem_base + t * npad, mk_desc(adesc_lo, sA + (t0 + t) * 2048 + k * 2 * in_cs),
                                mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
-            if (el) mma_commit(&mma_done[0]);
+            if (el) mma_commit(mma_done);
             __syncwarp();
             if (lead && t0 == 0 && !ctrl_busy) housekeeping();
             __syncwarp();
@@ -480,7 +478,8 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
           const bool has_rows = nt >= kFusedWarpgroups ? (t0 + wg) * 128 + (warp & 3) * 32 < rows_out
                                                        : (t0 * 128 + (warp & 3) * 32 < rows_out && wg < ph.chunks_out);
           if (has_rows) {
-            wait_bar(&mma_done[0], use0 & 1, 301);
+            if (t0 == 0 && !ctrl) wait_bar(par_bar, par_parity, 302);   // table and requant constants
+            wait_bar(mma_done, use0 & 1, 301);
             tc_fence_after();
             conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, t0, nt);
             tc_fence_before();
@@ -491,11 +490,12 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
         if (lead && ctrl_busy) housekeeping();
       } else if (kind == STEP_CONV_IM2COL) {
         if (ph.out_wp) fill_border(ph, smem, tid);
+        wait_bar(par_bar, par_parity, 302);
         wait_bar(in_full, in_uses & 1, 303); ++in_uses;
         const int rounds = (ntiles + 1) >> 1;
         for (int r = 0; r < rounds; ++r) {
           if (r >= 2) {                                       // the A stages of round r-2 must have been consumed
-            if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 304); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 304); ++use0; }
+            if (r & 1) { wait_bar(mma_done + 8, use1 & 1, 304); ++use1; } else { wait_bar(mma_done, use0 & 1, 304); ++use0; }
           }
           im2col_build(ph, smem, tid, r);
           fence_proxy_async_smem();
@@ -510,18 +510,19 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
               for (int k = 0; k < 2; ++k)
                 if (el) mma_i8(tmem_base + tt * npad, mk_desc(adesc_lo, sS + k * 4096), mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
             }
-            if (el) mma_commit(&mma_done[r & 1]);
+            if (el) mma_commit(mma_done + 8 * (r & 1));
             __syncwarp();
           }
         }
         for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
-          if (r & 1) { wait_bar(&mma_done[1], use1 & 1, 305); ++use1; } else { wait_bar(&mma_done[0], use0 & 1, 305); ++use0; }
+          if (r & 1) { wait_bar(mma_done + 8, use1 & 1, 305); ++use1; } else { wait_bar(mma_done, use0 & 1, 305); ++use0; }
         }
         tc_fence_after();
         conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, 0, ntiles);
         tc_fence_before();
         if (lead) housekeeping();
       } else {
+        wait_bar(par_bar, par_parity, 302);
         if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, tp);
         else if (kind == STEP_MAXPOOL) pool_phase(ph, smem, slot, tid);
         if (lead && pc_next <= pc + 1) housekeeping();        // only when the next phase's block is not even requested yet

@@ -665,6 +665,19 @@ bool build_fused(const Plan& P, FusedProgram* F) {
       ph.tpg = (ph.ntiles + groups - 1) / groups;
     }
     ph.scratch_ws = s.kind == STEP_MAXPOOL ? plane_stride(s.Hin * s.Wout, ph.nw) : 0;
+    {
+      // reciprocal multipliers; every quotient the kernel forms has x < 4096
+      auto rcp = [&](int d, int xmax, uint32_t* out) {
+        if (d <= 0) { *out = 0; return true; }
+        const uint32_t m = static_cast<uint32_t>(((1u << 20) + d - 1) / d);
+        for (int x = 0; x <= xmax; ++x) if (((static_cast<uint64_t>(x) * m) >> 20) != static_cast<uint64_t>(x / d) || static_cast<uint64_t>(x) * m >= (1ull << 32)) return false;
+        *out = m; return true;
+      };
+      const int ncell = ph.out_wp ? 2 * ph.out_wp + 2 * ph.Hout : 0;
+      const int xmax = std::max({kFusedWorkerThreads, ph.ntiles * 128, ph.Hin * ph.Wout + kFusedWorkerThreads, ncell * ph.nw + kFusedWorkerThreads, ph.rows_out});
+      if (xmax >= 4096 || !rcp(ph.nw, xmax, &ph.rcp_nw) || !rcp(ph.Wout, xmax, &ph.rcp_wout) || !rcp(ncell, xmax, &ph.rcp_ncell) || !rcp(ph.per, xmax, &ph.rcp_per))
+        return no("index range of step " + s.name + " exceeds the kernel's mul-shift division");
+    }
     ph.idesc = static_cast<int32_t>((2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(s.Npad >> 3) << 17) | (8u << 24));
     ph.adesc_lo = static_cast<uint32_t>(((s.kind == STEP_CONV_IM2COL ? 2048 : ph.in_cs) >> 4) & 0x3FFF) << 16;
     ph.bdesc_lo = static_cast<uint32_t>(((s.Npad * 16) >> 4) & 0x3FFF) << 16;

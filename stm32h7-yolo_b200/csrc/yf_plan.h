@@ -182,6 +182,8 @@ struct alignas(16) FusedPhase {
   int32_t in_wp, out_wp;        // padded row width in cells of the input / output buffer (0 = not padded)
   int32_t out_zp;               // border value of a padded output buffer (its tensor's zero point)
   int32_t in_ws, out_ws;        // bytes between the word planes of a padded input / output buffer
+  // x / d == (x * rcp_d) >> 20 for the small x the kernel divides (checked exhaustively by build_fused)
+  uint32_t rcp_nw, rcp_wout, rcp_ncell, rcp_per;   // d = nw, Wout, border cells (2*out_wp + 2*Hout), per
 };
 static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied to shared memory with 16-byte loads");
 

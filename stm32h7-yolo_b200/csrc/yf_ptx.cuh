@@ -33,37 +33,39 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
+// (the overloads taking a uint32_t work on a shared-space address the caller converted once)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { mbar_arrive_expect_tx(smem_u32(bar), bytes); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait(smem_u32(bar), parity); }
 // same, but the hardware may keep the thread suspended for up to `hint_ns` before it reports "not yet":
 // a waiting warp then costs (almost) no issue slots
-__device__ __forceinline__ bool mbar_try_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must never hang the GPU box.  Gives up after ~2^32 SM cycles (~2 s);
 // callers record the failure in a global error word and drain.
-static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   unsigned ns = 32;
 #pragma unroll 1
@@ -77,13 +79,14 @@ static __device__ __noinline__ bool mbar_wait_slow(uint64_t* bar, uint32_t parit
     if (clock64() - t0 > (1ll << 32)) return false;
   }
 }
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;                 // the common case: already complete
 #pragma unroll 1
   for (int i = 0; i < 16; ++i)
     if (mbar_try_wait_suspend(bar, parity, 4000u)) return true;
   return mbar_wait_slow(bar, parity);
 }
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) { return mbar_wait(smem_u32(bar), parity); }
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -97,11 +100,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 // 1D bulk copy global -> smem (UBLKCP); bytes multiple of 16, both addresses 16-B aligned
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  bulk_load_1d(smem_u32(smem_dst), gsrc, bytes, smem_u32(bar));
 }
 // 1D bulk copy smem -> global
 __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
@@ -144,10 +150,10 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_
       : "memory");
 }
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mma_commit(uint64_t* bar) { mma_commit(smem_u32(bar)); }
 // warp-collective: 32 lanes x 16 consecutive 32-bit columns; lane i of the warp reads TMEM lane
 // (taddr.lane + i); the warp may only touch lanes [32*(warpid%4), +32)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
