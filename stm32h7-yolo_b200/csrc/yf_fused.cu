@@ -198,6 +198,18 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* sme
 
 
 // DEPTHWISE_CONV_2D 3x3
+// requantise the four channels of one word and store it
+__device__ __forceinline__ void dw_store(const int32_t (&acc)[4], const int32_t (&k_mult)[4], const int32_t (&k_c2p)[4], const int32_t (&k_e)[4],
+                                         bool has_lut, const uint8_t* lut, uint8_t* o) {
+  uint32_t ow = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
+    ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(lut[idx]) : (idx ^ 0x80)) << (8 * j);
+  }
+  *reinterpret_cast<uint32_t*>(o) = ow;
+}
+
 __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, long long* tp) {
   const int nw = ph.nw, per = ph.per;
   YF_STAMP(tp, 0);
@@ -205,16 +217,17 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   int pix = small_div(tid, ph.rcp_nw);
   const int wd = tid - pix * nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
   const uint32_t* w1h = reinterpret_cast<const uint32_t*>(slot + ph.dw_off);
-  const uint8_t* kb = slot + ph.dwepi_off + wd * 64;
+  const uint8_t* kb = slot + ph.dwepi_off + wd * 16;          // [bias | mult | c2p | e][nw] int4: consecutive words are contiguous
   const uint8_t* lut = slot + ph.lut_off;
-  // The nine one-hot weight vectors are re-read from the slot for every pixel (one broadcast LDS.128 per tap)
-  // rather than held in 36 registers: the kernel runs three CTAs per SM on 80 registers per thread.
+  // The nine one-hot weight vectors stay in the slot (three CTAs per SM leave 80 registers per thread, not room
+  // for 36 weight words); every LDS.128 of a tap is shared by the two pixels of a loop step.
   const uint4* wv = reinterpret_cast<const uint4*>(w1h + ch0);
   const int wstep = cp >> 2;                                  // uint4 elements between taps
   int32_t k_bias[4], k_mult[4], k_c2p[4], k_e[4];
   {
-    const int4 b = *reinterpret_cast<const int4*>(kb), m = *reinterpret_cast<const int4*>(kb + 16);
-    const int4 c = *reinterpret_cast<const int4*>(kb + 32), e = *reinterpret_cast<const int4*>(kb + 48);
+    const int ks = nw * 16;
+    const int4 b = *reinterpret_cast<const int4*>(kb), m = *reinterpret_cast<const int4*>(kb + ks);
+    const int4 c = *reinterpret_cast<const int4*>(kb + 2 * ks), e = *reinterpret_cast<const int4*>(kb + 3 * ks);
     k_bias[0] = b.x; k_bias[1] = b.y; k_bias[2] = b.z; k_bias[3] = b.w;
     k_mult[0] = m.x; k_mult[1] = m.y; k_mult[2] = m.z; k_mult[3] = m.w;
     k_c2p[0] = c.x; k_c2p[1] = c.y; k_c2p[2] = c.z; k_c2p[3] = c.w;
@@ -235,30 +248,52 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   const int dP = (dy * stride * WP + dx * stride) * 4, dWrap = (stride * WP - Wout * stride) * 4, dO = per * 16;
   int n_it = pix < rows ? small_div(rows - 1 - pix, ph.rcp_per) + 1 : 0;
   YF_STAMP(tp, 1);
-  for (; n_it > 0; --n_it) {
-    uint32_t x[9];
+  for (; n_it >= 2; n_it -= 2) {                              // two pixels (this one and the one `per` further) per step
+    const uint8_t* q = p + dP;
+    int oxq = ox + dx;
+    if (oxq >= Wout) { oxq -= Wout; q += dWrap; }
+    int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+    int32_t bcc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      uint32_t xa[3], xb[3];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        xa[kx] = *reinterpret_cast<const uint32_t*>(p + ky * row4 + kx * 4);
+        xb[kx] = *reinterpret_cast<const uint32_t*>(q + ky * row4 + kx * 4);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint4 w = wv[(ky * 3 + kx) * wstep];
+        acc[0] = __dp4a(static_cast<int>(xa[kx]), static_cast<int>(w.x), acc[0]);
+        acc[1] = __dp4a(static_cast<int>(xa[kx]), static_cast<int>(w.y), acc[1]);
+        acc[2] = __dp4a(static_cast<int>(xa[kx]), static_cast<int>(w.z), acc[2]);
+        acc[3] = __dp4a(static_cast<int>(xa[kx]), static_cast<int>(w.w), acc[3]);
+        bcc[0] = __dp4a(static_cast<int>(xb[kx]), static_cast<int>(w.x), bcc[0]);
+        bcc[1] = __dp4a(static_cast<int>(xb[kx]), static_cast<int>(w.y), bcc[1]);
+        bcc[2] = __dp4a(static_cast<int>(xb[kx]), static_cast<int>(w.z), bcc[2]);
+        bcc[3] = __dp4a(static_cast<int>(xb[kx]), static_cast<int>(w.w), bcc[3]);
+      }
+    }
+    dw_store(acc, k_mult, k_c2p, k_e, has_lut, lut, o);
+    dw_store(bcc, k_mult, k_c2p, k_e, has_lut, lut, o + dO);
+    o += 2 * dO; p = q + dP; ox = oxq + dx;
+    if (ox >= Wout) { ox -= Wout; p += dWrap; }
+  }
+  if (n_it) {
+    int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) x[ky * 3 + kx] = *reinterpret_cast<const uint32_t*>(p + ky * row4 + kx * 4);
-    int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const uint4 w = wv[t * wstep];
-      acc[0] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.x), acc[0]);
-      acc[1] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.y), acc[1]);
-      acc[2] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.z), acc[2]);
-      acc[3] = __dp4a(static_cast<int>(x[t]), static_cast<int>(w.w), acc[3]);
-    }
-    uint32_t ow = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
-      ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(lut[idx]) : (idx ^ 0x80)) << (8 * j);
-    }
-    *reinterpret_cast<uint32_t*>(o) = ow;
-    o += dO; p += dP; ox += dx;
-    if (ox >= Wout) { ox -= Wout; p += dWrap; }
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(p + ky * row4 + kx * 4);
+        const uint4 w = wv[(ky * 3 + kx) * wstep];
+        acc[0] = __dp4a(static_cast<int>(x), static_cast<int>(w.x), acc[0]);
+        acc[1] = __dp4a(static_cast<int>(x), static_cast<int>(w.y), acc[1]);
+        acc[2] = __dp4a(static_cast<int>(x), static_cast<int>(w.z), acc[2]);
+        acc[3] = __dp4a(static_cast<int>(x), static_cast<int>(w.w), acc[3]);
+      }
+    dw_store(acc, k_mult, k_c2p, k_e, has_lut, lut, o);
   }
   YF_STAMP(tp, 8);
 }

@@ -716,14 +716,16 @@ bool build_fused(const Plan& P, FusedProgram* F) {
       ph.epi_off = put_epi();
     } else if (s.kind == STEP_DW) {
       ph.dw_off = put(P.wblob.data() + s.w_off, s.w_bytes);             // [9][CP] one-hot words
-      // per 4-channel word: {bias' x4 | mult x4 | c2p x4 | e x4} = 64 bytes, c2p = c2 + (128 << e)
-      std::vector<uint8_t> e(static_cast<size_t>(ph.nw) * 64, 0);
+      // four arrays [bias' | mult | c2p | e], each [nw words][4 channels] int32, c2p = c2 + (128 << e): the threads of
+      // a warp (consecutive words) read consecutive 16-byte groups of one array
+      const size_t arr = static_cast<size_t>(ph.nw) * 16;
+      std::vector<uint8_t> e(arr * 4, 0);
       for (int c = 0; c < s.Cout; ++c) {
         const EpiCh& k = P.epi[s.epi_base + c];
-        uint8_t* b = e.data() + static_cast<size_t>(c / 4) * 64; const int j = c % 4;
+        uint8_t* b = e.data() + static_cast<size_t>(c) * 4;
         const int32_t c2p = k.c2 + (128 << k.e), bf = bias_of(k);
-        std::memcpy(b + 4 * j, &bf, 4); std::memcpy(b + 16 + 4 * j, &k.mult, 4);
-        std::memcpy(b + 32 + 4 * j, &c2p, 4); std::memcpy(b + 48 + 4 * j, &k.e, 4);
+        std::memcpy(b, &bf, 4); std::memcpy(b + arr, &k.mult, 4);
+        std::memcpy(b + 2 * arr, &c2p, 4); std::memcpy(b + 3 * arr, &k.e, 4);
       }
       ph.dwepi_off = put(e.data(), e.size());
     }

@@ -83,12 +83,13 @@ def run_fused(F, img, seed=0):
             w = np.zeros((9, cp), np.int64)
             for c in range(cp):
                 w[:, c] = ((w1h[:, c] >> (8 * (c % 4))) & 0xFF).astype(np.uint8).view(np.int8)
-            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + ph["nw"] * 64].reshape(ph["nw"], 64)   # {bias' x4 | mult x4 | c2p x4 | e x4}
-            epi = np.zeros(ph["nw"] * 4, epi_all.dtype)
-            epi["mult"] = raw[:, 16:32].copy().view("<i4").reshape(-1)
-            epi["add64"] = raw[:, 0:16].copy().view("<i4").reshape(-1).astype(np.int64) * epi["mult"].astype(np.int64) + (1 << 30)
-            epi["e"] = raw[:, 48:64].copy().view("<i4").reshape(-1)
-            epi["c2"] = raw[:, 32:48].copy().view("<i4").reshape(-1) - (128 << epi["e"])
+            nch = ph["nw"] * 4
+            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + nch * 16].copy().view("<i4").reshape(4, nch)   # [bias' | mult | c2p | e][nw*4]
+            epi = np.zeros(nch, epi_all.dtype)
+            epi["mult"] = raw[1]
+            epi["add64"] = raw[0].astype(np.int64) * raw[1].astype(np.int64) + (1 << 30)
+            epi["e"] = raw[3]
+            epi["c2"] = raw[2] - (128 << epi["e"])
             epi["sgn_mask"] = -1
             epi = epi[:cout]
             ref = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
