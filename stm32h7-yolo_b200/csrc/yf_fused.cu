@@ -399,7 +399,10 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
   }
 }
 
-constexpr int kCtrlWarp = kFusedThreads / 32 - 1;        // TMEM lane quarter 3 of warpgroup 1: no rows in the 7x7 and 14x14 epilogues
+constexpr int kCtrlWarp = kFusedCtrlWarp;                // TMEM lane quarter 3 of warpgroup 1: no rows in the 7x7 and 14x14 epilogues
+// named barrier 1: the control warp (the only one polling the accumulator mbarrier) releases the epilogue warps
+__device__ __forceinline__ void epi_bar_sync(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
+__device__ __forceinline__ void epi_bar_arrive(int threads) { asm volatile("bar.arrive 1, %0;" ::"r"(threads) : "memory"); }
 
 __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -491,8 +494,14 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
         }
       };
       if (kind == STEP_CONV1X1) {
-        for (int t0 = 0; t0 < ntiles; t0 += tpg) {
+        uint32_t grp = ph.grp_warps;
+        for (int t0 = 0; t0 < ntiles; t0 += tpg, grp >>= 8) {
           const int nt = min(tpg, ntiles - t0);
+          // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 7x7 and 14x14 layers)
+          // never touch TMEM: they go straight to the end-of-phase barrier
+          const bool has_rows = fused_has_rows(warp, t0, nt, rows_out, ph.chunks_out);
+          const int meet = static_cast<int>(grp & 0xffu) * 32;   // threads at the release barrier: row owners + control warp
+          if (t0 == 0 && ph.out_wp && !ctrl) fill_border(ph, smem, tid);
           if (ctrl) {                                         // every tile of the group, one commit
             if (t0 == 0) wait_bar(par_bar, par_parity, 302);  // the weights
             tc_fence_after();
@@ -503,23 +512,24 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
                                mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
             if (el) mma_commit(mma_done);
             __syncwarp();
+            if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
+            // the control warp alone polls the accumulator barrier and then releases the row owners through a
+            // hardware barrier, where waiting costs no issue slots
+            wait_bar(mma_done, use0 & 1, 301);
+            tc_fence_before();
+            if (has_rows) epi_bar_sync(meet); else epi_bar_arrive(meet);
             if (lead && t0 == 0 && !ctrl_busy) housekeeping();
             __syncwarp();
+          } else if (has_rows) {
+            if (t0 == 0) wait_bar(par_bar, par_parity, 302);  // table and requant constants
+            epi_bar_sync(meet);
           }
-          if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
-          // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 7x7 and 14x14 layers)
-          // neither poll the barrier nor touch TMEM: they go straight to the end-of-phase barrier
-          const int wg = warp >> 2;
-          const bool has_rows = nt >= kFusedWarpgroups ? (t0 + wg) * 128 + (warp & 3) * 32 < rows_out
-                                                       : (t0 * 128 + (warp & 3) * 32 < rows_out && wg < ph.chunks_out);
+          ++use0;
           if (has_rows) {
-            if (t0 == 0 && !ctrl) wait_bar(par_bar, par_parity, 302);   // table and requant constants
-            wait_bar(mma_done, use0 & 1, 301);
             tc_fence_after();
             conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, t0, nt);
             tc_fence_before();
           }
-          ++use0;
           if (t0 + tpg < ntiles) __syncthreads();             // the next group overwrites these TMEM columns
         }
         if (lead && ctrl_busy) housekeeping();

@@ -665,6 +665,15 @@ bool build_fused(const Plan& P, FusedProgram* F) {
       ph.tpg = (ph.ntiles + groups - 1) / groups;
     }
     ph.scratch_ws = s.kind == STEP_MAXPOOL ? plane_stride(s.Hin * s.Wout, ph.nw) : 0;
+    if (s.kind == STEP_CONV1X1) {
+      if ((ph.ntiles + ph.tpg - 1) / ph.tpg > 4) return no("more than four tile groups in step " + s.name);
+      for (int t0 = 0, g = 0; t0 < ph.ntiles; t0 += ph.tpg, ++g) {
+        const int nt = std::min(ph.tpg, ph.ntiles - t0);
+        int n = fused_has_rows(kFusedCtrlWarp, t0, nt, ph.rows_out, ph.chunks_out) ? 0 : 1;
+        for (int w = 0; w < 4 * kFusedWarpgroups; ++w) n += fused_has_rows(w, t0, nt, ph.rows_out, ph.chunks_out) ? 1 : 0;
+        ph.grp_warps |= static_cast<uint32_t>(n) << (8 * g);
+      }
+    }
     {
       // reciprocal multipliers; every quotient the kernel forms has x < 4096
       auto rcp = [&](int d, int xmax, uint32_t* out) {

@@ -184,6 +184,10 @@ struct alignas(16) FusedPhase {
   int32_t in_ws, out_ws;        // bytes between the word planes of a padded input / output buffer
   // x / d == (x * rcp_d) >> 20 for the small x the kernel divides (checked exhaustively by build_fused)
   uint32_t rcp_nw, rcp_wout, rcp_ncell, rcp_per;   // d = nw, Wout, border cells (2*out_wp + 2*Hout), per
+  // conv: byte g = warps meeting at the named barrier that releases tile group g's epilogue (the warps owning
+  // accumulator rows plus the control warp), see fused_has_rows()
+  uint32_t grp_warps;
+  int32_t pad_[3];
 };
 static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied to shared memory with 16-byte loads");
 
@@ -206,6 +210,18 @@ constexpr int kFusedWarpgroups = 2;   // warps = 4 * kFusedWarpgroups (a warp re
 constexpr int kFusedWorkerThreads = kFusedWarpgroups * 128;
 constexpr int kFusedParamSlots = 4;
 constexpr int kFusedTmemCols = 128;     // per CTA (three CTAs share an SM's 512 columns); larger layers run in tile groups
+constexpr int kFusedCtrlWarp = 4 * kFusedWarpgroups - 1;   // issues the MMAs / bulk copies (lane quarter 3 of the last warpgroup)
+
+// Does `warp` own accumulator rows of the tile group [t0, t0 + nt) of a conv phase?  A warp reads TMEM lane
+// quarter warp % 4; with several tiles in the group a warpgroup takes whole tiles (first: t0 + warp / 4), with a
+// single tile the warpgroups split its 16-channel chunks.  Shared by the kernel and the host (barrier counts).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline bool fused_has_rows(int warp, int t0, int nt, int rows_out, int chunks) {
+  const int wg = warp >> 2, q = warp & 3;
+  return nt >= kFusedWarpgroups ? (t0 + wg) * 128 + q * 32 < rows_out : (t0 * 128 + q * 32 < rows_out && wg < chunks);
+}
 bool build_fused(const Plan& plan, FusedProgram* prog);
 
 }  // namespace yf
