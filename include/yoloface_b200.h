@@ -105,7 +105,7 @@ AI_API_ENTRY int32_t yf_b200_tensor_shape(ai_handle network, int32_t tflite_tens
 typedef struct yf_b200_stats_ {
   uint64_t kernel_launches;   /* kernels of this library launched since create */
   uint64_t images;            /* images inferred since create */
-  float last_run_device_ms;   /* CUDA-event time of the last run's kernels (excl. copies) */
+  float last_run_device_ms;   /* CUDA-event time of the last run's kernels (excl. copies); 0 after a pipelined host-to-host call */
   int32_t device;
   int32_t sm_count;
   uint32_t chunk_images;
