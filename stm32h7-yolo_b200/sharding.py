@@ -17,8 +17,10 @@ def shard_bounds(n_images, world_size, rank):
 def pack_detections(dets, counts):
     """[n, max_det, 5] + [n] -> (flat [total, 5] float32, counts int32): what travels between ranks."""
     dets = np.asarray(dets, np.float32); counts = np.asarray(counts, np.int32)
-    flat = np.concatenate([dets[i, :c] for i, c in enumerate(counts)], axis=0) if len(counts) else np.zeros((0, 5), np.float32)
-    return flat.reshape(-1, 5), counts
+    if not len(counts):
+        return np.zeros((0, 5), np.float32), counts
+    keep = np.arange(dets.shape[1])[None, :] < counts[:, None]      # image-major, slot order preserved
+    return dets[keep].reshape(-1, 5), counts
 
 
 def gather_detections(flat, counts, dist=None, dst=0):
