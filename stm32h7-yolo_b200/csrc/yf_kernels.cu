@@ -10,6 +10,8 @@
 //   prep_rgb565_kernel       camera-side RGB565 112x112 -> int8 56x56x3
 //
 // Reference semantics: SURVEY.md 8a rows a2-a14; each kernel cites the row it implements.
+#include <algorithm>
+
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
 
@@ -417,7 +419,11 @@ conv_im2col_tcgen05_kernel(const ConvIm2colArgs p) {
 // dp4a against one-hot weight words avoids unpacking; out-of-bounds taps read the zero point
 // (TFLite skips them; PAD writes the zero point -- identical once -zp*sum(w) is folded in the bias).
 // ------------------------------------------------------------------------------------------
-struct DwSmem { EpiCh epi[64]; uint32_t w1h[9 * 64]; uint8_t lut[512]; };
+// Requant constants are held field-major, [field][word] of int4 (= the 4 channels of a word): the threads of a warp
+// work on consecutive words, so every constant load is 16 contiguous bytes per lane.  (Channel-major 32-byte records put
+// the lanes 128 bytes apart -- a 9-10-way bank conflict for the 36/40-channel layers, which ran at 170 GB/s.)
+enum { DWK_ADD_LO, DWK_ADD_HI, DWK_MULT, DWK_C2, DWK_E, DWK_LS, DWK_SGN, DWK_FIELDS };
+struct DwSmem { int32_t k[DWK_FIELDS][64]; uint32_t w1h[9 * 64]; uint8_t lut[512]; };
 
 __device__ __forceinline__ void tail_word(int32_t (&y)[4], int c0, const EpiOut& eo, const uint8_t* sLut, long long row) {
   // y[] = clamped int8 results of channels c0..c0+3 (already requantised)
@@ -443,20 +449,28 @@ __device__ __forceinline__ void tail_word(int32_t (&y)[4], int c0, const EpiOut&
 
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
   __shared__ DwSmem sm;
-  for (int i = threadIdx.x; i < p.eo.cout; i += blockDim.x) sm.epi[i] = c_epi[p.eo.epi_base + i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    EpiCh k{};
+    if (i < p.eo.cout) k = c_epi[p.eo.epi_base + i];
+    sm.k[DWK_ADD_LO][i] = static_cast<int32_t>(static_cast<unsigned long long>(k.add64) & 0xffffffffull);
+    sm.k[DWK_ADD_HI][i] = static_cast<int32_t>(static_cast<unsigned long long>(k.add64) >> 32);
+    sm.k[DWK_MULT][i] = k.mult; sm.k[DWK_C2][i] = k.c2; sm.k[DWK_E][i] = k.e; sm.k[DWK_LS][i] = k.ls; sm.k[DWK_SGN][i] = k.sgn_mask;
+  }
   for (int i = threadIdx.x; i < 9 * p.in_pitch; i += blockDim.x) sm.w1h[(i / p.in_pitch) * 64 + i % p.in_pitch] = p.w1h[i];
   load_luts(sm.lut, p.eo, threadIdx.x, blockDim.x);
   __syncthreads();
-  const long long total = static_cast<long long>(p.n_img) * p.Hout * p.Wout * p.words;
+  // image = blockIdx.y (strided), item inside the image in 32-bit arithmetic: 64-bit div/mod per item cost more
+  // than the convolution itself
+  const uint32_t per_img = static_cast<uint32_t>(p.Hout) * p.Wout * p.words;
   const uint32_t zpw = static_cast<uint32_t>(p.in_zp & 0xff) * 0x01010101u;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int wq = static_cast<int>(idx % p.words);
-    const long long pix = idx / p.words;
-    const int ox = static_cast<int>(pix % p.Wout);
-    const int oy = static_cast<int>((pix / p.Wout) % p.Hout);
-    const long long img = pix / (static_cast<long long>(p.Wout) * p.Hout);
-    const int8_t* base = p.in + img * p.Hin * p.Win * p.in_pitch + wq * 4;
+  for (int img = blockIdx.y; img < p.n_img; img += gridDim.y)
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per_img; idx += gridDim.x * blockDim.x) {
+    const uint32_t pixi = idx / static_cast<uint32_t>(p.words);
+    const int wq = static_cast<int>(idx - pixi * p.words);
+    const int oy = static_cast<int>(pixi / static_cast<uint32_t>(p.Wout));
+    const int ox = static_cast<int>(pixi - static_cast<uint32_t>(oy) * p.Wout);
+    const long long pix = static_cast<long long>(img) * p.Hout * p.Wout + pixi;
+    const int8_t* base = p.in + static_cast<long long>(img) * p.Hin * p.Win * p.in_pitch + wq * 4;
     int32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -473,8 +487,21 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
       }
     }
     int32_t y[4];
+    {
+      const int4 alo = *reinterpret_cast<const int4*>(&sm.k[DWK_ADD_LO][wq * 4]), ahi = *reinterpret_cast<const int4*>(&sm.k[DWK_ADD_HI][wq * 4]);
+      const int4 km = *reinterpret_cast<const int4*>(&sm.k[DWK_MULT][wq * 4]), kc = *reinterpret_cast<const int4*>(&sm.k[DWK_C2][wq * 4]);
+      const int4 ke = *reinterpret_cast<const int4*>(&sm.k[DWK_E][wq * 4]), kl = *reinterpret_cast<const int4*>(&sm.k[DWK_LS][wq * 4]);
+      const int4 ks = *reinterpret_cast<const int4*>(&sm.k[DWK_SGN][wq * 4]);
+      const int32_t a_lo[4] = {alo.x, alo.y, alo.z, alo.w}, a_hi[4] = {ahi.x, ahi.y, ahi.z, ahi.w}, mm[4] = {km.x, km.y, km.z, km.w};
+      const int32_t cc[4] = {kc.x, kc.y, kc.z, kc.w}, ee[4] = {ke.x, ke.y, ke.z, ke.w}, ll[4] = {kl.x, kl.y, kl.z, kl.w}, ss[4] = {ks.x, ks.y, ks.z, ks.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = (wq * 4 + j < p.eo.cout) ? clamp_s8(requant(acc[j], sm.epi[wq * 4 + j])) : 0;
+      for (int j = 0; j < 4; ++j) {
+        EpiCh k;
+        k.add64 = static_cast<long long>((static_cast<unsigned long long>(static_cast<uint32_t>(a_hi[j])) << 32) | static_cast<uint32_t>(a_lo[j]));
+        k.mult = mm[j]; k.c2 = cc[j]; k.e = ee[j]; k.ls = ll[j]; k.sgn_mask = ss[j];
+        y[j] = (wq * 4 + j < p.eo.cout) ? clamp_s8(requant(acc[j], k)) : 0;
+      }
+    }
     tail_word(y, wq * 4, p.eo, sm.lut, pix);
   }
 }
@@ -486,15 +513,15 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
   __shared__ uint8_t sLut[512];
   load_luts(sLut, p.eo, threadIdx.x, blockDim.x);
   __syncthreads();
-  const long long total = static_cast<long long>(p.n_img) * p.Hout * p.Wout * p.words;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int wq = static_cast<int>(idx % p.words);
-    const long long pix = idx / p.words;
-    const int ox = static_cast<int>(pix % p.Wout);
-    const int oy = static_cast<int>((pix / p.Wout) % p.Hout);
-    const long long img = pix / (static_cast<long long>(p.Wout) * p.Hout);
-    const int8_t* base = p.in + img * p.Hin * p.Win * p.in_pitch + wq * 4;
+  const uint32_t per_img = static_cast<uint32_t>(p.Hout) * p.Wout * p.words;
+  for (int img = blockIdx.y; img < p.n_img; img += gridDim.y)
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < per_img; idx += gridDim.x * blockDim.x) {
+    const uint32_t pixi = idx / static_cast<uint32_t>(p.words);
+    const int wq = static_cast<int>(idx - pixi * p.words);
+    const int oy = static_cast<int>(pixi / static_cast<uint32_t>(p.Wout));
+    const int ox = static_cast<int>(pixi - static_cast<uint32_t>(oy) * p.Wout);
+    const long long pix = static_cast<long long>(img) * p.Hout * p.Wout + pixi;
+    const int8_t* base = p.in + static_cast<long long>(img) * p.Hin * p.Win * p.in_pitch + wq * 4;
     const int y0 = max(0, oy * p.stride - p.pad_t), y1 = min(p.Hin, oy * p.stride - p.pad_t + p.k);
     const int x0 = max(0, ox * p.stride - p.pad_l), x1 = min(p.Win, ox * p.stride - p.pad_l + p.k);
     // max on sign-unpacked 16-bit lanes (VIMNMX.S16x2 is native; __vmaxs4 is a 6-instruction emulation on sm_100)
@@ -694,17 +721,24 @@ static int grid_for(long long total, int block) {
   const long long cap = 148LL * 16;
   return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
 }
+// x: 256-thread blocks over the items of one image (at most 64 so small images still spread over y), y: images
+static dim3 grid_2d(int n_img, int per_img) {
+  const int bx = std::max(1, std::min(64, (per_img + 255) / 256));
+  const long long want = (148LL * 8 + bx - 1) / bx;           // about eight resident blocks per SM in total
+  const int by = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min(n_img, 65535), want)));
+  return dim3(static_cast<unsigned>(bx), static_cast<unsigned>(by), 1);
+}
 cudaError_t launch_dw(const DwArgs& a, cudaStream_t s) {
   const long long total = static_cast<long long>(a.n_img) * a.Hout * a.Wout * a.words;
   if (total <= 0) return cudaSuccess;
   if (a.in_pitch > 64 || a.eo.cout > 64) return cudaErrorInvalidValue;
-  dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
+  dwconv3x3_kernel<<<grid_2d(a.n_img, a.Hout * a.Wout * a.words), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_pool(const PoolArgs& a, cudaStream_t s) {
   const long long total = static_cast<long long>(a.n_img) * a.Hout * a.Wout * a.words;
   if (total <= 0) return cudaSuccess;
-  maxpool_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
+  maxpool_kernel<<<grid_2d(a.n_img, a.Hout * a.Wout * a.words), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_lut(const LutArgs& a, cudaStream_t s) {
