@@ -273,8 +273,8 @@ def run_ours(args, rank, local_rank, world):
         alg = BATCH * (IN_BYTES + OUT_BYTES)
         gbps = alg / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "yoloface_fused_kernel", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak,
-                    "traffic": 2562048, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 256 images "
-                    "(profiles/r01_fused_v6_ncu_summary.txt; the 225 KB of heads were still in L2 when the capture ended)",
+                    "traffic": 2552832, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 256 images "
+                    "(profiles/r01_fused_v7c_b256_ncu_summary.txt; the 225 KB of heads were still in L2 when the capture ended)",
                     "peak_source": peak_src, "launch_ms": kernel_ms,
                     "note": "the single persistent kernel IS the step: algorithmic bytes per launch = 256 x (9,408 B image in + 882 B head out) "
                             "/ median CUDA-event duration of one launch; the kernel is latency/issue-bound, not HBM-bound (DESIGN.md 'Roofline')"}
