@@ -261,6 +261,14 @@ def run_ours(args, rank, local_rank, world):
            "ms_per_step": 1e3 * dt / args.steps,
            "blocking": {"value": world * BATCH * args.steps / dt_block, "ms_per_step": 1e3 * dt_block / args.steps,
                         "api": "yf_b200_run(host pinned in, host pinned out), one blocking call per step"}}
+    # latency of the reference's own call pattern: one image per blocking ai_network_run-style call, pageable host buffers
+    one_in, one_out = np.ascontiguousarray(h_in[0][:1].numpy()).copy(), np.zeros((1, 7, 7, 18), np.int8)
+    for _ in range(20):
+        net.run(one_in, one_out, n=1)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        net.run(one_in, one_out, n=1)
+    e2e["single_image_call_us"] = 1e6 * (time.perf_counter() - t0) / 200
     # sanity: the e2e result of the last step equals the device-resident result for that input
     last = (args.steps - 1) % RING
     net.run(d_in[last], d_out[last], n=BATCH)

@@ -151,5 +151,10 @@ AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t height, int32_t width, const void
 /* Human-readable text of the last failure (CUDA error string, plan error, ...). */
 AI_API_ENTRY const char* yf_b200_last_error_text(void);
 
+/* Test hook: queue a one-thread kernel that sets the pipeline error word the way a kernel whose bounded wait gave up
+ * does; the next synchronising call (yf_b200_sync / yf_b200_wait / a run) must fail with AI_ERROR_INVALID_STATE /
+ * AI_ERROR_CODE_LAYER and clear the word. */
+AI_API_ENTRY int32_t yf_b200_debug_raise(ai_handle network, int32_t code);
+
 AI_API_DECLARE_END
 #endif

@@ -73,7 +73,7 @@ EXPORTS = [
     "ai_network_data_params_get", "yf_b200_set_input_size", "yf_b200_run", "yf_b200_decode", "yf_b200_detect",
     "yf_b200_preprocess_rgb565", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
     "yf_b200_get_stats", "yf_b200_step_count", "yf_b200_step_info_get", "yf_b200_set_step_profiling",
-    "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_enqueue_batches", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
+    "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_enqueue_batches", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_debug_raise", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
 ]
 
 _lib = None

@@ -747,6 +747,12 @@ cudaError_t launch_lut(const LutArgs& a, cudaStream_t s) {
   lut_kernel<<<grid_for(total, 256), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
+// test hook: what a kernel whose bounded wait gave up does to the pipeline error word
+__global__ void raise_error_kernel(int* err, int code) { atomicCAS(err, 0, code); }
+cudaError_t launch_raise_error(int* d_err, int code, cudaStream_t s) {
+  raise_error_kernel<<<1, 1, 0, s>>>(d_err, code);
+  return cudaGetLastError();
+}
 cudaError_t launch_decode_nms(const DecodeArgs& a, cudaStream_t s) {
   if (a.n_img <= 0) return cudaSuccess;
   decode_nms_kernel<<<(a.n_img + 3) / 4, 128, 0, s>>>(a);

@@ -83,6 +83,7 @@ cudaError_t launch_pool(const PoolArgs& a, cudaStream_t s);
 cudaError_t launch_lut(const LutArgs& a, cudaStream_t s);
 cudaError_t launch_decode_nms(const DecodeArgs& a, cudaStream_t s);
 cudaError_t launch_prep_rgb565(const PrepArgs& a, cudaStream_t s);
+cudaError_t launch_raise_error(int* d_err, int code, cudaStream_t s);   // test hook (yf_b200_debug_raise)
 cudaError_t kernels_init();              // opt-in dynamic smem sizes
 
 // fused single-kernel path (yf_fused.cu)

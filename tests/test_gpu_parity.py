@@ -266,6 +266,34 @@ def test_caller_supplied_weights_are_used(yf, oracle, golden):
         n.close()
 
 
+def test_pipeline_watchdog_word_reaches_the_host(yf, golden):
+    """The device error word lives in mapped pinned memory: a kernel that flags a failed bounded wait must surface
+    as INVALID_STATE / LAYER at the next synchronising call, once, and the context keeps working."""
+    n = yf.Network(chunk_images=16)
+    try:
+        x = golden["images"][:4]
+        ok = n.run(x)
+        n.L.yf_b200_debug_raise.restype = C.c_int32
+        n.L.yf_b200_debug_raise.argtypes = [C.c_void_p, C.c_int32]
+        assert n.L.yf_b200_debug_raise(n.handle, 301) == 0
+        with pytest.raises(yf.AiRuntimeError, match="watchdog.*301") as ei:
+            n.sync()
+        assert (ei.value.type, ei.value.code) == (0x11, 0x14)   # AI_ERROR_INVALID_STATE / AI_ERROR_CODE_LAYER
+        assert n.get_error() == (0, 0)                      # reading the error (done by the binding) cleared the latch
+        n.sync()                                            # ... and the device word was cleared too
+        assert n.L.yf_b200_debug_raise(n.handle, 302) == 0
+        with pytest.raises(yf.AiRuntimeError, match="watchdog.*302"):
+            n.run(x)                                        # the small-batch path reads the word after its synchronise
+        assert np.array_equal(n.run(x), ok)
+        big = real_batch(golden, 40, 9)                     # the pipelined host path reads it after the ring drained
+        assert n.L.yf_b200_debug_raise(n.handle, 303) == 0
+        with pytest.raises(yf.AiRuntimeError, match="watchdog.*303"):
+            n.run(big)
+        assert n.run(big).shape == (40, 7, 7, 18)
+    finally:
+        n.close()
+
+
 def test_launch_counter(net):
     s0 = net.stats()
     net.run(np.zeros((8, 56, 56, 3), np.int8))
