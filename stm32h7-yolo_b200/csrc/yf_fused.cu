@@ -10,14 +10,17 @@
 // three phases ahead; the next image is prefetched the same way.  HBM traffic per image is the I/O
 // floor: 9,408 B in + 882 B out.  75 KB smem, 80 registers, 128 TMEM columns per CTA.
 //
-//   conv phases   thread 0 issues the MMAs of a tile group (all 128-pixel tiles whose accumulators fit
-//                 the CTA's 128 TMEM columns; the 28x28x18 layer takes two groups) and commits once;
-//                 then the 8 warps split the (tile, 16-channel) units: tcgen05.ld -> TFLite requant
-//                 -> table / ADD -> st.shared.  Thread 0 refills the parameter slots meanwhile.
+//   conv phases   the last warp (no accumulator rows of its own in the 7x7 / 14x14 layers) issues the MMAs of a tile
+//                 group convergently -- one elect.sync lane, warp-uniform descriptors -- (all 128-pixel tiles whose
+//                 accumulators fit the CTA's 128 TMEM columns; the 28x28x18 layer takes two groups), commits once,
+//                 polls the accumulator mbarrier alone and releases the row-owning warps through a named
+//                 hardware barrier; those split the (tile, 16-channel) units: tcgen05.ld -> TFLite requant
+//                 -> table / ADD -> st.shared.  Its lane 0 refills the parameter slots meanwhile.
 //   first conv    implicit GEMM: all threads build A tiles (3 x 16-B chunks per pixel, K laid out
 //                 as [ky][9 taps + 7 don't-care bytes] against zero weights), two tiles per round
-//   depthwise     CUDA cores: one thread = one 4-channel word, fixed per thread (weights and
-//                 requant constants in registers), dp4a against one-hot words, interior fast path
+//   depthwise     CUDA cores: one thread = one 4-channel word, fixed per thread (requant constants in
+//                 registers, one-hot weight words re-read from the slot and shared by the two pixels of a
+//                 loop step), dp4a, zero-point-bordered input so no bounds checks
 //   max-pool      separable (row maxima to scratch, then columns), VIMNMX3.S16x2 on unpacked lanes
 #include <cstdlib>
 
