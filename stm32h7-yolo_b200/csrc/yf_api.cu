@@ -245,6 +245,14 @@ EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* 
     eo.lut1 = s.lut_fused >= 0 ? pd->d_luts + static_cast<size_t>(s.lut_fused) * 256 : nullptr;
     eo.lut2 = nullptr;
   }
+  // lean conv epilogue: not observing, at most one of {table, ADD}, every channel in the lean requant form, and
+  // 4-byte aligned skip operand / output slot (the ADD reads the skip tensor a word at a time)
+  eo.fast = 0;
+  if (!obs && (s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && !(eo.lut1 && s.add.enabled) &&
+      (!s.add.enabled || (eo.add_coff % 4 == 0 && eo.add_pitch % 4 == 0))) {
+    eo.fast = 1;
+    for (int c = 0; c < s.Cout && eo.fast; ++c) { int32_t b; if (!epi_lean_form(P.epi[s.epi_base + c], &b)) eo.fast = 0; }
+  }
   return eo;
 }
 

@@ -14,14 +14,34 @@
 
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
+#include "yf_requant.cuh"
 
 namespace yf {
 
 __constant__ EpiCh c_epi[kMaxEpiCh];
+__constant__ EpiChF c_epif[kMaxEpiCh];   // the same channels in the lean form of yf_requant.cuh (zero where it does not apply)
+
+bool epi_lean_form(const EpiCh& k, int32_t* bias) {
+  if (k.ls != 0 || k.e < 1 || k.mult == 0 || (k.add64 - (1LL << 30)) % k.mult != 0) return false;
+  const long long b = (k.add64 - (1LL << 30)) / k.mult;
+  if (b > 0x3fffffffLL || b < -0x40000000LL) return false;
+  *bias = static_cast<int32_t>(b);
+  return true;
+}
 
 cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s) {
   if (n > kMaxEpiCh) return cudaErrorInvalidValue;
-  return cudaMemcpyToSymbolAsync(c_epi, host, sizeof(EpiCh) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_epi, host, sizeof(EpiCh) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  static EpiChF lean[kMaxEpiCh];
+  for (int i = 0; i < n; ++i) {
+    int32_t b = 0;
+    lean[i] = EpiChF{};
+    if (epi_lean_form(host[i], &b)) lean[i] = EpiChF{b, host[i].mult, host[i].c2 + (128 << host[i].e), host[i].e};
+  }
+  e = cudaMemcpyToSymbolAsync(c_epif, lean, sizeof(EpiChF) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);       // `lean` is static scratch
 }
 
 // ------------------------------------------------------------------------------------------
@@ -117,8 +137,48 @@ __device__ __forceinline__ void epilogue_row(const uint32_t (&acc)[NPAD], const 
   if (eo.mid) store_row<NPAD / 4>(eo.mid + row * eo.mid_pitch, midw, eo.cout);
 }
 
+// The lean epilogue (no observer outputs; requant constants in the 16-byte form; table XOR fused ADD): only the real
+// 4-channel words are computed, a chunk of up to 16 channels per branch-free block (yf_requant.cuh).
+template <int NPAD>
+__device__ __forceinline__ void epilogue_row_fast(const uint32_t (&acc)[NPAD], const EpiOut& eo, long long row,
+                                                  const uint8_t* sLut, const EpiChF* sEpi) {
+  uint32_t outw[NPAD / 4];
+#pragma unroll
+  for (int i = 0; i < NPAD / 4; ++i) outw[i] = 0;
+  const int nw_total = (eo.cout + 3) >> 2;
+  const int8_t* addp = eo.add.enabled ? eo.add_in + row * eo.add_pitch + eo.add_coff : nullptr;
+#pragma unroll
+  for (int g = 0; g < NPAD / 16; ++g) {
+    const int nwords = min(4, nw_total - 4 * g);               // warp-uniform
+    if (nwords > 0) {
+      uint32_t v[16], w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = acc[g * 16 + j];
+      if (eo.lut1) {
+        requant_chunk<true>(v, sEpi + g * 16, sLut, nwords, w);
+      } else {
+        requant_chunk<false>(v, sEpi + g * 16, sLut, nwords, w);
+        if (addp) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nwords) w[j] = add_word(*reinterpret_cast<const uint32_t*>(addp + g * 16 + j * 4), w[j], eo.add);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) outw[g * 4 + j] = w[j];
+    }
+  }
+  if (eo.cout & 3) outw[(eo.cout >> 2) < NPAD / 4 ? (eo.cout >> 2) : 0] &= (1u << (8 * (eo.cout & 3))) - 1u;   // pad channels of the last word: 0
+  store_row<NPAD / 4>(eo.out + row * eo.out_pitch + eo.out_coff, outw, max(eo.cout, eo.fill_to));
+}
+
 template <int NPAD>
 __device__ __forceinline__ void load_epi(EpiCh* sEpi, const EpiOut& eo, int tid, int nthreads) {
+  if (eo.fast) {                          // the same smem region holds the 16-byte records
+    EpiChF* f = reinterpret_cast<EpiChF*>(sEpi);
+    for (int i = tid; i < NPAD; i += nthreads) f[i] = i < eo.cout ? c_epif[eo.epi_base + i] : EpiChF{0, 0, 0, 0};
+    return;
+  }
   for (int i = tid; i < NPAD; i += nthreads) sEpi[i] = c_epi[eo.epi_base + (i < eo.cout ? i : 0)];
 }
 __device__ __forceinline__ void load_luts(uint8_t* sLut, const EpiOut& eo, int tid, int nthreads) {
@@ -233,7 +293,10 @@ conv1x1_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const Conv1x1A
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       const long long row = static_cast<long long>(tile) * 128 + q * 32 + lane;
-      if (row < p.M) epilogue_row<NPAD>(acc, p.eo, row, sLut, sEpi);
+      if (row < p.M) {
+        if (p.eo.fast) epilogue_row_fast<NPAD>(acc, p.eo, row, sLut, reinterpret_cast<const EpiChF*>(sEpi));
+        else epilogue_row<NPAD>(acc, p.eo, row, sLut, sEpi);
+      }
     }
   }
   tc_fence_before();
@@ -356,7 +419,8 @@ conv_im2col_tcgen05_kernel(const ConvIm2colArgs p) {
         const int r = t * 128 + q * 32 + lane;
         if (r < npix) {
           const long long row = (static_cast<long long>(img) * p.Hout + oy0) * p.Wout + r;
-          epilogue_row<NPAD>(acc, p.eo, row, sLut, sEpi);
+          if (p.eo.fast) epilogue_row_fast<NPAD>(acc, p.eo, row, sLut, reinterpret_cast<const EpiChF*>(sEpi));
+          else epilogue_row<NPAD>(acc, p.eo, row, sLut, sEpi);
         }
       }
     }

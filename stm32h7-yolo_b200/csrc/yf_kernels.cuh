@@ -22,6 +22,7 @@ struct EpiOut {
   int epi_base;
   const uint8_t* lut1;                  // device pointers to 256-byte tables (nullptr = none)
   const uint8_t* lut2;
+  int fast;                             // conv kernels: lean epilogue (no observer outputs, one table XOR ADD, lean requant form)
 };
 
 struct Conv1x1Args {
@@ -76,6 +77,7 @@ struct PrepArgs {                        // yoloface.c:26-93 on device
 };
 
 cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s);
+bool epi_lean_form(const EpiCh& k, int32_t* bias);     // can this channel's requant use the 16-byte form of yf_requant.cuh?
 cudaError_t launch_conv1x1(const CUtensorMap& tmapA, const Conv1x1Args& a, int npad, int sm_count, cudaStream_t s);
 cudaError_t launch_conv_im2col(const ConvIm2colArgs& a, int npad, int sm_count, cudaStream_t s);
 cudaError_t launch_dw(const DwArgs& a, cudaStream_t s);
