@@ -248,7 +248,7 @@ EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* 
   // lean conv epilogue: not observing, at most one of {table, ADD}, every channel in the lean requant form, and
   // 4-byte aligned skip operand / output slot (the ADD reads the skip tensor a word at a time)
   eo.fast = 0;
-  if (!obs && (s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && !(eo.lut1 && s.add.enabled) &&
+  if (!obs && (s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL || s.kind == STEP_DW) && !(eo.lut1 && s.add.enabled) &&
       (!s.add.enabled || (eo.add_coff % 4 == 0 && eo.add_pitch % 4 == 0))) {
     eo.fast = 1;
     for (int c = 0; c < s.Cout && eo.fast; ++c) { int32_t b; if (!epi_lean_form(P.epi[s.epi_base + c], &b)) eo.fast = 0; }
@@ -287,7 +287,8 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
   if (n->step_profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
   for (size_t i = 0; i < P.steps.size(); ++i) {
     const Step& s = P.steps[i];
-    const EpiOut eo = make_epi_out(pd, s, d_in, d_head);
+    EpiOut eo = make_epi_out(pd, s, d_in, d_head);
+    eo.err_word = n->d_err;
     cudaError_t e = cudaSuccess;
     if (n->step_profiling) cudaEventRecord(e0, st);
     switch (s.kind) {

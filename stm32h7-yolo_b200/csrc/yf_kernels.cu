@@ -511,6 +511,96 @@ __device__ __forceinline__ void tail_word(int32_t (&y)[4], int c0, const EpiOut&
   if (eo.mid) { int8_t* r = eo.mid + row * eo.mid_pitch + c0; for (int j = 0; j < 4; ++j) if (c0 + j < eo.cout) r[j] = static_cast<int8_t>((midw >> (8 * j)) & 0xff); }
 }
 
+// Band variant (not observing, every channel in the lean requant form): the layer streams through HBM once.
+//   unit = (image, band of `band` output rows).  The input rows a band needs are contiguous in NHWC, so ONE bulk copy
+//   (TMA engine) brings them into one of two smem stages while the CTA computes the previous unit from the other.
+//   The block size is a multiple of `words`: a thread keeps one 4-channel word, so the nine one-hot weight vectors and the
+//   requant constants sit in registers and the inner loop is 9 LDS, 36 dp4a, 4 requants, one 4-byte store.
+constexpr int kDwStageBytes = 24 * 1024;
+__global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int band, int nbands) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  uint8_t* stage0 = dsm;
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + 2 * kDwStageBytes);
+  uint8_t* sLut = dsm + 2 * kDwStageBytes + 64;
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_mbar_init(); }
+  load_luts(sLut, p.eo, tid, blockDim.x);
+  __syncthreads();
+  const int wq = tid % p.words, c0 = wq * 4, pix0 = tid / p.words, per = static_cast<int>(blockDim.x) / p.words;
+  uint32_t w[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w1h + t * p.in_pitch + c0));
+    w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
+  }
+  int32_t k_bias[4], k_mult[4], k_c2p[4], k_e[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const EpiChF k = c0 + j < p.eo.cout ? c_epif[p.eo.epi_base + c0 + j] : EpiChF{0, 0, 0, 0};
+    k_bias[j] = k.bias; k_mult[j] = k.mult; k_c2p[j] = k.c2p; k_e[j] = k.e;
+  }
+  const uint32_t keep = c0 + 4 <= p.eo.cout ? 0xffffffffu : (c0 < p.eo.cout ? (1u << (8 * (p.eo.cout - c0))) - 1u : 0u);
+  const int lim = max(p.eo.cout, p.eo.fill_to);
+  const bool has_lut = p.eo.lut1 != nullptr;
+  const uint32_t zpw = static_cast<uint32_t>(p.in_zp & 0xff) * 0x01010101u;
+  const int row_bytes = p.Win * p.in_pitch;
+  const long long units = static_cast<long long>(p.n_img) * nbands;
+  // rows [lo, hi) of the input that band b reads (clipped to the image)
+  auto rows_of = [&](int b, int* lo, int* hi) {
+    const int oy0 = b * band, oy1 = min(p.Hout, oy0 + band);
+    *lo = max(0, oy0 * p.stride - p.pad_t); *hi = min(p.Hin, (oy1 - 1) * p.stride - p.pad_t + 3);
+  };
+  auto issue = [&](long long u, int st) {
+    const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
+    int lo, hi; rows_of(b, &lo, &hi);
+    const uint32_t bytes = static_cast<uint32_t>((hi - lo) * row_bytes);
+    mbar_arrive_expect_tx(&full[st], bytes);
+    bulk_load_1d(stage0 + st * kDwStageBytes, p.in + (static_cast<long long>(img) * p.Hin + lo) * row_bytes, bytes, &full[st]);
+  };
+  bool ok = true;
+  int it = 0;
+  if (tid == 0 && blockIdx.x < units) issue(blockIdx.x, 0);
+  for (long long u = blockIdx.x; u < units && ok; u += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (tid == 0 && u + gridDim.x < units) issue(u + gridDim.x, st ^ 1);   // that stage was last read before the barrier below
+    if (!mbar_wait(&full[st], (it >> 1) & 1)) { atomicCAS(p.eo.err_word, 0, 401); ok = false; }
+    const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
+    int lo, hi; rows_of(b, &lo, &hi);
+    const int oy0 = b * band, nrows = min(p.Hout, oy0 + band) - oy0, npix = nrows * p.Wout;
+    const uint8_t* sin = stage0 + st * kDwStageBytes + c0;
+    for (int pi = pix0; pi < npix && ok; pi += per) {
+      const int r = pi / p.Wout, ox = pi - r * p.Wout, oy = oy0 + r;
+      int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * p.stride - p.pad_t + ky;
+        const bool yin = iy >= lo && iy < hi;                 // rows outside [lo, hi) are outside the image
+        const uint8_t* rowp = sin + (iy - lo) * row_bytes;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = ox * p.stride - p.pad_l + kx;
+          uint32_t x = zpw;
+          if (yin && ix >= 0 && ix < p.Win) x = *reinterpret_cast<const uint32_t*>(rowp + ix * p.in_pitch);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __dp4a(static_cast<int>(x), static_cast<int>(w[ky * 3 + kx][j]), acc[j]);
+        }
+      }
+      uint32_t ow = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
+        ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(sLut[idx]) : (idx ^ 0x80)) << (8 * j);
+      }
+      ow &= keep;
+      const long long row = (static_cast<long long>(img) * p.Hout + oy) * p.Wout + ox;
+      int8_t* o = p.eo.out + row * p.eo.out_pitch + p.eo.out_coff + c0;
+      if (c0 + 4 <= lim && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = ow;
+      else for (int j = 0; j < 4; ++j) if (c0 + j < lim) o[j] = static_cast<int8_t>((ow >> (8 * j)) & 0xff);
+    }
+    __syncthreads();                                          // everyone is done with this stage before it is refilled
+  }
+}
+
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
   __shared__ DwSmem sm;
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
@@ -796,6 +886,20 @@ cudaError_t launch_dw(const DwArgs& a, cudaStream_t s) {
   const long long total = static_cast<long long>(a.n_img) * a.Hout * a.Wout * a.words;
   if (total <= 0) return cudaSuccess;
   if (a.in_pitch > 64 || a.eo.cout > 64) return cudaErrorInvalidValue;
+  if (a.eo.fast && a.words <= 10 && a.eo.err_word) {
+    // largest band whose input rows fit one stage
+    const int row_bytes = a.Win * a.in_pitch;
+    int band = a.Hout;
+    while (band > 1 && ((band - 1) * a.stride + 3) * row_bytes > kDwStageBytes) --band;
+    if (((band - 1) * a.stride + 3) * row_bytes <= kDwStageBytes && row_bytes % 16 == 0) {
+      const int nbands = (a.Hout + band - 1) / band;
+      const long long units = static_cast<long long>(a.n_img) * nbands;
+      const int grid = static_cast<int>(std::min<long long>(units, 148LL * 4));
+      const int block = 32 * a.words * std::max(1, 320 / (32 * a.words));      // a multiple of `words`, 192..320 threads
+      dwconv3x3_band_kernel<<<grid, block, 2 * kDwStageBytes + 64 + 512, s>>>(a, band, nbands);
+      return cudaGetLastError();
+    }
+  }
   dwconv3x3_kernel<<<grid_2d(a.n_img, a.Hout * a.Wout * a.words), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
@@ -838,6 +942,7 @@ cudaError_t kernels_init() {
   YF_OPTIN(conv1x1_tcgen05_kernel<64>, gemm_smem_bytes<64>())
   YF_OPTIN(conv_im2col_tcgen05_kernel<16>, im2col_smem_bytes<16>())
   YF_OPTIN(conv_im2col_tcgen05_kernel<32>, im2col_smem_bytes<32>())
+  YF_OPTIN(dwconv3x3_band_kernel, 2 * kDwStageBytes + 64 + 512)
 #undef YF_OPTIN
   return cudaSuccess;
 }

@@ -22,7 +22,8 @@ struct EpiOut {
   int epi_base;
   const uint8_t* lut1;                  // device pointers to 256-byte tables (nullptr = none)
   const uint8_t* lut2;
-  int fast;                             // conv kernels: lean epilogue (no observer outputs, one table XOR ADD, lean requant form)
+  int fast;                             // lean epilogue (no observer outputs, one table XOR ADD, lean requant form)
+  int* err_word;                        // pipeline error word for kernels with bounded waits (may be null)
 };
 
 struct Conv1x1Args {
