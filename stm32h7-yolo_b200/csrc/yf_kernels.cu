@@ -663,6 +663,95 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
 // ------------------------------------------------------------------------------------------
 // MAX_POOL_2D (row a7) + folded QUANTIZE table (row a9): max over the in-bounds window cells.
 // ------------------------------------------------------------------------------------------
+// Band variant (not observing): unit = (image, band of output rows).  The input rows of the band arrive by one bulk copy
+// into one of two smem stages; the window maximum is separable: pass 1 reduces every staged input row horizontally
+// (row maxima per output column, kept in smem), pass 2 reduces those vertically, applies the table and stores.
+// An 8x8 window costs 8 + 8 * rows_in / rows_out loads per output instead of 64.
+constexpr int kPoolStageBytes = 40 * 1024;
+constexpr int kPoolScratchBytes = 24 * 1024;
+__device__ __forceinline__ uint32_t pk_even(uint32_t x) { return __byte_perm(x, 0u, 0xA280u); }   // bytes 0,2 sign-extended to 16-bit lanes
+__device__ __forceinline__ uint32_t pk_odd(uint32_t x) { return __byte_perm(x, 0u, 0xB391u); }    // bytes 1,3
+__device__ __forceinline__ void pk_window(const uint8_t* q, int step, int n, uint32_t& ev, uint32_t& od) {
+  for (; n >= 2; n -= 2, q += 2 * step) {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(q), b = *reinterpret_cast<const uint32_t*>(q + step);
+    ev = __vimax3_s16x2(ev, pk_even(a), pk_even(b));
+    od = __vimax3_s16x2(od, pk_odd(a), pk_odd(b));
+  }
+  if (n) {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(q);
+    ev = __vmaxs2(ev, pk_even(a)); od = __vmaxs2(od, pk_odd(a));
+  }
+}
+__global__ void __launch_bounds__(256) maxpool_band_kernel(const PoolArgs p, int band, int nbands) {
+  extern __shared__ __align__(128) uint8_t psm[];
+  uint8_t* stage0 = psm;
+  uint8_t* scratch = psm + 2 * kPoolStageBytes;               // [rows_in][Wout][words] uint32 row maxima
+  uint64_t* full = reinterpret_cast<uint64_t*>(psm + 2 * kPoolStageBytes + kPoolScratchBytes);
+  uint8_t* sLut = psm + 2 * kPoolStageBytes + kPoolScratchBytes + 64;
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_mbar_init(); }
+  load_luts(sLut, p.eo, tid, blockDim.x);
+  __syncthreads();
+  const int row_bytes = p.Win * p.in_pitch, words = p.words;
+  const long long units = static_cast<long long>(p.n_img) * nbands;
+  const uint32_t neg = 0x80808080u;
+  const int lim = max(p.eo.cout, p.eo.fill_to);
+  auto rows_of = [&](int b, int* lo, int* hi) {
+    const int oy0 = b * band, oy1 = min(p.Hout, oy0 + band);
+    *lo = max(0, oy0 * p.stride - p.pad_t); *hi = min(p.Hin, (oy1 - 1) * p.stride - p.pad_t + p.k);
+  };
+  auto issue = [&](long long u, int st) {
+    const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
+    int lo, hi; rows_of(b, &lo, &hi);
+    const uint32_t bytes = static_cast<uint32_t>((hi - lo) * row_bytes);
+    mbar_arrive_expect_tx(&full[st], bytes);
+    bulk_load_1d(stage0 + st * kPoolStageBytes, p.in + (static_cast<long long>(img) * p.Hin + lo) * row_bytes, bytes, &full[st]);
+  };
+  bool ok = true;
+  int it = 0;
+  if (tid == 0 && blockIdx.x < units) issue(blockIdx.x, 0);
+  for (long long u = blockIdx.x; u < units && ok; u += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (tid == 0 && u + gridDim.x < units) issue(u + gridDim.x, st ^ 1);
+    if (!mbar_wait(&full[st], (it >> 1) & 1)) { atomicCAS(p.eo.err_word, 0, 402); ok = false; }
+    const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
+    int lo, hi; rows_of(b, &lo, &hi);
+    const int oy0 = b * band, nrows = min(p.Hout, oy0 + band) - oy0, rin = hi - lo;
+    const uint8_t* sin = stage0 + st * kPoolStageBytes;
+    // pass 1: item = (staged input row, output column, word)
+    const int n1 = ok ? rin * p.Wout * words : 0;
+    for (int i = tid; i < n1; i += blockDim.x) {
+      const int wq = i % words, t = i / words, ox = t % p.Wout, r = t / p.Wout;
+      const int x0 = max(0, ox * p.stride - p.pad_l), x1 = min(p.Win, ox * p.stride - p.pad_l + p.k);
+      uint32_t ev = pk_even(neg), od = pk_odd(neg);
+      pk_window(sin + r * row_bytes + x0 * p.in_pitch + wq * 4, p.in_pitch, x1 - x0, ev, od);
+      reinterpret_cast<uint32_t*>(scratch)[i] = __byte_perm(ev, od, 0x6240u);
+    }
+    __syncthreads();
+    // pass 2: item = (output row of the band, output column, word)
+    const int n2 = ok ? nrows * p.Wout * words : 0;
+    for (int i = tid; i < n2; i += blockDim.x) {
+      const int wq = i % words, t = i / words, ox = t % p.Wout, r = t / p.Wout, oy = oy0 + r;
+      const int y0 = max(0, oy * p.stride - p.pad_t), y1 = min(p.Hin, oy * p.stride - p.pad_t + p.k);     // inside [lo, hi)
+      uint32_t ev = pk_even(neg), od = pk_odd(neg);
+      pk_window(scratch + (((y0 - lo) * p.Wout + ox) * words + wq) * 4, p.Wout * words * 4, y1 - y0, ev, od);
+      uint32_t m = __byte_perm(ev, od, 0x6240u);
+      const int c0 = wq * 4;
+      if (p.eo.lut1) {
+        m ^= neg;
+        m = static_cast<uint32_t>(sLut[m & 0xff]) | (static_cast<uint32_t>(sLut[(m >> 8) & 0xff]) << 8) |
+            (static_cast<uint32_t>(sLut[(m >> 16) & 0xff]) << 16) | (static_cast<uint32_t>(sLut[m >> 24]) << 24);
+      }
+      if (c0 + 4 > p.eo.cout) m &= c0 < p.eo.cout ? (1u << (8 * (p.eo.cout - c0))) - 1u : 0u;      // pad channels: 0
+      const long long row = (static_cast<long long>(img) * p.Hout + oy) * p.Wout + ox;
+      int8_t* o = p.eo.out + row * p.eo.out_pitch + p.eo.out_coff + c0;
+      if (c0 + 4 <= lim && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = m;
+      else for (int j = 0; j < 4; ++j) if (c0 + j < lim) o[j] = static_cast<int8_t>((m >> (8 * j)) & 0xff);
+    }
+    __syncthreads();                                          // stage and scratch are free again
+  }
+}
+
 __global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
   __shared__ uint8_t sLut[512];
   load_luts(sLut, p.eo, threadIdx.x, blockDim.x);
@@ -906,6 +995,23 @@ cudaError_t launch_dw(const DwArgs& a, cudaStream_t s) {
 cudaError_t launch_pool(const PoolArgs& a, cudaStream_t s) {
   const long long total = static_cast<long long>(a.n_img) * a.Hout * a.Wout * a.words;
   if (total <= 0) return cudaSuccess;
+  const bool observing = a.eo.raw || a.eo.mid || a.eo.lut2;
+  if (!observing && a.eo.err_word) {
+    const int row_bytes = a.Win * a.in_pitch;
+    int band = a.Hout;
+    auto fits = [&](int b) {
+      const int rin = std::min(a.Hin, (b - 1) * a.stride + a.k);
+      return rin * row_bytes <= kPoolStageBytes && rin * a.Wout * a.words * 4 <= kPoolScratchBytes;
+    };
+    while (band > 1 && !fits(band)) --band;
+    if (fits(band) && row_bytes % 16 == 0) {
+      const int nbands = (a.Hout + band - 1) / band;
+      const long long units = static_cast<long long>(a.n_img) * nbands;
+      const int grid = static_cast<int>(std::min<long long>(units, 148LL * 2));
+      maxpool_band_kernel<<<grid, 256, 2 * kPoolStageBytes + kPoolScratchBytes + 64 + 512, s>>>(a, band, nbands);
+      return cudaGetLastError();
+    }
+  }
   maxpool_kernel<<<grid_2d(a.n_img, a.Hout * a.Wout * a.words), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
@@ -943,6 +1049,7 @@ cudaError_t kernels_init() {
   YF_OPTIN(conv_im2col_tcgen05_kernel<16>, im2col_smem_bytes<16>())
   YF_OPTIN(conv_im2col_tcgen05_kernel<32>, im2col_smem_bytes<32>())
   YF_OPTIN(dwconv3x3_band_kernel, 2 * kDwStageBytes + 64 + 512)
+  YF_OPTIN(maxpool_band_kernel, 2 * kPoolStageBytes + kPoolScratchBytes + 64 + 512)
 #undef YF_OPTIN
   return cudaSuccess;
 }
