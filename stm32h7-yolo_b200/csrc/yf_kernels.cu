@@ -517,7 +517,9 @@ __device__ __forceinline__ void tail_word(int32_t (&y)[4], int c0, const EpiOut&
 //   The block size is a multiple of `words`: a thread keeps one 4-channel word, so the nine one-hot weight vectors and the
 //   requant constants sit in registers and the inner loop is 9 LDS, 36 dp4a, 4 requants, one 4-byte store.
 constexpr int kDwStageBytes = 24 * 1024;
-__global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int band, int nbands) {
+// `group` > 1 only with nbands == 1: a unit is then `group` consecutive whole images (contiguous in memory) -- small
+// layers (7x7x40: 2.3 KB per image) would otherwise wait for HBM latency on every unit.
+__global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int band, int nbands, int group) {
   extern __shared__ __align__(128) uint8_t dsm[];
   uint8_t* stage0 = dsm;
   uint64_t* full = reinterpret_cast<uint64_t*>(dsm + 2 * kDwStageBytes);
@@ -543,59 +545,67 @@ __global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int
   const int lim = max(p.eo.cout, p.eo.fill_to);
   const bool has_lut = p.eo.lut1 != nullptr;
   const uint32_t zpw = static_cast<uint32_t>(p.in_zp & 0xff) * 0x01010101u;
-  const int row_bytes = p.Win * p.in_pitch;
-  const long long units = static_cast<long long>(p.n_img) * nbands;
-  // rows [lo, hi) of the input that band b reads (clipped to the image)
+  const int row_bytes = p.Win * p.in_pitch, img_bytes = p.Hin * row_bytes;
+  const long long units = nbands > 1 ? static_cast<long long>(p.n_img) * nbands : (p.n_img + group - 1) / group;
+  // unit -> first image, number of images, band; rows [lo, hi) of the input that the band reads (clipped to the image)
+  auto unit_of = [&](long long u, int* img, int* nimg, int* b) {
+    if (nbands > 1) { *img = static_cast<int>(u / nbands); *b = static_cast<int>(u - static_cast<long long>(*img) * nbands); *nimg = 1; }
+    else { *img = static_cast<int>(u) * group; *b = 0; *nimg = min(group, p.n_img - *img); }
+  };
   auto rows_of = [&](int b, int* lo, int* hi) {
     const int oy0 = b * band, oy1 = min(p.Hout, oy0 + band);
     *lo = max(0, oy0 * p.stride - p.pad_t); *hi = min(p.Hin, (oy1 - 1) * p.stride - p.pad_t + 3);
   };
   auto issue = [&](long long u, int st) {
-    const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
-    int lo, hi; rows_of(b, &lo, &hi);
-    const uint32_t bytes = static_cast<uint32_t>((hi - lo) * row_bytes);
+    int img, nimg, b, lo, hi; unit_of(u, &img, &nimg, &b); rows_of(b, &lo, &hi);
+    const uint32_t bytes = nbands > 1 ? static_cast<uint32_t>((hi - lo) * row_bytes) : static_cast<uint32_t>(nimg * img_bytes);
     mbar_arrive_expect_tx(&full[st], bytes);
-    bulk_load_1d(stage0 + st * kDwStageBytes, p.in + (static_cast<long long>(img) * p.Hin + lo) * row_bytes, bytes, &full[st]);
+    bulk_load_1d(stage0 + st * kDwStageBytes, p.in + static_cast<long long>(img) * img_bytes + (nbands > 1 ? lo * row_bytes : 0), bytes, &full[st]);
   };
   bool ok = true;
   int it = 0;
   if (tid == 0 && blockIdx.x < units) issue(blockIdx.x, 0);
+  const int dr = per / p.Wout, dc = per - dr * p.Wout;        // a thread advances `per` pixels per step: dr rows + dc columns
   for (long long u = blockIdx.x; u < units && ok; u += gridDim.x, ++it) {
     const int st = it & 1;
     if (tid == 0 && u + gridDim.x < units) issue(u + gridDim.x, st ^ 1);   // that stage was last read before the barrier below
     if (!mbar_wait(&full[st], (it >> 1) & 1)) { atomicCAS(p.eo.err_word, 0, 401); ok = false; }
-    const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
-    int lo, hi; rows_of(b, &lo, &hi);
+    int img0, nimg, b, lo, hi; unit_of(u, &img0, &nimg, &b); rows_of(b, &lo, &hi);
+    if (nbands == 1) { lo = 0; hi = p.Hin; }
     const int oy0 = b * band, nrows = min(p.Hout, oy0 + band) - oy0, npix = nrows * p.Wout;
-    const uint8_t* sin = stage0 + st * kDwStageBytes + c0;
-    for (int pi = pix0; pi < npix && ok; pi += per) {
-      const int r = pi / p.Wout, ox = pi - r * p.Wout, oy = oy0 + r;
-      int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+    for (int g = 0; g < nimg && ok; ++g) {
+      const uint8_t* sin = stage0 + st * kDwStageBytes + g * img_bytes + c0;
+      int r = pix0 / p.Wout, ox = pix0 - r * p.Wout;
+      for (int pi = pix0; pi < npix; pi += per) {
+        const int oy = oy0 + r, iy0 = oy * p.stride - p.pad_t, ix0 = ox * p.stride - p.pad_l;
+        int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int iy = oy * p.stride - p.pad_t + ky;
-        const bool yin = iy >= lo && iy < hi;                 // rows outside [lo, hi) are outside the image
-        const uint8_t* rowp = sin + (iy - lo) * row_bytes;
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = iy0 + ky;
+          const bool yin = iy >= lo && iy < hi;               // rows outside [lo, hi) are outside the image
+          const uint8_t* rowp = sin + (iy - lo) * row_bytes + ix0 * p.in_pitch;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int ix = ox * p.stride - p.pad_l + kx;
-          uint32_t x = zpw;
-          if (yin && ix >= 0 && ix < p.Win) x = *reinterpret_cast<const uint32_t*>(rowp + ix * p.in_pitch);
+          for (int kx = 0; kx < 3; ++kx) {
+            uint32_t x = zpw;
+            if (yin && ix0 + kx >= 0 && ix0 + kx < p.Win) x = *reinterpret_cast<const uint32_t*>(rowp + kx * p.in_pitch);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = __dp4a(static_cast<int>(x), static_cast<int>(w[ky * 3 + kx][j]), acc[j]);
+            for (int j = 0; j < 4; ++j) acc[j] = __dp4a(static_cast<int>(x), static_cast<int>(w[ky * 3 + kx][j]), acc[j]);
+          }
         }
-      }
-      uint32_t ow = 0;
+        uint32_t ow = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
-        ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(sLut[idx]) : (idx ^ 0x80)) << (8 * j);
+        for (int j = 0; j < 4; ++j) {
+          const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
+          ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(sLut[idx]) : (idx ^ 0x80)) << (8 * j);
+        }
+        ow &= keep;
+        const long long row = (static_cast<long long>(img0 + g) * p.Hout + oy) * p.Wout + ox;
+        int8_t* o = p.eo.out + row * p.eo.out_pitch + p.eo.out_coff + c0;
+        if (c0 + 4 <= lim && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = ow;
+        else for (int j = 0; j < 4; ++j) if (c0 + j < lim) o[j] = static_cast<int8_t>((ow >> (8 * j)) & 0xff);
+        r += dr; ox += dc;
+        if (ox >= p.Wout) { ox -= p.Wout; ++r; }
       }
-      ow &= keep;
-      const long long row = (static_cast<long long>(img) * p.Hout + oy) * p.Wout + ox;
-      int8_t* o = p.eo.out + row * p.eo.out_pitch + p.eo.out_coff + c0;
-      if (c0 + 4 <= lim && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = ow;
-      else for (int j = 0; j < 4; ++j) if (c0 + j < lim) o[j] = static_cast<int8_t>((ow >> (8 * j)) & 0xff);
     }
     __syncthreads();                                          // everyone is done with this stage before it is refilled
   }
@@ -980,12 +990,14 @@ cudaError_t launch_dw(const DwArgs& a, cudaStream_t s) {
     const int row_bytes = a.Win * a.in_pitch;
     int band = a.Hout;
     while (band > 1 && ((band - 1) * a.stride + 3) * row_bytes > kDwStageBytes) --band;
-    if (((band - 1) * a.stride + 3) * row_bytes <= kDwStageBytes && row_bytes % 16 == 0) {
+    if (band == a.Hout && a.Hin * row_bytes > kDwStageBytes && band > 1) band = (a.Hout + 1) / 2;   // whole-image units copy whole images
+    if (((band - 1) * a.stride + 3) * row_bytes <= kDwStageBytes && row_bytes % 16 == 0 && (band < a.Hout || a.Hin * row_bytes <= kDwStageBytes)) {
       const int nbands = (a.Hout + band - 1) / band;
-      const long long units = static_cast<long long>(a.n_img) * nbands;
+      const int group = nbands == 1 ? std::max(1, std::min(16, kDwStageBytes / (a.Hin * row_bytes))) : 1;   // whole small images per unit
+      const long long units = nbands > 1 ? static_cast<long long>(a.n_img) * nbands : (a.n_img + group - 1) / group;
       const int grid = static_cast<int>(std::min<long long>(units, 148LL * 4));
       const int block = 32 * a.words * std::max(1, 320 / (32 * a.words));      // a multiple of `words`, 192..320 threads
-      dwconv3x3_band_kernel<<<grid, block, 2 * kDwStageBytes + 64 + 512, s>>>(a, band, nbands);
+      dwconv3x3_band_kernel<<<grid, block, 2 * kDwStageBytes + 64 + 512, s>>>(a, band, nbands, group);
       return cudaGetLastError();
     }
   }
