@@ -677,8 +677,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
 // into one of two smem stages; the window maximum is separable: pass 1 reduces every staged input row horizontally
 // (row maxima per output column, kept in smem), pass 2 reduces those vertically, applies the table and stores.
 // An 8x8 window costs 8 + 8 * rows_in / rows_out loads per output instead of 64.
-constexpr int kPoolStageBytes = 40 * 1024;
-constexpr int kPoolScratchBytes = 24 * 1024;
+constexpr int kPoolSmemMax = 200 * 1024;   // 2 stages + row-maxima scratch, sized per launch (see launch_pool)
 __device__ __forceinline__ uint32_t pk_even(uint32_t x) { return __byte_perm(x, 0u, 0xA280u); }   // bytes 0,2 sign-extended to 16-bit lanes
 __device__ __forceinline__ uint32_t pk_odd(uint32_t x) { return __byte_perm(x, 0u, 0xB391u); }    // bytes 1,3
 __device__ __forceinline__ void pk_window(const uint8_t* q, int step, int n, uint32_t& ev, uint32_t& od) {
@@ -692,12 +691,12 @@ __device__ __forceinline__ void pk_window(const uint8_t* q, int step, int n, uin
     ev = __vmaxs2(ev, pk_even(a)); od = __vmaxs2(od, pk_odd(a));
   }
 }
-__global__ void __launch_bounds__(256) maxpool_band_kernel(const PoolArgs p, int band, int nbands) {
+__global__ void __launch_bounds__(512) maxpool_band_kernel(const PoolArgs p, int band, int nbands, int stage_bytes, int scratch_bytes) {
   extern __shared__ __align__(128) uint8_t psm[];
   uint8_t* stage0 = psm;
-  uint8_t* scratch = psm + 2 * kPoolStageBytes;               // [rows_in][Wout][words] uint32 row maxima
-  uint64_t* full = reinterpret_cast<uint64_t*>(psm + 2 * kPoolStageBytes + kPoolScratchBytes);
-  uint8_t* sLut = psm + 2 * kPoolStageBytes + kPoolScratchBytes + 64;
+  uint8_t* scratch = psm + 2 * stage_bytes;                   // [rows_in][Wout][words] uint32 row maxima
+  uint64_t* full = reinterpret_cast<uint64_t*>(psm + 2 * stage_bytes + scratch_bytes);
+  uint8_t* sLut = psm + 2 * stage_bytes + scratch_bytes + 64;
   const int tid = threadIdx.x;
   if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); fence_mbar_init(); }
   load_luts(sLut, p.eo, tid, blockDim.x);
@@ -715,7 +714,7 @@ __global__ void __launch_bounds__(256) maxpool_band_kernel(const PoolArgs p, int
     int lo, hi; rows_of(b, &lo, &hi);
     const uint32_t bytes = static_cast<uint32_t>((hi - lo) * row_bytes);
     mbar_arrive_expect_tx(&full[st], bytes);
-    bulk_load_1d(stage0 + st * kPoolStageBytes, p.in + (static_cast<long long>(img) * p.Hin + lo) * row_bytes, bytes, &full[st]);
+    bulk_load_1d(stage0 + st * stage_bytes, p.in + (static_cast<long long>(img) * p.Hin + lo) * row_bytes, bytes, &full[st]);
   };
   bool ok = true;
   int it = 0;
@@ -727,7 +726,7 @@ __global__ void __launch_bounds__(256) maxpool_band_kernel(const PoolArgs p, int
     const int img = static_cast<int>(u / nbands), b = static_cast<int>(u - static_cast<long long>(img) * nbands);
     int lo, hi; rows_of(b, &lo, &hi);
     const int oy0 = b * band, nrows = min(p.Hout, oy0 + band) - oy0, rin = hi - lo;
-    const uint8_t* sin = stage0 + st * kPoolStageBytes;
+    const uint8_t* sin = stage0 + st * stage_bytes;
     // pass 1: item = (staged input row, output column, word)
     const int n1 = ok ? rin * p.Wout * words : 0;
     for (int i = tid; i < n1; i += blockDim.x) {
@@ -1010,17 +1009,21 @@ cudaError_t launch_pool(const PoolArgs& a, cudaStream_t s) {
   const bool observing = a.eo.raw || a.eo.mid || a.eo.lut2;
   if (!observing && a.eo.err_word) {
     const int row_bytes = a.Win * a.in_pitch;
+    // largest band whose two stages + scratch fit; a band of b rows re-reduces (b-1)*stride + k input rows, so small
+    // bands waste work when rows are wide (224x224: 8 rows per band instead of 2)
     int band = a.Hout;
-    auto fits = [&](int b) {
-      const int rin = std::min(a.Hin, (b - 1) * a.stride + a.k);
-      return rin * row_bytes <= kPoolStageBytes && rin * a.Wout * a.words * 4 <= kPoolScratchBytes;
-    };
-    while (band > 1 && !fits(band)) --band;
-    if (fits(band) && row_bytes % 16 == 0) {
+    auto rows_in = [&](int b) { return std::min(a.Hin, (b - 1) * a.stride + a.k); };
+    auto need = [&](int b) { return 2 * ((rows_in(b) * row_bytes + 127) & ~127) + ((rows_in(b) * a.Wout * a.words * 4 + 127) & ~127) + 64 + 512; };
+    while (band > 1 && need(band) > kPoolSmemMax) --band;
+    if (need(band) <= kPoolSmemMax && row_bytes % 16 == 0) {
       const int nbands = (a.Hout + band - 1) / band;
+      const int stage_bytes = (rows_in(band) * row_bytes + 127) & ~127, scratch_bytes = (rows_in(band) * a.Wout * a.words * 4 + 127) & ~127;
+      const int smem = need(band);
+      const int per_sm = std::max(1, std::min(4, (227 * 1024) / (smem + 1024)));
+      const int block = per_sm >= 2 ? 256 : 512;
       const long long units = static_cast<long long>(a.n_img) * nbands;
-      const int grid = static_cast<int>(std::min<long long>(units, 148LL * 2));
-      maxpool_band_kernel<<<grid, 256, 2 * kPoolStageBytes + kPoolScratchBytes + 64 + 512, s>>>(a, band, nbands);
+      const int grid = static_cast<int>(std::min<long long>(units, 148LL * per_sm));
+      maxpool_band_kernel<<<grid, block, smem, s>>>(a, band, nbands, stage_bytes, scratch_bytes);
       return cudaGetLastError();
     }
   }
@@ -1061,7 +1064,7 @@ cudaError_t kernels_init() {
   YF_OPTIN(conv_im2col_tcgen05_kernel<16>, im2col_smem_bytes<16>())
   YF_OPTIN(conv_im2col_tcgen05_kernel<32>, im2col_smem_bytes<32>())
   YF_OPTIN(dwconv3x3_band_kernel, 2 * kDwStageBytes + 64 + 512)
-  YF_OPTIN(maxpool_band_kernel, 2 * kPoolStageBytes + kPoolScratchBytes + 64 + 512)
+  YF_OPTIN(maxpool_band_kernel, kPoolSmemMax)
 #undef YF_OPTIN
   return cudaSuccess;
 }
