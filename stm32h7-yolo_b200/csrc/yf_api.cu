@@ -877,6 +877,38 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, hsz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
   const bool in_dev = is_device_ptr(in);
   int32_t total = 0;
+  if (in_dev && !heads_out && count > pd->cap && uses_fused(n, pd) && !(reinterpret_cast<uintptr_t>(in) & 15)) {
+    // Device-resident images, several chunks, detections only: chunk i runs inference then decode + NMS on lane i % 4
+    // (its heads stay in that lane's staging buffer), so the inference of one chunk overlaps the decode of its
+    // neighbours; ONE copy brings all detections back.
+    if (!ring_prepare(n, pd) || !ring_wait(n, pd) || !ensure_dets(n, count, max_det)) return -1;   // the slots' head buffers must be idle
+    if (!cuda_ok(n, cudaEventRecord(n->ev_fork, n->stream), "fork")) return -1;
+    for (int l = 0; l < Network::kLanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
+    uint32_t ci = 0;
+    for (uint32_t done = 0; done < count; done += pd->cap, ++ci) {
+      const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
+      const int l = static_cast<int>(ci % Network::kLanes);
+      int8_t* heads = pd->r_head[l];                           // ring slots 0..3 double as the lanes' head buffers
+      if (!run_steps(n, pd, static_cast<const int8_t*>(in) + done * in_sz, heads, nb, n->lane[l])) return -1;
+      DecodeArgs a{};
+      a.head = heads; a.n_img = static_cast<int>(nb); a.gh = pd->plan.GH; a.gw = pd->plan.GW;
+      a.scale = pd->plan.out_scale; a.zp = pd->plan.out_zp;
+      a.conf_thr = conf_thr; a.iou_thr = iou_thr; a.plus_one = (flags & YF_B200_NMS_PLUS_ONE) ? 1 : 0;
+      a.dets = n->d_dets + static_cast<size_t>(done) * max_det * 5; a.counts = n->d_counts + done; a.max_det = static_cast<int>(max_det);
+      if (!cuda_ok(n, launch_decode_nms(a, n->lane[l]), "decode_nms")) return -1;
+      ++n->launches;
+    }
+    for (int l = 0; l < Network::kLanes; ++l) {
+      cudaEventRecord(n->ev_join[l], n->lane[l]);
+      if (!cuda_ok(n, cudaStreamWaitEvent(n->stream, n->ev_join[l], 0), "join")) return -1;
+    }
+    if (!cuda_ok(n, cudaMemcpyAsync(counts, n->d_counts, sizeof(int) * count, cudaMemcpyDeviceToHost, n->stream), "D2H counts")) return -1;
+    if (!cuda_ok(n, cudaMemcpyAsync(dets, n->d_dets, sizeof(float) * 5 * count * max_det, cudaMemcpyDeviceToHost, n->stream), "D2H detections")) return -1;
+    if (!check_device_err(n)) return -1;
+    n->images += count; n->last_run_n = std::min<uint32_t>(pd->cap, count);
+    for (uint32_t i = 0; i < count; ++i) total += counts[i];
+    return total;
+  }
   for (uint32_t done = 0; done < count; done += pd->cap) {
     const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
     const int8_t* src = static_cast<const int8_t*>(in) + done * in_sz;
