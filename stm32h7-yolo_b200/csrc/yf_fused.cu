@@ -546,7 +546,8 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
 }
 
 cudaError_t fused_init(int smem_bytes) {
-  return cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  const char* e = getenv("YF_B200_FUSED_PAD");
+  return cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes + (e ? atoi(e) : 0));
 }
 
 cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
@@ -558,9 +559,12 @@ cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_ou
   a.head_bytes = F.head_bytes; a.err = d_err; a.trace = d_trace; a.in_pf_phase = F.in_pf_phase;
   a.bars_off = F.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127);
   { const char* e = getenv("YF_B200_TRACE_PHASE"); a.trace_phase = e ? atoi(e) : 1; }
-  const int per_sm = F.smem_bytes <= 75 * 1024 ? kFusedCtasPerSm : F.smem_bytes <= 113 * 1024 ? 2 : 1;
+  // YF_B200_FUSED_PAD (diagnostics): extra dynamic shared memory per CTA, to measure the kernel at lower residency
+  static const int pad = [] { const char* e = getenv("YF_B200_FUSED_PAD"); return e ? atoi(e) : 0; }();
+  const int smem = F.smem_bytes + pad;
+  const int per_sm = smem <= 75 * 1024 ? kFusedCtasPerSm : smem <= 113 * 1024 ? 2 : 1;
   const int grid = n_img < sm_count * per_sm ? n_img : sm_count * per_sm;
-  yoloface_fused_kernel<<<grid, kFusedThreads, F.smem_bytes, s>>>(a);
+  yoloface_fused_kernel<<<grid, kFusedThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 
