@@ -261,6 +261,17 @@ def run_ours(args, rank, local_rank, world):
            "ms_per_step": 1e3 * dt / args.steps,
            "blocking": {"value": world * BATCH * args.steps / dt_block, "ms_per_step": 1e3 * dt_block / args.steps,
                         "api": "yf_b200_run(host pinned in, host pinned out), one blocking call per step"}}
+    # the bounds of SURVEY.md 8(d): PCIe-fed (this box's pinned host->device copy rate, measured here) and the HBM I/O floor
+    if rank == 0:
+        big_h = torch.empty(256 << 20, dtype=torch.int8).pin_memory()
+        big_d = torch.empty(256 << 20, dtype=torch.int8, device="cuda")
+        big_d.copy_(big_h, non_blocking=True); torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(); big_d.copy_(big_h, non_blocking=True); big_d.copy_(big_h, non_blocking=True); c1.record(); c1.synchronize()
+        h2d_gbs = 2 * (256 << 20) / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del big_h, big_d
+        e2e["bounds"] = {"pcie_h2d_GBps_measured": h2d_gbs, "pcie_fed_images_per_s_per_gpu": h2d_gbs * 1e9 / IN_BYTES,
+                         "e2e_frac_of_pcie_bound": (e2e["value"] / world) / (h2d_gbs * 1e9 / IN_BYTES)}
     # latency of the reference's own call pattern: one image per blocking ai_network_run-style call, pageable host buffers
     one_in, one_out = np.ascontiguousarray(h_in[0][:1].numpy()).copy(), np.zeros((1, 7, 7, 18), np.int8)
     for _ in range(20):
@@ -281,6 +292,7 @@ def run_ours(args, rank, local_rank, world):
         alg = BATCH * (IN_BYTES + OUT_BYTES)
         gbps = alg / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "yoloface_fused_kernel", "achieved": gbps, "peak": peak, "unit": "GB/s", "frac": gbps / peak,
+                    "io_floor_images_per_s": peak * 1e9 / (IN_BYTES + OUT_BYTES),
                     "traffic": 2552832, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at 256 images "
                     "(profiles/r01_fused_v7c_b256_ncu_summary.txt; the 225 KB of heads were still in L2 when the capture ended)",
                     "peak_source": peak_src, "launch_ms": kernel_ms,
