@@ -220,6 +220,24 @@ def test_other_resolutions(yf, oracle):
         n.close()
 
 
+@pytest.mark.parametrize("mode", ["fused", "layered"])
+def test_small_and_odd_resolutions(yf, oracle, mode):
+    """Shapes that stress the corner cases of both paths: pool windows larger than the tensor, single-tile
+    layers, one-row bands, widths that are not multiples of the thread tiling."""
+    n = yf.Network(chunk_images=64, mode=mode)
+    try:
+        rng = np.random.default_rng(21)
+        for H, W, b in ((8, 8, 70), (8, 16, 33), (24, 16, 65), (32, 32, 40), (40, 56, 17), (56, 64, 9), (16, 128, 12)):
+            n.set_input_size(H, W)
+            assert n.stats()["fused"] == (1 if mode == "fused" else 0)
+            x = rng.integers(-128, 128, (b, H, W, 3), dtype=np.int8)
+            out = n.run(x)
+            ref = np.stack([oracle.run(x[i]) for i in range(b)])
+            assert np.array_equal(out, ref), (H, W, mode)
+    finally:
+        n.close()
+
+
 def test_error_behaviour(yf, golden):
     """Error latch semantics of network.h:120-132,190-196: run returns <=0, first error is kept
     until read, reading clears it."""

@@ -133,6 +133,17 @@ def test_fused_program_reproduces_oracle(yf, oracle, golden):
         assert np.array_equal(head.reshape(7, 7, 18), oracle.run(img))
 
 
+@pytest.mark.parametrize("hw", [(8, 8), (8, 16), (24, 16), (32, 32), (40, 56), (56, 64), (64, 64), (16, 128)])
+def test_fused_program_other_resolutions(yf, oracle, hw):
+    """The allocator, the word-plane skew, the tile groups and the mul-shift divisions all depend on the shape:
+    tiny inputs (pool windows larger than the tensor, single-tile layers) up to the largest fused size."""
+    from fused_emulator import run_fused
+    H, W = hw
+    F = yf.fused_program(H, W)
+    img = np.random.default_rng(H * 1000 + W).integers(-128, 128, (H, W, 3), dtype=np.int8)
+    assert np.array_equal(run_fused(F, img, 1).reshape(H // 8, W // 8, 18), oracle.run(img))
+
+
 def test_fused_program_limits(yf):
     F = yf.fused_program(64, 64)                  # still fits shared memory and TMEM
     assert F["smem_bytes"] < 200 * 1024
