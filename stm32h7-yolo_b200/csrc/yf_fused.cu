@@ -546,8 +546,17 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
 }
 
 cudaError_t fused_init(int smem_bytes) {
+  // The attribute belongs to the function (per device), not to a plan: several plans / contexts share it, so it only
+  // ever grows -- a later, smaller plan must not take the larger ones' shared memory away.
   const char* e = getenv("YF_B200_FUSED_PAD");
-  return cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes + (e ? atoi(e) : 0));
+  const int want = smem_bytes + (e ? atoi(e) : 0);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int granted[64] = {};
+  if (want <= granted[dev & 63]) return cudaSuccess;
+  const cudaError_t r = cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+  if (r == cudaSuccess) granted[dev & 63] = want;
+  return r;
 }
 
 cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,

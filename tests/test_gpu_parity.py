@@ -238,6 +238,31 @@ def test_small_and_odd_resolutions(yf, oracle, mode):
         n.close()
 
 
+def test_interleaved_contexts_share_the_device_tables(yf, oracle, golden):
+    """Several live contexts (ST allows one; this library gives every create its own) with different constant tables --
+    TFLite vs ST activations, 56x56 vs 32x32, fused vs layered -- used alternately: every switch re-uploads the
+    per-device tables, and in-flight work of the other context must not be disturbed."""
+    ctxs = [yf.Network(chunk_images=64), yf.Network(chunk_images=64, st_activations=True),
+            yf.Network(chunk_images=64, mode="layered"), yf.Network(chunk_images=32)]
+    ctxs[3].set_input_size(32, 32)
+    try:
+        x = real_batch(golden, 48, 31)
+        small = np.random.default_rng(5).integers(-128, 128, (20, 32, 32, 3), dtype=np.int8)
+        want = oracle.run_batch(x, threads=os.cpu_count())
+        want_small = np.stack([oracle.run(small[i]) for i in range(len(small))])
+        st_first = None
+        for rep in range(3):
+            assert np.array_equal(ctxs[0].run(x), want)
+            st = ctxs[1].run(x)                             # ST tables: differs from TFLite, but must be reproducible
+            st_first = st if st_first is None else st_first
+            assert np.array_equal(st, st_first) and not np.array_equal(st, want)
+            assert np.array_equal(ctxs[2].run(x), want)
+            assert np.array_equal(ctxs[3].run(small), want_small)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_error_behaviour(yf, golden):
     """Error latch semantics of network.h:120-132,190-196: run returns <=0, first error is kept
     until read, reading clears it."""
