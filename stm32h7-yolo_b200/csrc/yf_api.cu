@@ -92,6 +92,7 @@ struct Network {
   cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {};
   uint64_t lane_seq = 0;
   uint32_t last_run_n = 0;
+  ai_buffer rep_in{}, rep_out{};        // I/O descriptors handed out by ai_network_get_report
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
   void latch(int type, int code) { if (err.type == AI_ERROR_NONE) { err.type = type; err.code = code; } }
@@ -104,7 +105,11 @@ bool make_lanes(Network* n) {
   return cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) == cudaSuccess;
 }
 
+// Locking: g_mu guards the registry of live contexts only.  Work on a device is serialised by that device's mutex
+// (contexts on one GPU share its __constant__ tables and take turns anyway); contexts on different GPUs driven from
+// different host threads run in parallel.  One context must not be used from two threads at once (same as ST).
 std::mutex g_mu;
+std::mutex g_dev_mu[64];
 // ST's runtime has one static context (g_network, network.c:36); a GPU process may want one per
 // device or per configuration, so every create returns a fresh context and all stay valid.
 std::vector<Network*> g_nets;
@@ -132,6 +137,7 @@ bool cuda_ok(Network* n, cudaError_t e, const char* what, int type = AI_ERROR_IN
 }
 
 Network* as_net(ai_handle h) {
+  std::lock_guard<std::mutex> lk(g_mu);
   for (Network* n : g_nets) if (n == h) return n;
   return nullptr;
 }
@@ -530,7 +536,7 @@ std::vector<uint8_t>& own_blob() {       // ST-layout blob regenerated from the 
 }
 
 void fill_report(Network* n, ai_network_report* r) {
-  static ai_buffer in_desc, out_desc;
+  ai_buffer& in_desc = n->rep_in; ai_buffer& out_desc = n->rep_out;   // the report points at descriptors owned by the context
   std::memset(r, 0, sizeof *r);
   r->model_name = AI_NETWORK_MODEL_NAME;
   r->model_signature = "yoloface_int8.tflite";
@@ -560,7 +566,6 @@ void fill_report(Network* n, ai_network_report* r) {
 extern "C" {
 
 AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* network_config) {
-  std::lock_guard<std::mutex> lk(g_mu);
   ai_error err{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
   if (!network) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return err; }
   *network = AI_HANDLE_NULL;
@@ -601,6 +606,7 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
   else if (const char* e = std::getenv("YF_B200_DEVICE")) dev = std::atoi(e);
   if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
   if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return err; }
+  std::lock_guard<std::mutex> lk(g_dev_mu[dev & 63]);
   cudaDeviceProp prop{};
   if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
     set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
@@ -621,15 +627,15 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
   }
   n->stream = n->own_stream;
-  g_nets.push_back(n.get());
+  { std::lock_guard<std::mutex> rk(g_mu); g_nets.push_back(n.get()); }
   *network = n.release();
   return err;
 }
 
 AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
-  std::lock_guard<std::mutex> lk(g_mu);
   Network* n = as_net(network);
   if (!n) return network;
+  std::lock_guard<std::mutex> lk(g_dev_mu[n->device & 63]);
   cudaSetDevice(n->device);
   cudaStreamSynchronize(n->stream);
   for (int l = 0; l < Network::kLanes; ++l) cudaStreamSynchronize(n->lane[l]);
@@ -645,24 +651,24 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream); cudaStreamDestroy(n->s_h2d); cudaStreamDestroy(n->s_d2h);
   for (int l = 0; l < Network::kLanes; ++l) { cudaStreamDestroy(n->lane[l]); cudaEventDestroy(n->ev_join[l]); }
   cudaEventDestroy(n->ev_fork);
-  g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end());
+  { std::lock_guard<std::mutex> rk(g_mu); g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end()); }
   delete n;
   return AI_HANDLE_NULL;
 }
 
 AI_API_ENTRY ai_error ai_network_get_error(ai_handle network) {
-  std::lock_guard<std::mutex> lk(g_mu);
   Network* n = as_net(network);
   if (!n) return ai_error{AI_ERROR_INVALID_HANDLE, AI_ERROR_CODE_NETWORK};
+  std::lock_guard<std::mutex> lk(g_dev_mu[n->device & 63]);
   ai_error e = n->err;
   n->err = ai_error{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
   return e;
 }
 
 AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params* params) {
-  std::lock_guard<std::mutex> lk(g_mu);
   Network* n = as_net(network);
   if (!n) return false;
+  std::lock_guard<std::mutex> lk(g_dev_mu[n->device & 63]);
   if (!params) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_NETWORK_PARAMS); return false; }
   const ai_buffer* wbuf = &params->params; const ai_buffer* abuf = &params->activations;
   if (params->map_signature == AI_MAGIC_SIGNATURE) {            // ai_network_data_params_get() form
@@ -694,9 +700,9 @@ AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params*
 }
 
 static ai_i32 process(ai_handle network, const ai_buffer* input, ai_buffer* output) {
-  std::lock_guard<std::mutex> lk(g_mu);
   Network* n = as_net(network);
   if (!n) return 0;
+  std::lock_guard<std::mutex> lk(g_dev_mu[n->device & 63]);
   if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return 0; }
   if (!input || !input->data) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return 0; }
   if (AI_BUFFER_FMT_GET(input->format) != AI_BUFFER_FORMAT_S8) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_FORMAT); return 0; }
@@ -720,9 +726,9 @@ AI_API_ENTRY ai_i32 ai_network_run(ai_handle network, const ai_buffer* input, ai
 AI_API_ENTRY ai_i32 ai_network_forward(ai_handle network, const ai_buffer* input) { return process(network, input, nullptr); }
 
 AI_API_ENTRY ai_bool ai_network_get_report(ai_handle network, ai_network_report* report) {
-  std::lock_guard<std::mutex> lk(g_mu);
   Network* n = as_net(network);
   if (!n || !report) return false;
+  std::lock_guard<std::mutex> lk(g_dev_mu[n->device & 63]);
   fill_report(n, report);
   return true;
 }
@@ -752,9 +758,9 @@ AI_API_ENTRY ai_bool ai_network_data_params_get(ai_handle network, ai_network_pa
 // B200 extensions
 // ============================================================================================
 #define YF_NET_OR_FAIL(n, network)                                                             \
-  std::lock_guard<std::mutex> lk(g_mu);                                                        \
   Network* n = as_net(network);                                                                \
   if (!n) return -1;                                                                           \
+  std::lock_guard<std::mutex> lk(g_dev_mu[n->device & 63]);                                    \
   cudaSetDevice(n->device);
 
 AI_API_ENTRY int32_t yf_b200_set_input_size(ai_handle network, int32_t height, int32_t width) {

@@ -11,6 +11,7 @@
 //
 // Reference semantics: SURVEY.md 8a rows a2-a14; each kernel cites the row it implements.
 #include <algorithm>
+#include <vector>
 
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
@@ -33,15 +34,15 @@ cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s) {
   if (n > kMaxEpiCh) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemcpyToSymbolAsync(c_epi, host, sizeof(EpiCh) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
-  static EpiChF lean[kMaxEpiCh];
+  std::vector<EpiChF> lean(static_cast<size_t>(std::max(n, 1)));   // not static: contexts on different devices upload concurrently
   for (int i = 0; i < n; ++i) {
     int32_t b = 0;
     lean[i] = EpiChF{};
     if (epi_lean_form(host[i], &b)) lean[i] = EpiChF{b, host[i].mult, host[i].c2 + (128 << host[i].e), host[i].e};
   }
-  e = cudaMemcpyToSymbolAsync(c_epif, lean, sizeof(EpiChF) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
+  e = cudaMemcpyToSymbolAsync(c_epif, lean.data(), sizeof(EpiChF) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(s);       // `lean` is static scratch
+  return cudaStreamSynchronize(s);       // `lean` dies with this frame
 }
 
 // ------------------------------------------------------------------------------------------

@@ -382,3 +382,45 @@ def test_st_activation_mode_on_device(yf, golden, monkeypatch):
         finally:
             n.close()
     assert not np.array_equal(exp, golden["heads_images"][:6])
+
+
+def test_contexts_on_two_gpus_from_two_threads(yf, oracle, golden):
+    """One process, one context per GPU, one host thread per context (SURVEY.md 8b threading): the calls of the two
+    threads must not serialise on a library-wide lock, and each context must keep to its own device."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import threading
+    import time
+    x = real_batch(golden, 256, 90)
+    want = oracle.run_batch(x, threads=os.cpu_count())
+    nets = [yf.Network(device=d, chunk_images=256) for d in (0, 1)]
+    errs, times = [], [0.0, 0.0]
+
+    def work(i, reps):
+        try:
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if not np.array_equal(nets[i].run(x), want):
+                    errs.append("mismatch on device %d" % i)
+            times[i] = time.perf_counter() - t0
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    try:
+        work(0, 5); work(1, 5)                              # warm-up, sequential
+        reps = 200
+        t0 = time.perf_counter(); work(0, reps); t_one = time.perf_counter() - t0
+        th = [threading.Thread(target=work, args=(i, reps)) for i in (0, 1)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        t_both = time.perf_counter() - t0
+        assert not errs, errs
+        assert nets[0].stats()["device"] == 0 and nets[1].stats()["device"] == 1
+        assert t_both < 1.6 * t_one, (t_one, t_both)        # two GPUs in parallel, not one after the other (2.0x)
+    finally:
+        for n in nets:
+            n.close()
