@@ -424,3 +424,16 @@ def test_contexts_on_two_gpus_from_two_threads(yf, oracle, golden):
     finally:
         for n in nets:
             n.close()
+
+
+def test_allocation_failure_is_reported_and_harmless(yf, golden):
+    """A chunk size whose staging / arena buffers cannot be allocated: init must fail with AI_ERROR_ALLOCATION_FAILED
+    (ai_platform.h:546-586), and a later, sane context on the same device must work."""
+    with pytest.raises(yf.AiRuntimeError) as ei:
+        yf.Network(chunk_images=1 << 30)
+    assert (ei.value.type, ei.value.code) == (0x31, 0x13), (hex(ei.value.type), hex(ei.value.code))   # ALLOCATION_FAILED / NETWORK_ACTIVATIONS
+    n = yf.Network(chunk_images=32)
+    try:
+        assert n.run(golden["images"][:3]).shape == (3, 7, 7, 18)
+    finally:
+        n.close()
