@@ -790,8 +790,9 @@ AI_API_ENTRY int32_t yf_b200_set_stream(ai_handle network, void* cuda_stream) {
 AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* d_out, uint32_t count) {
   YF_NET_OR_FAIL(n, network)
   if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
-  if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15)) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
-  if (!d_out) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  // the kernels dereference these pointers: device, managed or page-locked host memory -- never pageable host memory
+  if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || is_pageable_ptr(d_in)) { set_text("enqueue: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (!d_out || is_pageable_ptr(d_out)) { set_text("enqueue: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
   std::vector<DevChunk> ch;
@@ -811,8 +812,8 @@ AI_API_ENTRY int32_t yf_b200_enqueue_batches(ai_handle network, const void* cons
   std::vector<DevChunk> ch;
   uint64_t total = 0;
   for (uint32_t b = 0; b < n_batches; ++b) {
-    if (!d_in[b] || (reinterpret_cast<uintptr_t>(d_in[b]) & 15)) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
-    if (!d_out[b]) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+    if (!d_in[b] || (reinterpret_cast<uintptr_t>(d_in[b]) & 15) || is_pageable_ptr(d_in[b])) { set_text("enqueue_batches: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+    if (!d_out[b] || is_pageable_ptr(d_out[b])) { set_text("enqueue_batches: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
     for (uint32_t done = 0; done < counts[b]; done += pd->cap)
       ch.push_back({static_cast<const int8_t*>(d_in[b]) + done * in_sz, static_cast<int8_t*>(d_out[b]) + done * out_sz, std::min<uint32_t>(pd->cap, counts[b] - done)});
     total += counts[b];

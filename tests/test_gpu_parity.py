@@ -437,3 +437,27 @@ def test_allocation_failure_is_reported_and_harmless(yf, golden):
         assert n.run(golden["images"][:3]).shape == (3, 7, 7, 18)
     finally:
         n.close()
+
+
+def test_enqueue_rejects_pageable_host_memory(yf, golden):
+    """yf_b200_enqueue* hand their pointers to kernels: pageable host memory must be refused up front (INVALID_INPUT /
+    INVALID_OUTPUT + INVALID_PTR) instead of faulting the GPU; page-locked host memory is legal (the kernels read it
+    across PCIe)."""
+    torch = pytest.importorskip("torch")
+    n = yf.Network(chunk_images=64)
+    try:
+        x = np.ascontiguousarray(golden["images"][:8])
+        want = n.run(x)
+        d_out = torch.empty((8, 7, 7, 18), dtype=torch.int8, device="cuda")
+        with pytest.raises(yf.AiRuntimeError) as ei:
+            n.enqueue(x, d_out, 8)                          # numpy array = pageable
+        assert (ei.value.type, ei.value.code) == (0x12, 0x17)
+        d_in = torch.from_numpy(x).cuda()
+        with pytest.raises(yf.AiRuntimeError) as ei:
+            n.enqueue_batches([d_in], [np.zeros((8, 7, 7, 18), np.int8)], [8])
+        assert (ei.value.type, ei.value.code) == (0x13, 0x17)
+        pinned_in, pinned_out = torch.from_numpy(x).pin_memory(), torch.zeros((8, 7, 7, 18), dtype=torch.int8).pin_memory()
+        n.enqueue(pinned_in, pinned_out, 8); n.sync()
+        assert np.array_equal(pinned_out.numpy(), want)
+    finally:
+        n.close()
