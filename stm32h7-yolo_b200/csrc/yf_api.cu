@@ -148,6 +148,12 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// device memory of another GPU than the context's (no peer mapping is set up by this library)
+bool is_foreign_device_ptr(const Network* n, const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice && a.device != n->device;
+}
 bool is_pageable_ptr(const void* p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
@@ -428,6 +434,8 @@ int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool k
   const bool in_dev = is_device_ptr(in);
   const bool out_dev = out ? is_device_ptr(out) : true;
   if (in_dev && (reinterpret_cast<uintptr_t>(in) & 15)) { set_text("device input must be 16-byte aligned"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (in_dev && is_foreign_device_ptr(n, in)) { set_text("input lives on another GPU than this context"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (out && out_dev && is_foreign_device_ptr(n, out)) { set_text("output lives on another GPU than this context"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   // zero-copy pays up to 8 images when the caller's buffers are page-locked and up to 32 when they are pageable
   // (measured: 1 image 90 / 98 us -> 80 us; 32 pageable images 117 -> 103 us); YF_B200_SMALL overrides both
   static const int small_env = [] { const char* e = getenv("YF_B200_SMALL"); return e ? atoi(e) : -1; }();
@@ -791,8 +799,8 @@ AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* 
   YF_NET_OR_FAIL(n, network)
   if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
   // the kernels dereference these pointers: device, managed or page-locked host memory -- never pageable host memory
-  if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || is_pageable_ptr(d_in)) { set_text("enqueue: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
-  if (!d_out || is_pageable_ptr(d_out)) { set_text("enqueue: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || is_pageable_ptr(d_in) || is_foreign_device_ptr(n, d_in)) { set_text("enqueue: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (!d_out || is_pageable_ptr(d_out) || is_foreign_device_ptr(n, d_out)) { set_text("enqueue: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
   std::vector<DevChunk> ch;
@@ -812,8 +820,8 @@ AI_API_ENTRY int32_t yf_b200_enqueue_batches(ai_handle network, const void* cons
   std::vector<DevChunk> ch;
   uint64_t total = 0;
   for (uint32_t b = 0; b < n_batches; ++b) {
-    if (!d_in[b] || (reinterpret_cast<uintptr_t>(d_in[b]) & 15) || is_pageable_ptr(d_in[b])) { set_text("enqueue_batches: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
-    if (!d_out[b] || is_pageable_ptr(d_out[b])) { set_text("enqueue_batches: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+    if (!d_in[b] || (reinterpret_cast<uintptr_t>(d_in[b]) & 15) || is_pageable_ptr(d_in[b]) || is_foreign_device_ptr(n, d_in[b])) { set_text("enqueue_batches: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
+    if (!d_out[b] || is_pageable_ptr(d_out[b]) || is_foreign_device_ptr(n, d_out[b])) { set_text("enqueue_batches: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
     for (uint32_t done = 0; done < counts[b]; done += pd->cap)
       ch.push_back({static_cast<const int8_t*>(d_in[b]) + done * in_sz, static_cast<int8_t*>(d_out[b]) + done * out_sz, std::min<uint32_t>(pd->cap, counts[b] - done)});
     total += counts[b];

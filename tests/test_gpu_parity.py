@@ -421,6 +421,11 @@ def test_contexts_on_two_gpus_from_two_threads(yf, oracle, golden):
         assert not errs, errs
         assert nets[0].stats()["device"] == 0 and nets[1].stats()["device"] == 1
         assert t_both < 1.6 * t_one, (t_one, t_both)        # two GPUs in parallel, not one after the other (2.0x)
+        # memory of the other GPU is refused (no peer mapping), not dereferenced
+        x1 = torch.from_numpy(x[:8]).to("cuda:1"); y0 = torch.empty((8, 7, 7, 18), dtype=torch.int8, device="cuda:0")
+        with pytest.raises(yf.AiRuntimeError, match="another GPU"):
+            nets[0].run(x1, y0, n=8)
+        assert np.array_equal(nets[1].run(x1, n=8), want[:8])
     finally:
         for n in nets:
             n.close()
