@@ -466,3 +466,31 @@ def test_enqueue_rejects_pageable_host_memory(yf, golden):
         assert np.array_equal(pinned_out.numpy(), want)
     finally:
         n.close()
+
+
+def test_create_destroy_cycles_do_not_leak(yf, golden):
+    """Every buffer a context allocates (arena, ring slots, lanes, small-batch staging, detections) goes away with it."""
+    torch = pytest.importorskip("torch")
+    x = np.ascontiguousarray(golden["images"][:20])
+    xp = torch.from_numpy(np.concatenate([x] * 20)).pin_memory()
+    yp = torch.empty((400, 7, 7, 18), dtype=torch.int8).pin_memory()
+
+    def cycle():
+        n = yf.Network(chunk_images=128)
+        try:
+            n.run(x[:3])                                    # small-batch staging
+            n.run(x)                                        # ring
+            n.submit(xp, yp, 400); n.wait()                 # several ring slots and lanes
+            n.detect(x, 0.7, 0.4, max_det=16)               # detection buffers
+        finally:
+            n.close()
+
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(25):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 16 << 20, (free0, free1)
