@@ -524,23 +524,41 @@ int yfo_run_batch(const yfo_model* m, const int8_t* in, int n, int H, int W, int
 /* yoloface.c:98-102 */
 static float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-int yfo_decode_nms(const int8_t* head, int gh, int gw, float out_scale, int out_zp,
-                   float conf_thr, float iou_thr, int plus_one, yfo_det* dets, int max_det) {
-  static const float anchors[3][2] = {{9, 14}, {12, 17}, {22, 21}};      /* yoloface.c:20 */
+/* One candidate (cell i, anchor j) of a [gh,gw,3*6] head: yoloface.c:116-138 with the canonical (un-swapped)
+ * box form of tflite_prediction.py:5-11,43-57.  stride = input pixels per head cell (8 for this model). */
+static void decode_one(const int8_t* head, int gw, float out_scale, int out_zp, const float anchors[3][2], float stride,
+                       int i, int j, yfo_det* d) {
+  const int8_t* q = head + (size_t)i * 18 + j * 6;                     /* yoloface.c:116 */
+  float conf = sigmoidf_(((float)q[4] - (float)out_zp) * out_scale);
+  int gx = i % gw, gy = i / gw;                                         /* yoloface.c:129-130 */
+  float x = ((float)q[0] - (float)out_zp) * out_scale, y = ((float)q[1] - (float)out_zp) * out_scale;
+  float w = ((float)q[2] - (float)out_zp) * out_scale, h = ((float)q[3] - (float)out_zp) * out_scale;
+  x = (sigmoidf_(x) + (float)gx) * stride; y = (sigmoidf_(y) + (float)gy) * stride;   /* :135-136 */
+  w = expf(w) * anchors[j][0]; h = expf(h) * anchors[j][1];            /* :137-138 */
+  /* tflite_prediction.py:5-11 xywh2xyxy (the firmware's x/y swap + clamp is an LCD quirk) */
+  d->x1 = x - w / 2; d->y1 = y - h / 2; d->x2 = x + w / 2; d->y2 = y + h / 2; d->conf = conf;
+}
+
+static const float kAnchors[3][2] = {{9, 14}, {12, 17}, {22, 21}};      /* yoloface.c:20 */
+
+void yfo_decode_all(const int8_t* head, int gh, int gw, float out_scale, int out_zp, const float* anchors6, float stride,
+                    yfo_det* cands) {
+  const float (*an)[2] = anchors6 ? (const float (*)[2])anchors6 : kAnchors;
+  for (int i = 0; i < gh * gw; ++i) for (int j = 0; j < 3; ++j)
+    decode_one(head, gw, out_scale, out_zp, an, stride, i, j, &cands[i * 3 + j]);
+}
+
+int yfo_decode_nms_ex(const int8_t* head, int gh, int gw, float out_scale, int out_zp, const float* anchors6, float stride,
+                      float conf_thr, float iou_thr, int plus_one, yfo_det* dets, int max_det) {
+  const float (*an)[2] = anchors6 ? (const float (*)[2])anchors6 : kAnchors;
   int ncand = gh * gw * 3, n = 0;
   yfo_det* c = (yfo_det*)malloc(sizeof(yfo_det) * (size_t)ncand);
   int* idx = (int*)malloc(sizeof(int) * (size_t)ncand);
   for (int i = 0; i < gh * gw; ++i) for (int j = 0; j < 3; ++j) {
-    const int8_t* q = head + (size_t)i * 18 + j * 6;                   /* yoloface.c:116 */
+    const int8_t* q = head + (size_t)i * 18 + j * 6;
     float conf = sigmoidf_(((float)q[4] - (float)out_zp) * out_scale);
     if (!(conf >= conf_thr)) continue;                                  /* yoloface.c:123 */
-    int gx = i % gw, gy = i / gw;                                       /* yoloface.c:129-130 */
-    float x = ((float)q[0] - (float)out_zp) * out_scale, y = ((float)q[1] - (float)out_zp) * out_scale;
-    float w = ((float)q[2] - (float)out_zp) * out_scale, h = ((float)q[3] - (float)out_zp) * out_scale;
-    x = (sigmoidf_(x) + (float)gx) * 8.f; y = (sigmoidf_(y) + (float)gy) * 8.f;   /* :135-136 */
-    w = expf(w) * anchors[j][0]; h = expf(h) * anchors[j][1];          /* :137-138 */
-    /* tflite_prediction.py:5-11 xywh2xyxy (the firmware's x/y swap + clamp is an LCD quirk) */
-    c[n].x1 = x - w / 2; c[n].y1 = y - h / 2; c[n].x2 = x + w / 2; c[n].y2 = y + h / 2; c[n].conf = conf;
+    decode_one(head, gw, out_scale, out_zp, an, stride, i, j, &c[n]);
     idx[n] = i * 3 + j; ++n;
   }
   /* stable insertion sort: conf desc, candidate index asc */
@@ -557,12 +575,12 @@ int yfo_decode_nms(const int8_t* head, int gh, int gw, float out_scale, int out_
     if (iou_thr < 0) continue;
     float one = plus_one ? 1.f : 0.f;
     float ax1 = c[a].x1, ay1 = c[a].y1, ax2 = c[a].x2, ay2 = c[a].y2;
-    if (plus_one) { ax1 = (float)(int)ax1; ay1 = (float)(int)ay1; ax2 = (float)(int)ax2; ay2 = (float)(int)ay2; }
+    if (plus_one) { ax1 = truncf(ax1); ay1 = truncf(ay1); ax2 = truncf(ax2); ay2 = truncf(ay2); }
     float area_a = (ax2 - ax1 + one) * (ay2 - ay1 + one);
     for (int b = a + 1; b < n; ++b) {                                    /* yoloface_test.py:177-199 */
       if (dead[b]) continue;
       float bx1 = c[b].x1, by1 = c[b].y1, bx2 = c[b].x2, by2 = c[b].y2;
-      if (plus_one) { bx1 = (float)(int)bx1; by1 = (float)(int)by1; bx2 = (float)(int)bx2; by2 = (float)(int)by2; }
+      if (plus_one) { bx1 = truncf(bx1); by1 = truncf(by1); bx2 = truncf(bx2); by2 = truncf(by2); }
       float area_b = (bx2 - bx1 + one) * (by2 - by1 + one);
       float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1), xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
       float iw = fmaxf(0.f, xx2 - xx1 + one), ih = fmaxf(0.f, yy2 - yy1 + one);
@@ -573,6 +591,11 @@ int yfo_decode_nms(const int8_t* head, int gh, int gw, float out_scale, int out_
   }
   free(dead); free(c); free(idx);
   return kept;
+}
+
+int yfo_decode_nms(const int8_t* head, int gh, int gw, float out_scale, int out_zp,
+                   float conf_thr, float iou_thr, int plus_one, yfo_det* dets, int max_det) {
+  return yfo_decode_nms_ex(head, gh, gw, out_scale, out_zp, NULL, 8.f, conf_thr, iou_thr, plus_one, dets, max_det);
 }
 
 /* ------------------------------------------------------------------------------------------ */

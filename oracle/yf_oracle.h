@@ -81,6 +81,12 @@ typedef struct { float x1, y1, x2, y2, conf; } yfo_det;
  * Returns #detections written (<= max_det), sorted by conf desc, ties by candidate index asc. */
 int yfo_decode_nms(const int8_t* head, int gh, int gw, float out_scale, int out_zp,
                    float conf_thr, float iou_thr, int plus_one, yfo_det* dets, int max_det);
+/* The same with the anchor table (3 x {w,h}, NULL = yoloface.c:20) and the cell stride as parameters. */
+int yfo_decode_nms_ex(const int8_t* head, int gh, int gw, float out_scale, int out_zp, const float* anchors6, float stride,
+                      float conf_thr, float iou_thr, int plus_one, yfo_det* dets, int max_det);
+/* Every candidate decoded, no threshold, memory order (cands[gh*gw*3], index = cell*3 + anchor). */
+void yfo_decode_all(const int8_t* head, int gh, int gw, float out_scale, int out_zp, const float* anchors6, float stride,
+                    yfo_det* cands);
 
 /* ---- camera-side pre-processing (yoloface.c:26-93): RGB565 112x112 big-endian byte pairs ->
  * 2x2 box average per 5/6/5 field -> expand (r<<3,g<<2,b<<3) -> -128 -> int8 [56,56,3] ---- */

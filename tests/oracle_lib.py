@@ -57,6 +57,10 @@ class Oracle:
         lib.yfo_leaky_lut.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.yfo_decode_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int,
                                        C.POINTER(Det), C.c_int]
+        lib.yfo_decode_nms_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_float, C.c_float,
+                                          C.c_float, C.c_int, C.POINTER(Det), C.c_int]
+        lib.yfo_decode_all.restype = None
+        lib.yfo_decode_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_float, C.POINTER(Det)]
         lib.yfo_rgb565_to_input.argtypes = [C.c_void_p, C.c_void_p]
         self.m = lib.yfo_load(self._cbuf, len(self.buf))
         if not self.m:
@@ -124,12 +128,25 @@ class Oracle:
             raise ValueError("op %d is not LEAKY_RELU" % op)
         return lut
 
-    def decode_nms(self, head, conf_thr=0.7, iou_thr=0.4, plus_one=False, scale=0.14218327403068542, zp=-15):
+    def decode_nms(self, head, conf_thr=0.7, iou_thr=0.4, plus_one=False, scale=0.14218327403068542, zp=-15,
+                   anchors=None, stride=8.0, max_det=None):
+        head = np.ascontiguousarray(head, dtype=np.int8)
+        gh, gw, _ = head.shape
+        cap = gh * gw * 3 if max_det is None else max_det
+        dets = (Det * max(cap, 1))()
+        an = None if anchors is None else np.ascontiguousarray(anchors, np.float32).reshape(6)
+        n = self.lib.yfo_decode_nms_ex(head.ctypes.data, gh, gw, scale, zp, None if an is None else an.ctypes.data, stride,
+                                       conf_thr, iou_thr, int(plus_one), dets, cap)
+        return np.frombuffer(dets, np.float32, n * 5).reshape(-1, 5).copy()
+
+    def decode_all(self, head, scale=0.14218327403068542, zp=-15, anchors=None, stride=8.0):
+        """every candidate, memory order (cell-major, anchor-minor): [gh*gw*3, 5] = x1,y1,x2,y2,conf"""
         head = np.ascontiguousarray(head, dtype=np.int8)
         gh, gw, _ = head.shape
         dets = (Det * (gh * gw * 3))()
-        n = self.lib.yfo_decode_nms(head.ctypes.data, gh, gw, scale, zp, conf_thr, iou_thr, int(plus_one), dets, gh * gw * 3)
-        return np.array([[d.x1, d.y1, d.x2, d.y2, d.conf] for d in dets[:n]], np.float32).reshape(-1, 5)
+        an = None if anchors is None else np.ascontiguousarray(anchors, np.float32).reshape(6)
+        self.lib.yfo_decode_all(head.ctypes.data, gh, gw, scale, zp, None if an is None else an.ctypes.data, stride, dets)
+        return np.frombuffer(dets, np.float32, gh * gw * 15).reshape(-1, 5).copy()
 
     def rgb565_to_input(self, frame):
         frame = np.ascontiguousarray(frame, dtype=np.uint8)

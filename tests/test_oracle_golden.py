@@ -176,3 +176,35 @@ def test_ragged_and_edge_inputs(oracle):
         assert np.array_equal(big[12, 12], big[14, 15])
     out = oracle.run_batch(np.zeros((0, 56, 56, 3), np.int8), threads=4)
     assert out.shape == (0, 7, 7, 18)
+
+
+def test_requant_primitives_vs_reference_cmsis_nn(oracle):
+    """Row a11: the reference tree carries CMSIS-NN's statement of TFLite's two fixed-point primitives
+    (stm32/Drivers/CMSIS/NN/Include/arm_nnsupportfunctions.h:210-263), compiled in place into oracle/_ref/libcmsis_ref.so
+    (oracle/Makefile `ref`).  RoundingDivideByPOT is compared over the full sign range; the doubling-high-mult only for
+    non-negative products: the header is ILP32 code and its `mult / (1UL << 31)` divides unsigned on an LP64 host."""
+    import ctypes as C
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcmsis_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libcmsis_ref.so not built (needs /root/reference at build time)")
+    ref = C.CDLL(so)
+    for f in (ref.ref_sat_doubling_high_mult, ref.ref_divide_by_power_of_two):
+        f.restype = C.c_int32; f.argtypes = [C.c_int32, C.c_int32]
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([rng.integers(-2**31, 2**31, 20000), np.arange(-4096, 4096), [2**31 - 1, -2**31, -2**31 + 1]])
+    for e in (0, 1, 2, 5, 7, 8, 12, 20, 30, 31):
+        for x in xs[:: 7 if e not in (1, 8) else 1]:
+            assert oracle.lib.yfo_rdivpot(int(x), e) == ref.ref_divide_by_power_of_two(int(x), e), (x, e)
+    mults = [1825044608, 1460035712, 1073741824, 2147483647, 1518500250] + rng.integers(2**30, 2**31, 40).tolist()
+    accs = np.concatenate([rng.integers(0, 2**22, 4000), np.arange(0, 3000), rng.integers(0, 2**31, 2000)])
+    n = 0
+    for m in mults:
+        for a in accs[::3]:
+            assert oracle.lib.yfo_srdhm(int(a), int(m)) == ref.ref_sat_doubling_high_mult(int(a), int(m)), (a, m)
+            n += 1
+    # both negative -> non-negative product as well
+    for a in rng.integers(-2**22, 0, 3000):
+        m = -int(rng.integers(2**30, 2**31))
+        assert oracle.lib.yfo_srdhm(int(a), m) == ref.ref_sat_doubling_high_mult(int(a), m)
+    assert n > 50000

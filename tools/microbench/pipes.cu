@@ -19,6 +19,10 @@ __global__ void k(int* out, int n, int seed, long long* cyc) {
       else if (KIND == 4) { long long p = (long long)a[i] * b + 0x40000000ll; a[i] = (int)(p >> 31); }
       else if (KIND == 5) a[i] = __vimin_s32_relu(a[i] + it, 255);
       else if (KIND == 6) a[i] = (a[i] >> 3) + b;
+      else if (KIND == 7) a[i] = (__mulhi(a[i], b) + 128) >> 8;                    // IMAD.HI (+ addend) + SHF: 32-bit form of the SRDHM
+      else if (KIND == 8) a[i] = __mulhi(a[i], b);                                 // IMAD.HI alone
+      else if (KIND == 9) { long long p = (long long)a[i] * b; a[i] = (int)p ^ (int)(p >> 32); }   // IMAD.WIDE alone (+ LOP3)
+      else if (KIND == 10) a[i] = __funnelshift_r(a[i], b, 31) + it;                // SHF.R funnel + IADD
     }
   }
   long long t1 = clock64();
@@ -44,10 +48,10 @@ int main() {
   int* out; long long* cyc; cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 1024);
   int h[4096]; for (int i = 0; i < 4096; ++i) h[i] = (i * 7 + 1) & 4095;
   cudaMemcpyToSymbol(c_tab, h, sizeof h);
-  const char* names[] = {"IDP.4A (dp4a)", "IMAD", "PRMT", "VIMNMX3.S16x2", "IMAD.WIDE+SHF (srdhm)", "IADD+VIMNMX.RELU", "SHF+IADD"};
+  const char* names[] = {"IDP.4A (dp4a)", "IMAD", "PRMT", "VIMNMX3.S16x2", "IMAD.WIDE+SHF (srdhm)", "IADD+VIMNMX.RELU", "SHF+IADD", "IMAD.HI+IADD+SHF", "IMAD.HI", "IMAD.WIDE+LOP3", "SHF.funnel+IADD"};
   const int n = 2000;
   for (int warps : {1, 4, 8, 16}) {
-    for (int kind = 0; kind < 7; ++kind) {
+    for (int kind = 0; kind < 11; ++kind) {
       long long c = 0;
       for (int rep = 0; rep < 2; ++rep) {
         switch (kind) {
@@ -55,6 +59,8 @@ int main() {
           case 2: k<2><<<1, warps * 32>>>(out, n, 3, cyc); break; case 3: k<3><<<1, warps * 32>>>(out, n, 3, cyc); break;
           case 4: k<4><<<1, warps * 32>>>(out, n, 3, cyc); break; case 5: k<5><<<1, warps * 32>>>(out, n, 3, cyc); break;
           case 6: k<6><<<1, warps * 32>>>(out, n, 3, cyc); break;
+          case 7: k<7><<<1, warps * 32>>>(out, n, 3, cyc); break; case 8: k<8><<<1, warps * 32>>>(out, n, 3, cyc); break;
+          case 9: k<9><<<1, warps * 32>>>(out, n, 3, cyc); break; case 10: k<10><<<1, warps * 32>>>(out, n, 3, cyc); break;
         }
         cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
       }
