@@ -84,6 +84,13 @@ AI_API_ENTRY int32_t yf_b200_wait(ai_handle network);
 AI_API_ENTRY int32_t yf_b200_decode(ai_handle network, const void* heads, uint32_t n, float conf_thr, float iou_thr,
                                     uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det);
 
+/* Anchor table (3 x {w, h} in input pixels; NULL keeps the current one, default = yoloface.c:20) and the input
+ * pixels per head cell (0 = input height / head rows, 8 for this model: yoloface.c:135-136) used by the decode.
+ * Every candidate that passes conf_thr takes part in the NMS, whatever the head size: heads up to 8x8 cells use one
+ * warp per image, larger ones one thread block per image with storage for all gh*gw*3 candidates (heads beyond
+ * 52x52 cells are refused with an error, never truncated). */
+AI_API_ENTRY int32_t yf_b200_set_decode_params(ai_handle network, const float* anchors6, float stride);
+
 /* Inference + decode + NMS in one call; only detections travel back to the host.
  * heads_out may be NULL. */
 AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t n, float conf_thr, float iou_thr,

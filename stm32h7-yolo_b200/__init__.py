@@ -71,7 +71,7 @@ EXPORTS = [
     "ai_network_create", "ai_network_init", "ai_network_run", "ai_network_forward", "ai_network_destroy",
     "ai_network_get_error", "ai_network_get_report", "ai_network_get_info", "ai_network_data_weights_get",
     "ai_network_data_params_get", "yf_b200_set_input_size", "yf_b200_run", "yf_b200_decode", "yf_b200_detect",
-    "yf_b200_preprocess_rgb565", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
+    "yf_b200_preprocess_rgb565", "yf_b200_set_decode_params", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
     "yf_b200_get_stats", "yf_b200_step_count", "yf_b200_step_info_get", "yf_b200_set_step_profiling",
     "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_enqueue_batches", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_debug_raise", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
 ]
@@ -134,6 +134,8 @@ def lib():
     L.yf_b200_detect.argtypes = [vp, vp, u32, C.c_float, C.c_float, u32, vp, vp, u32, vp]
     L.yf_b200_preprocess_rgb565.restype = i32
     L.yf_b200_preprocess_rgb565.argtypes = [vp, vp, vp, u32]
+    L.yf_b200_set_decode_params.restype = i32
+    L.yf_b200_set_decode_params.argtypes = [vp, vp, C.c_float]
     L.yf_b200_set_observer.restype = i32
     L.yf_b200_set_observer.argtypes = [vp, i32]
     L.yf_b200_get_tensor.restype = C.c_int64
@@ -368,6 +370,12 @@ class Network:
         if r < 0:
             self._raise("yf_b200_decode")
         return dets, counts
+
+    def set_decode_params(self, anchors=None, stride=0.0):
+        """anchors: 3 x (w, h) in input pixels (None keeps the current table); stride 0 = input height / head rows"""
+        an = None if anchors is None else np.ascontiguousarray(anchors, np.float32).reshape(6)
+        if self.L.yf_b200_set_decode_params(self.handle, None if an is None else an.ctypes.data, float(stride)) < 0:
+            self._raise("yf_b200_set_decode_params")
 
     def preprocess_rgb565(self, frames):
         frames = np.ascontiguousarray(frames, np.uint8).reshape(-1, 112 * 112 * 2)

@@ -40,25 +40,30 @@ struct PlanDev {
   uint8_t* d_wblob = nullptr;
   uint8_t* d_luts = nullptr;
   uint8_t* d_arena = nullptr;
-  int8_t* d_in = nullptr;               // staging for host inputs [cap,H,W,3]      (= ring slot 0)
-  int8_t* d_head = nullptr;             // staging for host outputs [cap,GH,GW,18] (= ring slot 0)
+  int8_t* d_in = nullptr;               // staging of the synchronous paths for host inputs [cap,H,W,3] (never a ring slot)
+  int8_t* d_head = nullptr;             // staging of the synchronous paths for heads [cap,GH,GW,C]
   static constexpr int kRing = 6;       // pipelined host path: slots of (input, head) staging + events
   int8_t* r_in[kRing] = {};
   int8_t* r_head[kRing] = {};
   cudaEvent_t ev_h2d[kRing] = {}, ev_comp[kRing] = {}, ev_d2h[kRing] = {};
   bool busy[kRing] = {};
+  bool ring_ready = false;              // set only once every slot and event exists
   uint64_t seq = 0;
   std::vector<CUtensorMap> tmaps;       // per step (conv1x1 only)
   std::vector<float> step_ms;
   Plan fplan;                           // same steps with 16-aligned concat slots, for the fused kernel
   FusedProgram fprog;
   uint8_t* d_fparams = nullptr;
+  FusedPhase* d_fphases = nullptr;      // this plan's phase descriptors (global memory: nothing is shared between plans)
+  bool fused_spec = false;              // the plan is the one the specialised kernel was generated from
   ~PlanDev() {
-    cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams);
-    for (int i = 1; i < kRing; ++i) { cudaFree(r_in[i]); cudaFree(r_head[i]); }
+    cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams); cudaFree(d_fphases);
+    for (int i = 0; i < kRing; ++i) { cudaFree(r_in[i]); cudaFree(r_head[i]); }
     for (int i = 0; i < kRing; ++i) { if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]); if (ev_comp[i]) cudaEventDestroy(ev_comp[i]); if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]); }
   }
 };
+
+size_t head_bytes(const PlanDev* pd) { const Plan& P = pd->plan; return static_cast<size_t>(P.GH) * P.GW * P.buffers[P.output_buf].C; }
 
 struct Network {
   bool initialized = false;
@@ -79,6 +84,8 @@ struct Network {
   int* d_err = nullptr;                 // device view of the same word
   long long* d_trace = nullptr; bool trace_on = false;
   float* d_dets = nullptr; int* d_counts = nullptr; size_t dets_cap = 0; uint32_t dets_max = 0;
+  float anchors[6] = {9.f, 14.f, 12.f, 17.f, 22.f, 21.f};   // yoloface.c:20 (yf_b200_set_decode_params overrides)
+  float stride = 0.f;                   // 0: input height / head rows (8 for this model)
   uint8_t* d_frames = nullptr; size_t frames_cap = 0;
   // small host batches: the kernels read the images from / write the heads to mapped pinned memory (no DMA copies)
   int8_t* h_small = nullptr; size_t small_cap = 0;      // [in | out], device-visible at the same address (UVA)
@@ -96,6 +103,21 @@ struct Network {
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
   void latch(int type, int code) { if (err.type == AI_ERROR_NONE) { err.type = type; err.code = code; } }
+  // Everything the context owns on its device; shared by ai_network_destroy and the failure paths of ai_network_create
+  // (the caller has selected n->device).  Safe on a partially constructed object: every handle starts out null.
+  ~Network() {
+    plans.clear();
+    if (h_err) cudaFreeHost(h_err);
+    if (h_small) cudaFreeHost(h_small);
+    cudaFree(d_trace); cudaFree(d_dets); cudaFree(d_counts); cudaFree(d_frames);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (own_stream) cudaStreamDestroy(own_stream);
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+    for (int l = 0; l < kLanes; ++l) { if (lane[l]) cudaStreamDestroy(lane[l]); if (ev_join[l]) cudaEventDestroy(ev_join[l]); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+  }
 };
 
 bool make_lanes(Network* n) {
@@ -114,7 +136,6 @@ std::mutex g_dev_mu[64];
 // device or per configuration, so every create returns a fresh context and all stay valid.
 std::vector<Network*> g_nets;
 const void* g_active_epi[64] = {};      // per device: whose EpiCh table sits in __constant__ memory
-const void* g_active_fused[64] = {};    // per device: whose fused tables sit in __constant__ memory
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -167,7 +188,6 @@ PlanDev* get_plan(Network* n, int H, int W) {
   if (it != n->plans.end() && it->second->observer == n->observer && it->second->cap == n->chunk) return it->second.get();
   if (it != n->plans.end()) {
     if (g_active_epi[n->device & 63] == it->second.get()) g_active_epi[n->device & 63] = nullptr;
-    if (g_active_fused[n->device & 63] == it->second.get()) g_active_fused[n->device & 63] = nullptr;
     n->plans.erase(it);
   }
   std::unique_ptr<PlanDev> pd(new PlanDev);
@@ -184,7 +204,7 @@ PlanDev* get_plan(Network* n, int H, int W) {
   if (!cuda_ok(n, cudaMalloc(&pd->d_luts, std::max<size_t>(P.luts.size(), 256)), "cudaMalloc luts", al, ac)) return nullptr;
   if (!cuda_ok(n, cudaMalloc(&pd->d_arena, per_img * pd->cap + 1024), "cudaMalloc arena", al, ac)) return nullptr;
   if (!cuda_ok(n, cudaMalloc(&pd->d_in, static_cast<size_t>(H) * W * 3 * pd->cap), "cudaMalloc input staging", al, ac)) return nullptr;
-  if (!cuda_ok(n, cudaMalloc(&pd->d_head, static_cast<size_t>(P.GH) * P.GW * 18 * pd->cap), "cudaMalloc head staging", al, ac)) return nullptr;
+  if (!cuda_ok(n, cudaMalloc(&pd->d_head, head_bytes(pd.get()) * pd->cap), "cudaMalloc head staging", al, ac)) return nullptr;
   if (!cuda_ok(n, cudaMemcpyAsync(pd->d_wblob, P.wblob.data(), P.wblob.size(), cudaMemcpyHostToDevice, n->stream), "upload weights")) return nullptr;
   if (!P.luts.empty() && !cuda_ok(n, cudaMemcpyAsync(pd->d_luts, P.luts.data(), P.luts.size(), cudaMemcpyHostToDevice, n->stream), "upload luts")) return nullptr;
   // pad channels of every buffer must read as defined bytes: clear the arena once
@@ -214,7 +234,12 @@ PlanDev* get_plan(Network* n, int H, int W) {
       build_fused(pd->fplan, &pd->fprog) && pd->fprog.ok) {
     if (!cuda_ok(n, cudaMalloc(&pd->d_fparams, pd->fprog.params.size()), "cudaMalloc fused params", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
     if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fparams, pd->fprog.params.data(), pd->fprog.params.size(), cudaMemcpyHostToDevice, n->stream), "upload fused params")) return nullptr;
-    if (!cuda_ok(n, fused_init(pd->fprog.smem_bytes), "fused kernel attributes")) return nullptr;
+    const size_t dbytes = pd->fprog.phases.size() * sizeof(FusedPhase);
+    if (!cuda_ok(n, cudaMalloc(&pd->d_fphases, dbytes), "cudaMalloc fused descriptors", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+    if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fphases, pd->fprog.phases.data(), dbytes, cudaMemcpyHostToDevice, n->stream), "upload fused descriptors")) return nullptr;
+    static const bool spec_off = [] { const char* e = std::getenv("YF_B200_FUSED_SPEC"); return e && !std::atoi(e); }();
+    pd->fused_spec = !spec_off && fused_spec_matches(pd->fprog);
+    if (!cuda_ok(n, fused_init(pd->fprog.smem_bytes, pd->fused_spec ? pd->fprog.smem_bytes_spec : 0), "fused kernel attributes")) return nullptr;
   } else {
     pd->fprog.ok = false;
     if (pd->fprog.why.empty()) pd->fprog.why = ferr;
@@ -273,19 +298,16 @@ EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* 
 // independent chunks may then run concurrently)
 bool uses_fused(const Network* n, const PlanDev* pd) { return !pd->observer && !n->step_profiling && n->mode != 1 && pd->fprog.ok; }
 
-bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb, cudaStream_t st = nullptr) {
+// overlapped: the caller queues further launches around this one (kernel lanes / the pipelined host ring)
+bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb, cudaStream_t st = nullptr, bool overlapped = false) {
   const Plan& P = pd->plan;
   if (!st) st = n->stream;
   if (uses_fused(n, pd)) {
-    if (g_active_fused[n->device & 63] != pd) {
-      if (!cuda_ok(n, cudaDeviceSynchronize(), "synchronize before table switch")) return false;
-      if (!cuda_ok(n, upload_fused_tables(pd->fplan.epi.data(), static_cast<int>(pd->fplan.epi.size()), pd->fprog.phases.data(),
-                                          static_cast<int>(pd->fprog.phases.size()), n->stream), "upload fused tables")) return false;
-      if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "upload fused tables")) return false;   // visible to every lane
-      g_active_fused[n->device & 63] = pd;
-    }
-    if (!cuda_ok(n, launch_fused(pd->fprog, d_in, d_head, pd->d_fparams, static_cast<int>(nb), n->sm_count, n->d_err, st,
-                                 n->trace_on ? n->d_trace : nullptr), "fused kernel")) return false;
+    FusedLaunch L{};
+    L.d_in = d_in; L.d_out = d_head; L.d_params = pd->d_fparams; L.d_phases = pd->d_fphases; L.n_img = static_cast<int>(nb);
+    L.sm_count = n->sm_count; L.d_err = n->d_err; L.stream = st; L.d_trace = n->trace_on ? n->d_trace : nullptr;
+    L.use_spec = pd->fused_spec; L.overlapped = overlapped;
+    if (!cuda_ok(n, launch_fused(pd->fprog, L), "fused kernel")) return false;
     ++n->launches;
     return true;
   }
@@ -376,7 +398,7 @@ bool run_chunks(Network* n, PlanDev* pd, const std::vector<DevChunk>& ch) {
   if (!cuda_ok(n, cudaEventRecord(n->ev_fork, n->stream), "fork")) return false;
   for (int l = 0; l < Network::kLanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
   for (size_t i = 0; i < ch.size(); ++i) {
-    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[i % Network::kLanes])) return false;
+    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[i % Network::kLanes], true)) return false;
     n->last_run_n = ch[i].nb;
   }
   for (int l = 0; l < Network::kLanes; ++l) {
@@ -388,29 +410,31 @@ bool run_chunks(Network* n, PlanDev* pd, const std::vector<DevChunk>& ch) {
 
 // ---- pipelined host path: H2D (s_h2d) -> kernels (lanes) -> D2H (s_d2h) over a ring of staging slots ----
 bool ring_prepare(Network* n, PlanDev* pd) {
-  if (pd->ev_h2d[0]) return true;
-  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3 * pd->cap, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18 * pd->cap;
-  pd->r_in[0] = pd->d_in; pd->r_head[0] = pd->d_head;
+  if (pd->ring_ready) return true;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3 * pd->cap, out_sz = head_bytes(pd) * pd->cap;
+  // The ring owns its buffers: the synchronous paths (d_in / d_head) may run while submissions are still in flight.
+  // A partial failure leaves ring_ready false; what was allocated is reused by the next attempt / freed with the plan.
   for (int i = 0; i < PlanDev::kRing; ++i) {
-    if (i && (!cuda_ok(n, cudaMalloc(&pd->r_in[i], in_sz), "cudaMalloc ring", AI_ERROR_ALLOCATION_FAILED) ||
-              !cuda_ok(n, cudaMalloc(&pd->r_head[i], out_sz), "cudaMalloc ring", AI_ERROR_ALLOCATION_FAILED))) return false;
-    if (!cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_h2d[i], cudaEventDisableTiming), "event") ||
-        !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_comp[i], cudaEventDisableTiming), "event") ||
-        !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_d2h[i], cudaEventDisableTiming), "event")) return false;
+    if (!pd->r_in[i] && !cuda_ok(n, cudaMalloc(&pd->r_in[i], in_sz), "cudaMalloc ring", AI_ERROR_ALLOCATION_FAILED)) return false;
+    if (!pd->r_head[i] && !cuda_ok(n, cudaMalloc(&pd->r_head[i], out_sz), "cudaMalloc ring", AI_ERROR_ALLOCATION_FAILED)) return false;
+    if (!pd->ev_h2d[i] && !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_h2d[i], cudaEventDisableTiming), "event")) return false;
+    if (!pd->ev_comp[i] && !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_comp[i], cudaEventDisableTiming), "event")) return false;
+    if (!pd->ev_d2h[i] && !cuda_ok(n, cudaEventCreateWithFlags(&pd->ev_d2h[i], cudaEventDisableTiming), "event")) return false;
   }
+  pd->ring_ready = true;
   return true;
 }
 // queue one chunk (nb <= cap) from host memory; returns without waiting.  out may be NULL (heads stay in the slot).
 bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_host, uint32_t nb, int8_t** slot_heads) {
   if (!ring_prepare(n, pd)) return false;
   const int s = static_cast<int>(pd->seq++ % PlanDev::kRing);
-  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
   if (pd->busy[s] && !cuda_ok(n, cudaEventSynchronize(pd->ev_d2h[s]), "ring slot wait")) return false;   // slot's previous user has drained
   if (!cuda_ok(n, cudaMemcpyAsync(pd->r_in[s], in_host, nb * in_sz, cudaMemcpyHostToDevice, n->s_h2d), "H2D input", AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
   cudaEventRecord(pd->ev_h2d[s], n->s_h2d);
   cudaStream_t ks = uses_fused(n, pd) ? n->lane[n->lane_seq++ % Network::kLanes] : n->stream;
   cudaStreamWaitEvent(ks, pd->ev_h2d[s], 0);
-  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb, ks)) return false;
+  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb, ks, true)) return false;
   cudaEventRecord(pd->ev_comp[s], ks);
   cudaStreamWaitEvent(n->s_d2h, pd->ev_comp[s], 0);
   if (out_host && !cuda_ok(n, cudaMemcpyAsync(out_host, pd->r_head[s], nb * out_sz, cudaMemcpyDeviceToHost, n->s_d2h), "D2H output", AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
@@ -425,12 +449,23 @@ bool ring_wait(Network* n, PlanDev* pd) {
   return true;
 }
 
+// failure path: whatever a partly queued submission left on the copy / kernel streams must finish before the caller
+// gets its buffers back
+void ring_drain(Network* n, PlanDev* pd) {
+  ring_wait(n, pd);
+  cudaStreamSynchronize(n->s_h2d);
+  for (int l = 0; l < Network::kLanes; ++l) cudaStreamSynchronize(n->lane[l]);
+  cudaStreamSynchronize(n->stream);
+  cudaStreamSynchronize(n->s_d2h);
+  for (int i = 0; i < PlanDev::kRing; ++i) pd->busy[i] = false;
+}
+
 // inference of n images; in/out host or device
 int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool keep_heads_on_device, int8_t** dev_heads) {
   PlanDev* pd = get_plan(n, n->H, n->W);
   if (!pd) return -1;
   const Plan& P = pd->plan;
-  const size_t in_sz = static_cast<size_t>(P.H) * P.W * 3, out_sz = static_cast<size_t>(P.GH) * P.GW * 18;
+  const size_t in_sz = static_cast<size_t>(P.H) * P.W * 3, out_sz = head_bytes(pd);
   const bool in_dev = is_device_ptr(in);
   const bool out_dev = out ? is_device_ptr(out) : true;
   if (in_dev && (reinterpret_cast<uintptr_t>(in) & 15)) { set_text("device input must be 16-byte aligned"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
@@ -468,7 +503,10 @@ int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool k
     if (uses_fused(n, pd) && count >= 512) piece = std::min<uint32_t>(pd->cap, std::max<uint32_t>(256, ((count + 3) / 4 + 15) & ~15u));
     for (uint32_t done = 0; done < count; done += piece) {
       const uint32_t nb = std::min<uint32_t>(piece, count - done);
-      if (!ring_submit(n, pd, static_cast<const int8_t*>(in) + done * in_sz, static_cast<int8_t*>(out) + done * out_sz, nb, nullptr)) return -1;
+      if (!ring_submit(n, pd, static_cast<const int8_t*>(in) + done * in_sz, static_cast<int8_t*>(out) + done * out_sz, nb, nullptr)) {
+        ring_drain(n, pd);                                  // copies into the caller's buffers must not stay pending
+        return -1;
+      }
     }
     if (!ring_wait(n, pd)) return -1;
     if (!check_mirrored_err(n)) return -1;
@@ -505,16 +543,30 @@ bool ensure_dets(Network* n, uint32_t count, uint32_t max_det) {
   return true;
 }
 
+// decode + NMS launch arguments from the plan (head geometry, output quantisation) and the context (anchors, stride)
+bool fill_decode_args(Network* n, const PlanDev* pd, DecodeArgs* a, const int8_t* d_heads, uint32_t count, float conf_thr, float iou_thr,
+                      uint32_t flags, float* d_dets, int* d_counts, uint32_t max_det) {
+  const Plan& P = pd->plan;
+  if (P.buffers[P.output_buf].C != 18) {   // 3 anchors x {x, y, w, h, conf, class} (yoloface.c:116)
+    set_text("decode: the model's head does not have 3 x 6 channels"); n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_INVALID_FORMAT); return false;
+  }
+  a->head = d_heads; a->n_img = static_cast<int>(count); a->gh = P.GH; a->gw = P.GW;
+  a->scale = P.out_scale; a->zp = P.out_zp;
+  for (int i = 0; i < 6; ++i) a->anchors[i] = n->anchors[i];
+  a->stride = n->stride > 0.f ? n->stride : static_cast<float>(P.H) / static_cast<float>(P.GH);
+  a->conf_thr = conf_thr; a->iou_thr = iou_thr; a->plus_one = (flags & YF_B200_NMS_PLUS_ONE) ? 1 : 0;
+  a->dets = d_dets; a->counts = d_counts; a->max_det = static_cast<int>(max_det);
+  return true;
+}
+
 int32_t decode_on_device(Network* n, const int8_t* d_heads, uint32_t count, int gh, int gw, float conf_thr, float iou_thr,
                          uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det) {
   if (!ensure_dets(n, count, max_det)) return -1;
-  DecodeArgs a{};
-  a.head = d_heads; a.n_img = static_cast<int>(count); a.gh = gh; a.gw = gw;
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
-  a.scale = pd->plan.out_scale; a.zp = pd->plan.out_zp;
-  a.conf_thr = conf_thr; a.iou_thr = iou_thr; a.plus_one = (flags & YF_B200_NMS_PLUS_ONE) ? 1 : 0;
-  a.dets = n->d_dets; a.counts = n->d_counts; a.max_det = static_cast<int>(max_det);
-  if (!cuda_ok(n, launch_decode_nms(a, n->stream), "decode_nms")) return -1;
+  DecodeArgs a{};
+  if (!fill_decode_args(n, pd, &a, d_heads, count, conf_thr, iou_thr, flags, n->d_dets, n->d_counts, max_det)) return -1;
+  (void)gh; (void)gw;
+  if (!cuda_ok(n, launch_decode_nms(a, n->stream), "decode_nms (head too large for the on-device decode?)")) return -1;
   ++n->launches;
   if (!cuda_ok(n, cudaMemcpyAsync(counts, n->d_counts, sizeof(int) * count, cudaMemcpyDeviceToHost, n->stream), "D2H counts")) return -1;
   if (!cuda_ok(n, cudaMemcpyAsync(dets, n->d_dets, sizeof(float) * 5 * count * max_det, cudaMemcpyDeviceToHost, n->stream), "D2H detections")) return -1;
@@ -556,13 +608,34 @@ void fill_report(Network* n, ai_network_report* r) {
   r->tool_api_version = ai_platform_version{AI_TOOLS_API_VERSION_MAJOR, AI_TOOLS_API_VERSION_MINOR, AI_TOOLS_API_VERSION_MICRO, 0};
   r->api_version = ai_platform_version{1, 1, 0, 0};
   r->interface_api_version = ai_platform_version{1, 3, 0, 0};
-  r->n_macc = 1344320;                  /* ST's count incl. pools/activations (network.c:3296) */
-  in_desc = ai_buffer{AI_BUFFER_FORMAT_S8, 1, static_cast<ai_u16>(n->H), static_cast<ai_u16>(n->W), 3, nullptr, nullptr};
-  out_desc = ai_buffer{AI_BUFFER_FORMAT_S8, 1, static_cast<ai_u16>(n->H / 8), static_cast<ai_u16>(n->W / 8), 18, nullptr, nullptr};
+  // The numbers describe the model and input size this context actually runs (not the macros of the deployed model).
+  // MACC in ST's convention: conv / depthwise MACs + the window elements of every pooled output + one op per
+  // LEAKY_RELU / ADD output element (network_generate_report.txt:484-519).  For yoloface at 56x56 this gives 1,343,776
+  // against ST's 1,344,320 (network_generate_report.txt:20): the generator's exact rule for the last 0.04 % is not
+  // documented, so the figure is computed, not quoted.
+  int in_c = 3, out_c = 18, gh = n->H / 8, gw = n->W / 8, nodes = AI_NETWORK_N_NODES; long long macc = 0; size_t wbytes = AI_NETWORK_DATA_WEIGHTS_SIZE;
+  auto it = n->plans.find(std::make_pair(n->H, n->W));
+  if (it != n->plans.end()) {
+    const Plan& P = it->second->plan;
+    in_c = P.buffers[P.input_buf].C; out_c = P.buffers[P.output_buf].C; gh = P.GH; gw = P.GW; nodes = static_cast<int>(P.steps.size());
+    macc = P.macs_per_image;
+    for (const Step& s : P.steps) {
+      const long long opix = static_cast<long long>(s.Hout) * s.Wout;
+      if (s.kind == STEP_MAXPOOL) macc += opix * s.Cout * s.kh * s.kw;
+      for (int op : s.ops) {
+        const int code = n->model.ops[static_cast<size_t>(op)].opcode;
+        if (code == OP_LEAKY_RELU || code == OP_ADD) macc += opix * s.Cout;
+      }
+    }
+    st_blob_layout(n->model, &wbytes);
+  }
+  r->n_macc = static_cast<ai_u32>(macc);
+  in_desc = ai_buffer{AI_BUFFER_FORMAT_S8, 1, static_cast<ai_u16>(n->H), static_cast<ai_u16>(n->W), static_cast<ai_u32>(in_c), nullptr, nullptr};
+  out_desc = ai_buffer{AI_BUFFER_FORMAT_S8, 1, static_cast<ai_u16>(gh), static_cast<ai_u16>(gw), static_cast<ai_u32>(out_c), nullptr, nullptr};
   r->n_inputs = 1; r->n_outputs = 1; r->inputs = &in_desc; r->outputs = &out_desc;
-  r->params = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, AI_NETWORK_DATA_WEIGHTS_SIZE, nullptr, nullptr};
+  r->params = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, static_cast<ai_u32>(wbytes), nullptr, nullptr};
   r->activations = ai_buffer{AI_BUFFER_FORMAT_U8, 1, 1, 1, AI_NETWORK_DATA_ACTIVATIONS_SIZE, nullptr, nullptr};
-  r->n_nodes = AI_NETWORK_N_NODES;
+  r->n_nodes = static_cast<ai_u32>(nodes);
   r->signature = 0;
 }
 
@@ -616,6 +689,8 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
   if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return err; }
   std::lock_guard<std::mutex> lk(g_dev_mu[dev & 63]);
   cudaDeviceProp prop{};
+  int prev_dev = -1;
+  if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
   if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
     set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
   }
@@ -630,8 +705,9 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
       (*n->h_err = 0, cudaHostGetDevicePointer(reinterpret_cast<void**>(&n->d_err), n->h_err, 0)) != cudaSuccess ||
       !make_lanes(n.get()) ||
       kernels_init() != cudaSuccess) {
-    if (n->h_err) cudaFreeHost(n->h_err);
     set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
+    n.reset();                                              // ~Network releases whatever was created, on this device
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);             // leave the caller's current device as it was
     err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
   }
   n->stream = n->own_stream;
@@ -650,17 +726,9 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   cudaStreamSynchronize(n->s_d2h);
   for (auto& kv : n->plans) {
     if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
-    if (g_active_fused[n->device & 63] == kv.second.get()) g_active_fused[n->device & 63] = nullptr;
   }
-  n->plans.clear();
-  if (n->h_err) cudaFreeHost(n->h_err);
-  if (n->h_small) cudaFreeHost(n->h_small);
-  cudaFree(n->d_trace); cudaFree(n->d_dets); cudaFree(n->d_counts); cudaFree(n->d_frames);
-  cudaEventDestroy(n->ev0); cudaEventDestroy(n->ev1); cudaStreamDestroy(n->own_stream); cudaStreamDestroy(n->s_h2d); cudaStreamDestroy(n->s_d2h);
-  for (int l = 0; l < Network::kLanes; ++l) { cudaStreamDestroy(n->lane[l]); cudaEventDestroy(n->ev_join[l]); }
-  cudaEventDestroy(n->ev_fork);
   { std::lock_guard<std::mutex> rk(g_mu); g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end()); }
-  delete n;
+  delete n;                                                 // ~Network
   return AI_HANDLE_NULL;
 }
 
@@ -698,7 +766,6 @@ AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params*
   cudaSetDevice(n->device);
   for (auto& kv : n->plans) {
     if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
-    if (g_active_fused[n->device & 63] == kv.second.get()) g_active_fused[n->device & 63] = nullptr;
   }
   n->plans.clear();
   if (!get_plan(n, n->H, n->W)) return false;
@@ -802,7 +869,7 @@ AI_API_ENTRY int32_t yf_b200_enqueue(ai_handle network, const void* d_in, void* 
   if (!d_in || (reinterpret_cast<uintptr_t>(d_in) & 15) || is_pageable_ptr(d_in) || is_foreign_device_ptr(n, d_in)) { set_text("enqueue: input must be 16-byte aligned device-accessible memory"); n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (!d_out || is_pageable_ptr(d_out) || is_foreign_device_ptr(n, d_out)) { set_text("enqueue: output must be device-accessible memory"); n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
-  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
   std::vector<DevChunk> ch;
   for (uint32_t done = 0; done < count; done += pd->cap)
     ch.push_back({static_cast<const int8_t*>(d_in) + done * in_sz, static_cast<int8_t*>(d_out) + done * out_sz, std::min<uint32_t>(pd->cap, count - done)});
@@ -816,7 +883,7 @@ AI_API_ENTRY int32_t yf_b200_enqueue_batches(ai_handle network, const void* cons
   if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
   if (!d_in || !d_out || !counts) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
-  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
   std::vector<DevChunk> ch;
   uint64_t total = 0;
   for (uint32_t b = 0; b < n_batches; ++b) {
@@ -838,10 +905,13 @@ AI_API_ENTRY int32_t yf_b200_submit(ai_handle network, const void* in_host, void
   if (!in_host || is_device_ptr(in_host)) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (!out_host || is_device_ptr(out_host)) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
-  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
   for (uint32_t done = 0; done < count; done += pd->cap) {
     const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
-    if (!ring_submit(n, pd, static_cast<const int8_t*>(in_host) + done * in_sz, static_cast<int8_t*>(out_host) + done * out_sz, nb, nullptr)) return -1;
+    if (!ring_submit(n, pd, static_cast<const int8_t*>(in_host) + done * in_sz, static_cast<int8_t*>(out_host) + done * out_sz, nb, nullptr)) {
+      ring_drain(n, pd);                                    // drain what was queued: nothing may land in the caller's buffers later
+      return -1;
+    }
   }
   n->images += count;
   return static_cast<int32_t>(count);
@@ -865,7 +935,7 @@ AI_API_ENTRY int32_t yf_b200_decode(ai_handle network, const void* heads, uint32
   if (!heads || !dets || !counts || !max_det) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (count == 0) return 0;
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
-  const size_t hsz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const size_t hsz = head_bytes(pd);
   int32_t total = 0;
   for (uint32_t done = 0; done < count; done += pd->cap) {
     const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
@@ -889,7 +959,7 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
   if (!in || !dets || !counts || !max_det) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (count == 0) return 0;
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
-  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, hsz = static_cast<size_t>(pd->plan.GH) * pd->plan.GW * 18;
+  const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, hsz = head_bytes(pd);
   const bool in_dev = is_device_ptr(in);
   int32_t total = 0;
   if (in_dev && !heads_out && count > pd->cap && uses_fused(n, pd) && !(reinterpret_cast<uintptr_t>(in) & 15)) {
@@ -904,12 +974,9 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
       const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
       const int l = static_cast<int>(ci % Network::kLanes);
       int8_t* heads = pd->r_head[l];                           // ring slots 0..3 double as the lanes' head buffers
-      if (!run_steps(n, pd, static_cast<const int8_t*>(in) + done * in_sz, heads, nb, n->lane[l])) return -1;
+      if (!run_steps(n, pd, static_cast<const int8_t*>(in) + done * in_sz, heads, nb, n->lane[l], true)) return -1;
       DecodeArgs a{};
-      a.head = heads; a.n_img = static_cast<int>(nb); a.gh = pd->plan.GH; a.gw = pd->plan.GW;
-      a.scale = pd->plan.out_scale; a.zp = pd->plan.out_zp;
-      a.conf_thr = conf_thr; a.iou_thr = iou_thr; a.plus_one = (flags & YF_B200_NMS_PLUS_ONE) ? 1 : 0;
-      a.dets = n->d_dets + static_cast<size_t>(done) * max_det * 5; a.counts = n->d_counts + done; a.max_det = static_cast<int>(max_det);
+      if (!fill_decode_args(n, pd, &a, heads, nb, conf_thr, iou_thr, flags, n->d_dets + static_cast<size_t>(done) * max_det * 5, n->d_counts + done, max_det)) return -1;
       if (!cuda_ok(n, launch_decode_nms(a, n->lane[l]), "decode_nms")) return -1;
       ++n->launches;
     }
@@ -941,6 +1008,17 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
     total += r;
   }
   return total;
+}
+
+AI_API_ENTRY int32_t yf_b200_set_decode_params(ai_handle network, const float* anchors6, float stride) {
+  YF_NET_OR_FAIL(n, network)
+  if (anchors6) for (int i = 0; i < 6; ++i) {
+    if (!(anchors6[i] > 0.f)) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_OUT_OF_RANGE); return -1; }
+    n->anchors[i] = anchors6[i];
+  }
+  if (stride < 0.f) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_OUT_OF_RANGE); return -1; }
+  n->stride = stride;
+  return 0;
 }
 
 AI_API_ENTRY int32_t yf_b200_preprocess_rgb565(ai_handle network, const void* frames, void* out, uint32_t count) {
@@ -1144,7 +1222,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
   kv("in_off", F.in_off); kv("in_bytes", F.in_bytes); kv("arena_off", F.arena_off); kv("arena_bytes", F.arena_bytes);
   kv("slot_off", F.slot_off); kv("slot_bytes", F.slot_bytes); kv("smem_bytes", F.smem_bytes); kv("head_bytes", F.head_bytes);
   kv("warpgroups", kFusedWarpgroups); kv("tmem_cols", kFusedTmemCols); kv("param_slots", kFusedParamSlots); kv("desc_off", F.desc_off);
-  kv("in_pf_phase", F.in_pf_phase);
+  kv("in_pf_phase", F.in_pf_phase); kv("split", F.split); kv("smem_bytes_spec", F.smem_bytes_spec); kv("spec", fused_spec_matches(F) ? 1 : 0);
   j += "\"phases\":[";
   for (size_t i = 0; i < F.phases.size(); ++i) {
     const FusedPhase& p = F.phases[i];
@@ -1156,6 +1234,8 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
     kv("to_global", p.to_global); kv("param_off", p.param_off); kv("param_bytes", p.param_bytes); kv("w_off", p.w_off); kv("lut_off", p.lut_off);
     kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("epi_off", p.epi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw); kv("in_wp", p.in_wp); kv("out_wp", p.out_wp); kv("out_zp", p.out_zp);
     kv("in_ws", p.in_ws); kv("out_ws", p.out_ws); kv("scratch_ws", p.scratch_ws); kv("tpg", p.tpg); kv("ntiles", p.ntiles);
+    kv("pair", p.pair); kv("sep_y", p.sep_y); kv("rows_a", p.rows_a); kv("row_b0", p.row_b0); kv("rows_single", p.rows_single);
+    kv("out_pair_shift", p.out_pair_shift); kv("grp_warps", p.grp_warps); kv("grp_warps_single", p.grp_warps_single);
     j += "\"add\":[" + std::to_string(p.add.enabled) + "," + std::to_string(p.add.zp1) + "," + std::to_string(p.add.zp2) + "," + std::to_string(p.add.zp_out) + "," +
          std::to_string(p.add.m1) + "," + std::to_string(p.add.m2) + "," + std::to_string(p.add.mo) + "," + std::to_string(p.add.s1) + "," +
          std::to_string(p.add.s2) + "," + std::to_string(p.add.so) + "]";

@@ -1,28 +1,38 @@
 // yf_fused.cu -- the whole yoloface int8 network as ONE persistent sm_100a kernel.
 //
-// One CTA (256 threads, three CTAs per SM) takes one image at a time through all 26 fused steps
-// (SURVEY.md 8a rows a2-a11).  Activations never leave the SM: MMA operands sit in shared memory in
-// chunk-planar form [C/16][H*W][16 B], which is directly the canonical no-swizzle K-major UMMA operand
-// layout, so every CONV_2D is  tcgen05.mma.kind::i8 (smem x smem -> TMEM)  on the data where the
-// previous phase left it; tensors only the depthwise / pool phases read are word-planar
-// [C/4][cells][4 B] with a zero-point border.  Per-phase parameters (packed weights, 256-entry
-// tables, requant constants) stream through four smem slots with cp.async.bulk (TMA engine), up to
-// three phases ahead; the next image is prefetched the same way.  HBM traffic per image is the I/O
-// floor: 9,408 B in + 882 B out.  75 KB smem, 80 registers, 128 TMEM columns per CTA.
+// One CTA (256 threads, three CTAs per SM) takes its images through all 26 fused steps.
+// Activations never leave the SM: MMA operands sit in shared memory in chunk-planar form [C/16][rows][16 B], which is
+// directly the canonical no-swizzle K-major UMMA operand layout, so every CONV_2D is  tcgen05.mma.kind::i8
+// (smem x smem -> TMEM)  on the data where the previous phase left it; tensors only the depthwise / pool phases read
+// are word-planar [C/4][cells][4 B] with a zero-point border.  Per-phase parameters (packed weights, 256-entry tables,
+// requant constants) stream through three smem slots with cp.async.bulk (TMA engine), two phases ahead; the next
+// image is prefetched the same way.  HBM traffic per image is the I/O floor: 9,408 B in + 882 B out.
 //
-//   conv phases   the last warp (no accumulator rows of its own in the 7x7 / 14x14 layers) issues the MMAs of a tile
-//                 group convergently -- one elect.sync lane, warp-uniform descriptors -- (all 128-pixel tiles whose
-//                 accumulators fit the CTA's 128 TMEM columns; the 28x28x18 layer takes two groups), commits once,
-//                 polls the accumulator mbarrier alone and releases the row-owning warps through a named
-//                 hardware barrier; those split the (tile, 16-channel) units: tcgen05.ld -> TFLite requant
-//                 -> table / ADD -> st.shared.  Its lane 0 refills the parameter slots meanwhile.
+// IMAGE PAIRS.  The "front" phases (56x56 -> 28x28 -> 14x14 stages, up to and including the pool / strided depthwise
+// that produce the 7x7 tensors) run per image; the "back" phases (the twelve 7x7 layers, where one image fills only 49
+// of an MMA tile's 128 rows) run ONCE for two images stacked into a tall 16x7 image: rows 0-6 image A, rows 7-8
+// separators, rows 9-15 image B -- 112 rows of one tile.  The separator rows are the shared zero-point border of A's
+// bottom and B's top in the bordered (depthwise-input) buffers, and carry don't-care values elsewhere.
+//
+// TWO KERNELS, ONE BODY.  yoloface_fused_kernel reads its phase descriptors from shared memory (any model /
+// resolution the planner accepts).  yoloface_fused_spec_kernel is the same body instantiated per phase with the
+// descriptors of the deployed model at 56x56 as compile-time constants (csrc/build/yf_fused_spec.inc, written at build
+// time by yf_gen_spec from the planner's own output -- the role of X-CUBE-AI's code generator, network.c): addresses,
+// trip counts, divisions and the per-layer branches fold away, and the 6 KB of descriptors leave shared memory, which
+// is what lets the pair buffers fit at three CTAs per SM.  The host picks it when the plan matches the table word for word.
+//
+//   conv phases   the last warp issues the MMAs of a tile group convergently -- one elect.sync lane, warp-uniform
+//                 descriptors -- commits once, polls the accumulator mbarrier alone and releases the row-owning warps
+//                 through a named hardware barrier; those split the (tile, 16-channel) units: tcgen05.ld -> TFLite
+//                 requant -> table / ADD -> st.shared.  Its lane 0 refills the parameter slots meanwhile.
 //   first conv    implicit GEMM: all threads build A tiles (3 x 16-B chunks per pixel, K laid out
 //                 as [ky][9 taps + 7 don't-care bytes] against zero weights), two tiles per round
 //   depthwise     CUDA cores: one thread = one 4-channel word, fixed per thread (requant constants in
 //                 registers, one-hot weight words re-read from the slot and shared by the two pixels of a
 //                 loop step), dp4a, zero-point-bordered input so no bounds checks
-//   max-pool      separable (row maxima to scratch, then columns), VIMNMX3.S16x2 on unpacked lanes
+//   max-pool      separable (row maxima to scratch, then columns), VIMNMX3.U16x2 on masked even / odd bytes
 #include <cstdlib>
+#include <cstring>
 
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
@@ -30,21 +40,13 @@
 
 namespace yf {
 
-__constant__ FusedPhase c_fphase[kFusedMaxPhases];
-
-cudaError_t upload_fused_tables(const EpiCh*, int, const FusedPhase* phases, int nph, cudaStream_t s) {
-  if (nph > kFusedMaxPhases) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_fphase, phases, sizeof(FusedPhase) * static_cast<size_t>(nph), 0, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(s);
-}
-
 struct FusedArgs {
   const int8_t* in; int8_t* out; const uint8_t* params;
-  int n_img, nphases;
+  const FusedPhase* phases;   // device copy of the descriptors (generic kernel: copied to smem; both: parameter block table)
+  int n_img, nphases, split;
   int in_off, in_bytes, slot_off, slot_bytes, head_bytes, desc_off, bars_off, in_pf_phase;
   int* err;
-  long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first image
+  long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first images
   int trace_phase;            // phase whose inner stamps (trace[96..127]) are recorded
 };
 #ifdef YF_TRACE
@@ -53,8 +55,9 @@ struct FusedArgs {
 #define YF_STAMP(tp, i) do { } while (0)
 #endif
 
-constexpr int kFusedThreads = kFusedWorkerThreads;       // 8 warps; thread 0 doubles as MMA issuer / prefetcher
+constexpr int kFusedThreads = kFusedWorkerThreads;       // 8 warps; the last one doubles as MMA issuer / prefetcher
 constexpr int kFusedCtasPerSm = 3;
+constexpr int kCtrlWarp = kFusedCtrlWarp;                // TMEM lane quarter 3 of warpgroup 1
 
 // UMMA smem descriptor: template low word (LBO) + start address; high word: SBO = 128 B, version 1, no swizzle
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
@@ -63,6 +66,62 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
 
 // x / d for the small non-negative x of this kernel: rcp = ceil(2^20 / d), exactness checked on the host (build_fused)
 __device__ __forceinline__ int small_div(int x, uint32_t rcp) { return static_cast<int>((static_cast<uint32_t>(x) * rcp) >> 20); }
+
+// named barrier 1: the control warp (the only one polling the accumulator mbarrier) releases the epilogue warps
+__device__ __forceinline__ void epi_bar_sync(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
+__device__ __forceinline__ void epi_bar_arrive(int threads) { asm volatile("bar.arrive 1, %0;" ::"r"(threads) : "memory"); }
+
+// ---- per-thread state shared by every phase --------------------------------------------------------------------
+struct Cx {
+  uint8_t* smem;
+  uint32_t smem_base, in_full, par_full, mma_done, tmem_base;
+  int tid, warp, lane;
+  bool ctrl, lead, ok;
+  uint32_t use0, use1, in_uses;                // completed waits on mma_done[0/1], in_full
+  // lead thread: parameter blocks go round the slots; block j may be requested once block j - kFusedParamSlots (the
+  // slot's previous tenant) belongs to a finished phase, i.e. j < pc + kFusedParamSlots
+  uint32_t pc_next, total_pc;
+  int pnext, knext, my_images;
+  const int2* pb;                              // smem: {param_off, param_bytes} per phase
+};
+// what changes from one execution of a phase to the next
+struct Rt {
+  uint32_t pc;                                 // running count of executed phases (parameter slot / barrier parity)
+  int out_shift;                               // front phases feeding the back: byte offset of this image's rows in the tall buffer
+  bool pair_b;                                 // back phases: the pair holds a second image
+  int8_t* ghead_a; int8_t* ghead_b;            // back phases: where the two heads go
+  const int8_t* next_in;                       // front phases: next image of this CTA (input prefetch), or null
+};
+
+__device__ __forceinline__ void wait_bar(Cx& c, const FusedArgs& a, uint32_t bar, uint32_t parity, int code) {
+  if (c.ok && !mbar_wait(bar, parity)) { atomicCAS(a.err, 0, code); c.ok = false; }
+}
+// phase order of one CTA: front(image 0), front(image 1), back(pair), front(image 2), ...
+__device__ __forceinline__ void advance_phase(int& p, int& k, int split, int nph, int my_images) {
+  if (p == split - 1 && split < nph) {
+    if ((k & 1) || k == my_images - 1) p = split; else { p = 0; ++k; }
+  } else if (p == nph - 1) { p = 0; ++k; }
+  else ++p;
+}
+__device__ __forceinline__ void refill(Cx& c, const FusedArgs& a, uint32_t pc_now) {
+#pragma unroll 1
+  while (c.pc_next < c.total_pc && c.pc_next < pc_now + kFusedParamSlots) {
+    const int2 e = c.pb[c.pnext];
+    const uint32_t s = c.pc_next % kFusedParamSlots, bar = c.par_full + 8 * s;
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(e.y));
+    bulk_load_1d(c.smem_base + a.slot_off + s * a.slot_bytes, a.params + e.x, static_cast<uint32_t>(e.y), bar);
+    ++c.pc_next;
+    advance_phase(c.pnext, c.knext, a.split, a.nphases, c.my_images);
+  }
+}
+// lead thread, off the critical path: refill the slot the previous phase released, prefetch the next image
+__device__ __forceinline__ void housekeeping(Cx& c, const FusedArgs& a, const Rt& rt, bool prefetch_image) {
+  refill(c, a, rt.pc);
+  if (prefetch_image && rt.next_in) {                        // the image buffer is free after phase 0
+    mbar_arrive_expect_tx(c.in_full, static_cast<uint32_t>(a.in_bytes));
+    bulk_load_1d(c.smem_base + a.in_off, rt.next_in, static_cast<uint32_t>(a.in_bytes), c.in_full);
+  }
+}
 
 // border cells of a padded output buffer <- the tensor's zero point (run by the workers while the MMAs are in flight)
 __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem, int tid) {
@@ -81,29 +140,19 @@ __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem,
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
-                                          int row, int g, int8_t* ghead) {
+                                          int row, int g, int rows, const Rt& rt) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   tmem_ld_wait();
-  if (row >= ph.rows_out) return;
+  if (row >= rows) return;
   const int nreal = ph.cout - g * 16;                        // real channels in this chunk (> 0)
   const int nwords = nreal >= 13 ? 4 : (nreal + 3) >> 2;     // warp-uniform
   const EpiChF* ek = epi + g * 16;                           // shared memory (broadcast reads)
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (ph.has_lut) {
-    switch (nwords) {
-      case 1: requant_words<1, true>(v, ek, lut, w); break;
-      case 2: requant_words<2, true>(v, ek, lut, w); break;
-      case 3: requant_words<3, true>(v, ek, lut, w); break;
-      default: requant_words<4, true>(v, ek, lut, w); break;
-    }
+    requant_chunk<true>(v, ek, lut, nwords, w);
   } else {
-    switch (nwords) {
-      case 1: requant_words<1, false>(v, ek, lut, w); break;
-      case 2: requant_words<2, false>(v, ek, lut, w); break;
-      case 3: requant_words<3, false>(v, ek, lut, w); break;
-      default: requant_words<4, false>(v, ek, lut, w); break;
-    }
+    requant_chunk<false>(v, ek, lut, nwords, w);
     if (ph.add_off >= 0) {
       const uint4 sk = *reinterpret_cast<const uint4*>(smem + ph.add_off + g * ph.add_cs + row * 16);
       w[0] = add_word(sk.x, w[0], ph.add);
@@ -113,44 +162,51 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
     }
   }
   if (ph.to_global) {                                        // dense [pixels][cout] int8 head, 2-byte aligned rows
-    uint16_t* o = reinterpret_cast<uint16_t*>(ghead + row * ph.cout + g * 16);
+    int8_t* gh = rt.ghead_a; int r = row;
+    if (ph.pair) {                                           // tall image: rows [0, rows_a) image A, [row_b0, ..) image B
+      if (row >= ph.row_b0) { gh = rt.ghead_b; r = row - ph.row_b0; }
+      else if (row >= ph.rows_a) return;                     // separator rows
+    }
+    uint16_t* o = reinterpret_cast<uint16_t*>(gh + r * ph.cout + g * 16);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
   } else if (ph.out_wp) {                                    // word-planar, zero-point-bordered: depthwise / pool consumers
     const int y = small_div(row, ph.rcp_wout);
+    if (ph.pair && static_cast<unsigned>(y - ph.sep_y) < 2u) {   // separator rows ARE border: A's bottom, B's top
+      const uint32_t z = static_cast<uint32_t>(ph.out_zp & 0xff) * 0x01010101u;
+      w[0] = z; w[1] = z; w[2] = z; w[3] = z;
+    }
     uint8_t* o = smem + ph.out_off + g * 4 * ph.out_ws + ((y + 1) * ph.out_wp + (row - y * ph.Wout) + 1) * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (j < nwords) *reinterpret_cast<uint32_t*>(o + j * ph.out_ws) = w[j];
   } else {
-    *reinterpret_cast<uint4*>(smem + ph.out_off + g * ph.out_cs + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(smem + ph.out_off + rt.out_shift + g * ph.out_cs + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
 // all (tile, chunk) units of a conv phase, split across the worker warps (no divisions)
 // (tiles t0 .. t0+nt-1 are the group whose accumulators sit in TMEM, tile t at column (t - t0) * npad)
-__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, uint32_t tmem_base,
-                                              int warp, int lane, int8_t* ghead, int t0, int nt) {
-  const int q = warp & 3, chunks = ph.chunks_out;
+__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt) {
+  const int q = c.warp & 3, chunks = ph.chunks_out;
   const uint8_t* lut = slot + ph.lut_off;
   const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
-  const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const uint32_t tq = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   if (nt >= kFusedWarpgroups) {
     // several tiles: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
-    for (int t = warp >> 2; t < nt; t += kFusedWarpgroups) {
+    for (int t = c.warp >> 2; t < nt; t += kFusedWarpgroups) {
       const int row0 = (t0 + t) * 128 + q * 32;
-      if (row0 >= ph.rows_out) continue;                     // this warp's 32 rows are all padding
-      for (int g = 0; g < chunks; ++g) conv_unit(ph, smem, lut, epi, tq + t * ph.npad + g * 16, row0 + lane, g, ghead);
+      if (row0 >= rows) continue;                            // this warp's 32 rows are all padding
+      for (int g = 0; g < chunks; ++g) conv_unit(ph, c.smem, lut, epi, tq + t * ph.npad + g * 16, row0 + c.lane, g, rows, rt);
     }
   } else {
     // a single tile: split its chunks across the warpgroups
     const int row0 = t0 * 128 + q * 32;
-    if (row0 < ph.rows_out)
-      for (int g = warp >> 2; g < chunks; g += kFusedWarpgroups) conv_unit(ph, smem, lut, epi, tq + g * 16, row0 + lane, g, ghead);
+    if (row0 < rows)
+      for (int g = c.warp >> 2; g < chunks; g += kFusedWarpgroups) conv_unit(ph, c.smem, lut, epi, tq + g * 16, row0 + c.lane, g, rows, rt);
   }
 }
-
 
 // DEPTHWISE_CONV_2D 3x3
 // requantise the four channels of one word and store it
@@ -165,7 +221,7 @@ __device__ __forceinline__ void dw_store(const int32_t (&acc)[4], const int32_t 
   *reinterpret_cast<uint32_t*>(o) = ow;
 }
 
-__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, long long* tp) {
+__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int rows, int out_shift, long long* tp) {
   const int nw = ph.nw, per = ph.per;
   YF_STAMP(tp, 0);
   if (tid >= per * nw) return;
@@ -188,12 +244,12 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
     k_c2p[0] = c.x; k_c2p[1] = c.y; k_c2p[2] = c.z; k_c2p[3] = c.w;
     k_e[0] = e.x; k_e[1] = e.y; k_e[2] = e.z; k_e[3] = e.w;
   }
-  const int WP = ph.in_wp, Wout = ph.Wout, stride = ph.stride, rows = ph.rows_out;
+  const int WP = ph.in_wp, Wout = ph.Wout, stride = ph.stride;
   const int row4 = WP * 4, dy = ph.dy, dx = ph.dx;
   // input is stored with a one-cell zero-point border: tap (ky,kx) of output (oy,ox) is padded cell
   // (oy*stride - pad_t + 1 + ky, ox*stride - pad_l + 1 + kx), always inside the buffer -> no bounds checks
   const uint8_t* ib = smem + ph.in_off + wd * ph.in_ws + ((1 - ph.pad_t) * WP + (1 - ph.pad_l)) * 4;
-  uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
+  uint8_t* ob = smem + ph.out_off + out_shift + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
   const bool has_lut = ph.has_lut != 0;
   const int oy = small_div(pix, ph.rcp_wout);
   int ox = pix - oy * Wout;
@@ -253,19 +309,21 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   YF_STAMP(tp, 8);
 }
 
-// signed bytes (b0,b2) / (b1,b3) of a word as two 16-bit lanes each
-__device__ __forceinline__ uint32_t unpack_even(uint32_t x) { return __byte_perm(x, 0u, 0xA280u); }
-__device__ __forceinline__ uint32_t unpack_odd(uint32_t x) { return __byte_perm(x, 0u, 0xB391u); }
-__device__ __forceinline__ uint32_t repack(uint32_t ev, uint32_t od) { return __byte_perm(ev, od, 0x6240u); }
+// Signed byte maximum on the packed 16-bit min/max unit without unpacking: x ^ 0x80808080 orders signed bytes as
+// unsigned ones; the even bytes (x & 0x00ff00ff) and the odd bytes LEFT IN PLACE (x & 0xff00ff00, i.e. byte * 256) are
+// two vectors of unsigned 16-bit lanes whose maxima are the byte maxima.  One LOP3 each instead of a PRMT (a third of
+// the LOP3 rate on this part).
+__device__ __forceinline__ uint32_t ev_of(uint32_t x) { return (x ^ 0x80808080u) & 0x00ff00ffu; }
+__device__ __forceinline__ uint32_t od_of(uint32_t x) { return (x ^ 0x80808080u) & 0xff00ff00u; }
+__device__ __forceinline__ uint32_t pool_join(uint32_t ev, uint32_t od) { return (ev | od) ^ 0x80808080u; }
 
 // MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only
-__device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid) {
+__device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
   const int nw = ph.nw, per = ph.per;
   const bool active = tid < per * nw;
   const int it0 = small_div(tid, ph.rcp_nw), wd = tid - it0 * nw;
   const int Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout, k = ph.ksize, stride = ph.stride;
   const int sws = ph.scratch_ws;                              // word-plane stride of the row-maxima scratch
-  const uint32_t neg = 0x80808080u;
   const int dy = ph.dy, dx = ph.dx;
   if (active) {                                               // pass 1: horizontal window of every input row
     const uint8_t* ib = smem + ph.in_off + wd * ph.in_ws;
@@ -275,19 +333,19 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
     int y = small_div(it, ph.rcp_wout), ox = it - y * Wout;
     for (; it < total; it += per) {
       const int x0 = max(0, ox * stride - ph.pad_l), x1 = min(Win, ox * stride - ph.pad_l + k);
-      uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
+      uint32_t ev = 0u, od = 0u;                              // = the biased form of -128
       const uint8_t* p = ib + ((y + 1) * ph.in_wp + x0 + 1) * 4;
       int n = x1 - x0;
       for (; n >= 2; n -= 2, p += 8) {
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + 4);
-        ev = __vimax3_s16x2(ev, unpack_even(a), unpack_even(b));
-        od = __vimax3_s16x2(od, unpack_odd(a), unpack_odd(b));
+        ev = __vimax3_u16x2(ev, ev_of(a), ev_of(b));
+        od = __vimax3_u16x2(od, od_of(a), od_of(b));
       }
       if (n) {
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p);
-        ev = __vmaxs2(ev, unpack_even(a)); od = __vmaxs2(od, unpack_odd(a));
+        ev = __vmaxu2(ev, ev_of(a)); od = __vmaxu2(od, od_of(a));
       }
-      *reinterpret_cast<uint32_t*>(sb + it * 4) = repack(ev, od);
+      *reinterpret_cast<uint32_t*>(sb + it * 4) = ev | od;    // row maxima stay in the biased (unsigned) form
       ox += dx; y += dy;
       if (ox >= Wout) { ox -= Wout; ++y; }
     }
@@ -295,31 +353,32 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
   __syncthreads();
   if (active) {                                               // pass 2: vertical window over the row maxima
     const uint8_t* sb = smem + ph.scratch_off + wd * sws;
-    uint8_t* ob = smem + ph.out_off + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
+    uint8_t* ob = smem + ph.out_off + out_shift + (wd >> 2) * ph.out_cs + (wd & 3) * 4;
     const uint8_t* lut = slot + ph.lut_off;
     const int total = Hout * Wout;
     int it = it0;
     int oy = small_div(it, ph.rcp_wout), ox = it - oy * Wout;
     for (; it < total; it += per) {
       const int y0 = max(0, oy * stride - ph.pad_t), y1 = min(Hin, oy * stride - ph.pad_t + k);
-      uint32_t ev = unpack_even(neg), od = unpack_odd(neg);
+      uint32_t ev = 0u, od = 0u;
       const uint8_t* p = sb + (y0 * Wout + ox) * 4;
       const int step = Wout * 4;
       int n = y1 - y0;
       for (; n >= 2; n -= 2, p += 2 * step) {
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p), b = *reinterpret_cast<const uint32_t*>(p + step);
-        ev = __vimax3_s16x2(ev, unpack_even(a), unpack_even(b));
-        od = __vimax3_s16x2(od, unpack_odd(a), unpack_odd(b));
+        ev = __vimax3_u16x2(ev, a & 0x00ff00ffu, b & 0x00ff00ffu);
+        od = __vimax3_u16x2(od, a & 0xff00ff00u, b & 0xff00ff00u);
       }
       if (n) {
         const uint32_t a = *reinterpret_cast<const uint32_t*>(p);
-        ev = __vmaxs2(ev, unpack_even(a)); od = __vmaxs2(od, unpack_odd(a));
+        ev = __vmaxu2(ev, a & 0x00ff00ffu); od = __vmaxu2(od, a & 0xff00ff00u);
       }
-      uint32_t m = repack(ev, od);
+      uint32_t m = ev | od;                                   // biased bytes = table indices
       if (ph.has_lut) {
-        m ^= neg;                                             // int8 -> table index
         m = static_cast<uint32_t>(lut[m & 0xff]) | (static_cast<uint32_t>(lut[(m >> 8) & 0xff]) << 8) |
             (static_cast<uint32_t>(lut[(m >> 16) & 0xff]) << 16) | (static_cast<uint32_t>(lut[m >> 24]) << 24);
+      } else {
+        m ^= 0x80808080u;
       }
       *reinterpret_cast<uint32_t*>(ob + it * 16) = m;
       ox += dx; oy += dy;
@@ -354,226 +413,289 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
   }
 }
 
-constexpr int kCtrlWarp = kFusedCtrlWarp;                // TMEM lane quarter 3 of warpgroup 1: no rows in the 7x7 and 14x14 epilogues
-// named barrier 1: the control warp (the only one polling the accumulator mbarrier) releases the epilogue warps
-__device__ __forceinline__ void epi_bar_sync(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
-__device__ __forceinline__ void epi_bar_arrive(int threads) { asm volatile("bar.arrive 1, %0;" ::"r"(threads) : "memory"); }
+// ---- one phase ------------------------------------------------------------------------------------------------------
+// `ph` is a shared-memory descriptor (generic kernel) or a bundle of compile-time constants (specialised kernel);
+// p = its index; everything that varies between executions is in rt.
+__device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& c, const FusedArgs& a, const Rt& rt, long long* tp) {
+  uint8_t* const smem = c.smem;
+  const int tid = c.tid, warp = c.warp;
+  const int kind = ph.kind, ntiles = ph.ntiles, tpg = ph.tpg;
+  // rows that carry data: a pair phase holding only image A stops after the separator rows
+  const int rows = ph.pair ? (rt.pair_b ? ph.rows_out : ph.rows_single) : ph.rows_out;
+  const uint32_t s_idx = rt.pc % kFusedParamSlots;
+  const uint32_t par_bar = c.par_full + 8 * s_idx, par_parity = (rt.pc / kFusedParamSlots) & 1;
+  const uint8_t* slot = smem + a.slot_off + s_idx * a.slot_bytes;
+  const bool pf_here = p == a.in_pf_phase;
+  if (kind == STEP_CONV1X1) {
+    uint32_t grp = (ph.pair && !rt.pair_b) ? ph.grp_warps_single : ph.grp_warps;
+    const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off, sA = c.smem_base + ph.in_off;
+    const bool ctrl_busy = fused_has_rows(kCtrlWarp, 0, min(tpg, ntiles), rows, ph.chunks_out);
+    for (int t0 = 0; t0 < ntiles; t0 += tpg, grp >>= 8) {
+      const int nt = min(tpg, ntiles - t0);
+      // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 14x14 layers)
+      // never touch TMEM: they go straight to the end-of-phase barrier
+      const bool has_rows = fused_has_rows(warp, t0, nt, rows, ph.chunks_out);
+      const int meet = static_cast<int>(grp & 0xffu) * 32;   // threads at the release barrier: row owners + control warp
+      if (t0 == 0 && ph.out_wp && !c.ctrl) fill_border(ph, smem, tid);
+      if (c.ctrl) {                                          // every tile of the group, one commit
+        if (t0 == 0) wait_bar(c, a, par_bar, par_parity, 302);   // the weights
+        tc_fence_after();
+        const bool el = elect_one();
+        for (int t = 0; t < nt; ++t)
+          for (int k = 0; k < ph.nk; ++k)
+            if (el) mma_i8(c.tmem_base + t * ph.npad, mk_desc(ph.adesc_lo, sA + (t0 + t) * 2048 + k * 2 * ph.in_cs),
+                           mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16), static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
+        if (el) mma_commit(c.mma_done);
+        __syncwarp();
+        if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
+        // the control warp alone polls the accumulator barrier and then releases the row owners through a
+        // hardware barrier, where waiting costs no issue slots
+        wait_bar(c, a, c.mma_done, c.use0 & 1, 301);
+        tc_fence_before();
+        if (has_rows) epi_bar_sync(meet); else epi_bar_arrive(meet);
+        if (c.lead && t0 == 0 && !ctrl_busy) housekeeping(c, a, rt, pf_here);
+        __syncwarp();
+      } else if (has_rows) {
+        if (t0 == 0) wait_bar(c, a, par_bar, par_parity, 302);   // table and requant constants
+        epi_bar_sync(meet);
+      }
+      ++c.use0;
+      if (has_rows) {
+        tc_fence_after();
+        conv_epilogue(ph, c, slot, t0, nt, rows, rt);
+        tc_fence_before();
+      }
+      if (t0 + tpg < ntiles) __syncthreads();                // the next group overwrites these TMEM columns
+    }
+    if (c.lead && ctrl_busy) housekeeping(c, a, rt, pf_here);
+  } else if (kind == STEP_CONV_IM2COL) {
+    const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off;
+    if (ph.out_wp) fill_border(ph, smem, tid);
+    wait_bar(c, a, par_bar, par_parity, 302);
+    wait_bar(c, a, c.in_full, c.in_uses & 1, 303); ++c.in_uses;
+    const int rounds = (ntiles + 1) >> 1;
+    for (int r = 0; r < rounds; ++r) {
+      if (r >= 2) {                                          // the A stages of round r-2 must have been consumed
+        if (r & 1) { wait_bar(c, a, c.mma_done + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done, c.use0 & 1, 304); ++c.use0; }
+      }
+      im2col_build(ph, smem, tid, r);
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (c.ctrl) {
+        tc_fence_after();
+        const bool el = elect_one();
+        for (int h = 0; h < 2; ++h) {
+          const int tt = 2 * r + h;
+          if (tt >= ntiles) break;
+          const uint32_t sS = c.smem_base + ph.scratch_off + (tt & 3) * 6144;
+          for (int k = 0; k < 2; ++k)
+            if (el) mma_i8(c.tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
+                           static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
+        }
+        if (el) mma_commit(c.mma_done + 8 * (r & 1));
+        __syncwarp();
+      }
+    }
+    for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
+      if (r & 1) { wait_bar(c, a, c.mma_done + 8, c.use1 & 1, 305); ++c.use1; } else { wait_bar(c, a, c.mma_done, c.use0 & 1, 305); ++c.use0; }
+    }
+    tc_fence_after();
+    conv_epilogue(ph, c, slot, 0, ntiles, rows, rt);
+    tc_fence_before();
+    if (c.lead) housekeeping(c, a, rt, pf_here);
+  } else {
+    wait_bar(c, a, par_bar, par_parity, 302);
+    if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, (ph.pair && !rt.pair_b) ? ph.rows_a : ph.rows_out, rt.out_shift, tp);
+    else if (kind == STEP_MAXPOOL) pool_phase(ph, smem, slot, tid, rt.out_shift);
+    if (c.lead && c.pc_next <= rt.pc + 1) housekeeping(c, a, rt, pf_here);   // only when the next phase's block is not even requested yet
+  }
+  fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
+#ifdef YF_TRACE
+  if (tp) tp[10] = clock64();
+#endif
+  __syncthreads();
+#ifdef YF_TRACE
+  if (tp) tp[11] = clock64();
+#endif
+}
 
-__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  // mbarriers, as 32-bit shared-space addresses (8 bytes each): input image landed | [kFusedParamSlots] parameter slot
-  // landed | [2] accumulators ready (two used by the first conv's rounds)
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t in_full = smem_base + a.bars_off, par_full = in_full + 8, mma_done = par_full + 8 * kFusedParamSlots;
+// ---- prologue / epilogue shared by the two kernels ---------------------------------------------------------------
+__device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* smem) {
+  c.smem = smem; c.smem_base = smem_u32(smem);
+  c.in_full = c.smem_base + a.bars_off; c.par_full = c.in_full + 8; c.mma_done = c.par_full + 8 * kFusedParamSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // The last warp doubles as the control warp: it runs the MMA-issue loops convergently (one elected lane issues,
-  // operands stay warp-uniform) and its lane 0 issues every bulk copy.
-  const bool ctrl = warp == kCtrlWarp;
-  const bool lead = tid == kCtrlWarp * 32;
-
-  if (tid == 0) {
+  c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
+  c.ctrl = c.warp == kCtrlWarp; c.lead = c.tid == kCtrlWarp * 32; c.ok = true;
+  c.use0 = 0u; c.use1 = 0u; c.in_uses = 0u;
+  if (c.tid == 0) {
     for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
+  if (c.warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
+  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 64);           // parameter block table (<= kFusedMaxPhases entries)
+  for (int i = c.tid; i < a.nphases; i += kFusedThreads) pb[i] = make_int2(a.phases[i].param_off, a.phases[i].param_bytes);
+  c.pb = pb;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  {                                                           // phase descriptors: __constant__ -> smem, read with LDS from here on
-    const uint4* src = reinterpret_cast<const uint4*>(c_fphase);
-    uint4* dst = reinterpret_cast<uint4*>(smem + a.desc_off);
-    for (int i = tid; i < a.nphases * static_cast<int>(sizeof(FusedPhase) / 16); i += kFusedThreads) dst[i] = src[i];
-    __syncthreads();
+  c.tmem_base = *tmem_slot;
+  c.my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int nback = a.nphases - a.split;
+  c.total_pc = static_cast<uint32_t>(c.my_images * a.split + ((c.my_images + 1) >> 1) * nback);
+  c.pc_next = 0u; c.pnext = 0; c.knext = 0;
+  if (c.lead && c.my_images > 0) {
+    mbar_arrive_expect_tx(c.in_full, static_cast<uint32_t>(a.in_bytes));
+    bulk_load_1d(c.smem_base + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), c.in_full);
+    refill(c, a, 0u);
   }
-  const FusedPhase* s_ph = reinterpret_cast<const FusedPhase*>(smem + a.desc_off);
-  const uint32_t tmem_base = *tmem_slot;
-  uint32_t use0 = 0u, use1 = 0u, in_uses = 0u;              // completed waits on mma_done[0/1], in_full
-  bool ok = true;
-  const int nph = a.nphases;
-  const int my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const uint32_t total_pc = static_cast<uint32_t>(my_images) * static_cast<uint32_t>(nph);
-  auto wait_bar = [&](uint32_t bar, uint32_t parity, int code) {
-    if (ok && !mbar_wait(bar, parity)) { atomicCAS(a.err, 0, code); ok = false; }
-  };
-  // ---- lead thread: parameter blocks go round the slots; block j may be requested once block j - kFusedParamSlots
-  //      (the slot's previous tenant) belongs to a finished phase, i.e. j < pc + kFusedParamSlots
-  int pnext = 0;                                              // phase index of parameter block pc_next
-  uint32_t pc_next = 0;
-  auto refill = [&](uint32_t pc_now) {
-#pragma unroll 1
-    while (pc_next < total_pc && pc_next < pc_now + kFusedParamSlots) {
-      const FusedPhase& nx = s_ph[pnext];
-      const uint32_t bar = par_full + 8 * (pc_next % kFusedParamSlots);
-      mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nx.param_bytes));
-      bulk_load_1d(smem_base + a.slot_off + (pc_next % kFusedParamSlots) * a.slot_bytes, a.params + nx.param_off, static_cast<uint32_t>(nx.param_bytes), bar);
-      ++pc_next; if (++pnext == nph) pnext = 0;
-    }
-  };
-  if (lead && my_images > 0) {
-    mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(smem_base + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
-    refill(0);
-  }
-
-  uint32_t pc = 0;
-  for (int img = blockIdx.x; img < a.n_img; img += gridDim.x) {
-    int8_t* ghead = a.out + static_cast<long long>(img) * a.head_bytes;
-    for (int p = 0; p < nph; ++p, ++pc) {
-      const FusedPhase& ph = s_ph[p];
-      const int kind = ph.kind, ntiles = ph.ntiles, tpg = ph.tpg, rows_out = ph.rows_out;
-      // the fields the issue path needs, fetched by the control warp in one burst before the barrier wait below
-      int nk = 0, npad = 0, in_cs = 0;
-      uint32_t adesc_lo = 0, bdesc_lo = 0, idesc = 0, sW = 0, sA = 0;
-      if (ctrl) {
-        nk = ph.nk; npad = ph.npad; in_cs = ph.in_cs; adesc_lo = ph.adesc_lo; bdesc_lo = ph.bdesc_lo; idesc = static_cast<uint32_t>(ph.idesc);
-        sW = smem_base + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes + ph.w_off;
-        sA = smem_base + ph.in_off;
-      }
-      const bool ctrl_busy = rows_out > 224;                  // the control warp owns epilogue rows only in the 28x28 layers
-#ifdef YF_TRACE
-      const bool tr = a.trace && tid == 0 && blockIdx.x == 0 && pc < 2u * static_cast<uint32_t>(nph);
-      if (tr) a.trace[pc + pc / nph] = clock64();
-      long long* const tp = (tr && p == a.trace_phase && pc < static_cast<uint32_t>(nph)) ? a.trace + 96 : nullptr;
-#else
-      long long* const tp = nullptr;
-#endif
-      const uint32_t par_bar = par_full + 8 * (pc % kFusedParamSlots), par_parity = (pc / kFusedParamSlots) & 1;
-      const uint8_t* slot = smem + a.slot_off + (pc % kFusedParamSlots) * a.slot_bytes;
-      // lead thread, off the critical path: refill the slot the previous phase released, prefetch the next image
-      auto housekeeping = [&]() {
-        refill(pc);
-        if (p == a.in_pf_phase && img + static_cast<int>(gridDim.x) < a.n_img) {     // the image buffer is free after phase 0
-          mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(a.in_bytes));
-          bulk_load_1d(smem_base + a.in_off, a.in + static_cast<long long>(img + gridDim.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), in_full);
-        }
-      };
-      if (kind == STEP_CONV1X1) {
-        uint32_t grp = ph.grp_warps;
-        for (int t0 = 0; t0 < ntiles; t0 += tpg, grp >>= 8) {
-          const int nt = min(tpg, ntiles - t0);
-          // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 7x7 and 14x14 layers)
-          // never touch TMEM: they go straight to the end-of-phase barrier
-          const bool has_rows = fused_has_rows(warp, t0, nt, rows_out, ph.chunks_out);
-          const int meet = static_cast<int>(grp & 0xffu) * 32;   // threads at the release barrier: row owners + control warp
-          if (t0 == 0 && ph.out_wp && !ctrl) fill_border(ph, smem, tid);
-          if (ctrl) {                                         // every tile of the group, one commit
-            if (t0 == 0) wait_bar(par_bar, par_parity, 302);  // the weights
-            tc_fence_after();
-            const bool el = elect_one();
-            for (int t = 0; t < nt; ++t)
-              for (int k = 0; k < nk; ++k)
-                if (el) mma_i8(tmem_base + t * npad, mk_desc(adesc_lo, sA + (t0 + t) * 2048 + k * 2 * in_cs),
-                               mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
-            if (el) mma_commit(mma_done);
-            __syncwarp();
-            if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
-            // the control warp alone polls the accumulator barrier and then releases the row owners through a
-            // hardware barrier, where waiting costs no issue slots
-            wait_bar(mma_done, use0 & 1, 301);
-            tc_fence_before();
-            if (has_rows) epi_bar_sync(meet); else epi_bar_arrive(meet);
-            if (lead && t0 == 0 && !ctrl_busy) housekeeping();
-            __syncwarp();
-          } else if (has_rows) {
-            if (t0 == 0) wait_bar(par_bar, par_parity, 302);  // table and requant constants
-            epi_bar_sync(meet);
-          }
-          ++use0;
-          if (has_rows) {
-            tc_fence_after();
-            conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, t0, nt);
-            tc_fence_before();
-          }
-          if (t0 + tpg < ntiles) __syncthreads();             // the next group overwrites these TMEM columns
-        }
-        if (lead && ctrl_busy) housekeeping();
-      } else if (kind == STEP_CONV_IM2COL) {
-        if (ph.out_wp) fill_border(ph, smem, tid);
-        wait_bar(par_bar, par_parity, 302);
-        wait_bar(in_full, in_uses & 1, 303); ++in_uses;
-        const int rounds = (ntiles + 1) >> 1;
-        for (int r = 0; r < rounds; ++r) {
-          if (r >= 2) {                                       // the A stages of round r-2 must have been consumed
-            if (r & 1) { wait_bar(mma_done + 8, use1 & 1, 304); ++use1; } else { wait_bar(mma_done, use0 & 1, 304); ++use0; }
-          }
-          im2col_build(ph, smem, tid, r);
-          fence_proxy_async_smem();
-          __syncthreads();
-          if (ctrl) {
-            tc_fence_after();
-            const bool el = elect_one();
-            for (int h = 0; h < 2; ++h) {
-              const int tt = 2 * r + h;
-              if (tt >= ntiles) break;
-              const uint32_t sS = smem_base + ph.scratch_off + (tt & 3) * 6144;
-              for (int k = 0; k < 2; ++k)
-                if (el) mma_i8(tmem_base + tt * npad, mk_desc(adesc_lo, sS + k * 4096), mk_desc(bdesc_lo, sW + k * 2 * npad * 16), idesc, k > 0 ? 1u : 0u);
-            }
-            if (el) mma_commit(mma_done + 8 * (r & 1));
-            __syncwarp();
-          }
-        }
-        for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
-          if (r & 1) { wait_bar(mma_done + 8, use1 & 1, 305); ++use1; } else { wait_bar(mma_done, use0 & 1, 305); ++use0; }
-        }
-        tc_fence_after();
-        conv_epilogue(ph, smem, slot, tmem_base, warp, lane, ghead, 0, ntiles);
-        tc_fence_before();
-        if (lead) housekeeping();
-      } else {
-        wait_bar(par_bar, par_parity, 302);
-        if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, tp);
-        else if (kind == STEP_MAXPOOL) pool_phase(ph, smem, slot, tid);
-        if (lead && pc_next <= pc + 1) housekeeping();        // only when the next phase's block is not even requested yet
-      }
-      fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
-#ifdef YF_TRACE
-      if (tp) tp[10] = clock64();
-#endif
-      __syncthreads();
-#ifdef YF_TRACE
-      if (tp) tp[11] = clock64();
-#endif
-    }
-  }
-#ifdef YF_TRACE
-  if (a.trace && tid == 0 && blockIdx.x == 0) a.trace[(my_images >= 2 ? 2 : 1) * (nph + 1) - 1] = clock64();
-#endif
+}
+__device__ __forceinline__ void cta_teardown(const Cx& c) {
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, kFusedTmemCols);
+  if (c.warp == 0) tmem_dealloc(c.tmem_base, kFusedTmemCols);
+}
+// the image-dependent part of Rt for front phases of the CTA's k-th image / for the back phases that follow it
+__device__ __forceinline__ void rt_front(Rt& rt, const FusedArgs& a, int k, int my_images) {
+  const long long img = static_cast<long long>(blockIdx.x) + static_cast<long long>(k) * gridDim.x;
+  rt.pair_b = false; rt.ghead_a = nullptr; rt.ghead_b = nullptr;
+  rt.next_in = (k + 1 < my_images) ? a.in + (img + gridDim.x) * a.in_bytes : nullptr;
+}
+__device__ __forceinline__ void rt_back(Rt& rt, const FusedArgs& a, int k) {
+  const long long img = static_cast<long long>(blockIdx.x) + static_cast<long long>(k) * gridDim.x;
+  rt.pair_b = (k & 1) != 0; rt.out_shift = 0; rt.next_in = nullptr;
+  rt.ghead_b = a.out + img * a.head_bytes;                               // only used when pair_b
+  rt.ghead_a = rt.pair_b ? a.out + (img - gridDim.x) * a.head_bytes : rt.ghead_b;
 }
 
-cudaError_t fused_init(int smem_bytes) {
+#ifdef YF_TRACE
+#define YF_TRACE_PHASE(p)                                                                                      \
+  const bool tr = a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u;                                     \
+  if (tr) a.trace[rt.pc] = clock64();                                                                          \
+  long long* const tp = (tr && (p) == a.trace_phase && rt.pc < static_cast<uint32_t>(a.nphases)) ? a.trace + 96 : nullptr;
+#else
+#define YF_TRACE_PHASE(p) long long* const tp = nullptr;
+#endif
+
+// ---- generic kernel: descriptors in shared memory ----------------------------------------------------------------
+__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Cx c;
+  {                                                           // phase descriptors: global -> smem, read with LDS from here on
+    const uint4* src = reinterpret_cast<const uint4*>(a.phases);
+    uint4* dst = reinterpret_cast<uint4*>(smem + a.desc_off);
+    for (int i = threadIdx.x; i < a.nphases * static_cast<int>(sizeof(FusedPhase) / 16); i += kFusedThreads) dst[i] = src[i];
+  }
+  cta_setup(c, a, smem);
+  const FusedPhase* s_ph = reinterpret_cast<const FusedPhase*>(smem + a.desc_off);
+  const int nph = a.nphases, split = a.split;
+  Rt rt; rt.pc = 0u;
+  int p = 0, k = 0;                                           // ONE call site of do_phase: the body exists once in the code
+#pragma unroll 1
+  for (; rt.pc < c.total_pc; ++rt.pc) {
+    if (p == 0) rt_front(rt, a, k, c.my_images);
+    if (p == split) rt_back(rt, a, k);
+    if (p < split) rt.out_shift = (k & 1) ? s_ph[p].out_pair_shift : 0;
+    YF_TRACE_PHASE(p)
+    do_phase(s_ph[p], p, c, a, rt, tp);
+    advance_phase(p, k, split, nph, c.my_images);
+  }
+#ifdef YF_TRACE
+  if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
+#endif
+  cta_teardown(c);
+}
+
+// ---- specialised kernel: descriptors compiled in --------------------------------------------------------------------
+// yf_fused_spec.inc (generated): kSpecNumPhases, kSpecSplit, kSpecWords[][72] (host-side identity check) and
+// template <int P> FusedPhase spec_phase() returning phase P as a bundle of constants.
+#include "yf_fused_spec.inc"
+
+template <int P>
+__device__ __forceinline__ void spec_step(Cx& c, const FusedArgs& a, Rt& rt, int k) {
+  const FusedPhase ph = spec_phase<P>();
+  if (P < kSpecSplit) rt.out_shift = (k & 1) ? ph.out_pair_shift : 0;
+  YF_TRACE_PHASE(P)
+  do_phase(ph, P, c, a, rt, tp);
+  ++rt.pc;
+}
+template <int P0, int P1>
+__device__ __forceinline__ void spec_range(Cx& c, const FusedArgs& a, Rt& rt, int k) {
+  if constexpr (P0 < P1) {
+    spec_step<P0>(c, a, rt, k);
+    spec_range<P0 + 1, P1>(c, a, rt, k);
+  }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_spec_kernel(const FusedArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Cx c;
+  cta_setup(c, a, smem);
+  Rt rt; rt.pc = 0u;
+#pragma unroll 1
+  for (int k = 0; k < c.my_images; ++k) {
+    rt_front(rt, a, k, c.my_images);
+    spec_range<0, kSpecSplit>(c, a, rt, k);
+    if ((k & 1) || k == c.my_images - 1) {
+      rt_back(rt, a, k);
+      spec_range<kSpecSplit, kSpecNumPhases>(c, a, rt, k);
+    }
+  }
+#ifdef YF_TRACE
+  if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
+#endif
+  cta_teardown(c);
+}
+
+// does the specialised kernel implement exactly this program?
+bool fused_spec_matches(const FusedProgram& F) {
+  if (static_cast<int>(F.phases.size()) != kSpecNumPhases || F.split != kSpecSplit) return false;
+  static_assert(sizeof(FusedPhase) == sizeof(kSpecWords[0]), "generated table and FusedPhase disagree");
+  return std::memcmp(F.phases.data(), kSpecWords, sizeof(FusedPhase) * kSpecNumPhases) == 0;
+}
+
+cudaError_t fused_init(int smem_bytes, int smem_bytes_spec) {
   // The attribute belongs to the function (per device), not to a plan: several plans / contexts share it, so it only
   // ever grows -- a later, smaller plan must not take the larger ones' shared memory away.
   const char* e = getenv("YF_B200_FUSED_PAD");
-  const int want = smem_bytes + (e ? atoi(e) : 0);
+  const int pad = e ? atoi(e) : 0;
   int dev = 0;
   cudaGetDevice(&dev);
-  static int granted[64] = {};
-  if (want <= granted[dev & 63]) return cudaSuccess;
-  const cudaError_t r = cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-  if (r == cudaSuccess) granted[dev & 63] = want;
-  return r;
+  static int granted[64] = {}, granted_spec[64] = {};
+  if (smem_bytes + pad > granted[dev & 63]) {
+    const cudaError_t r = cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes + pad);
+    if (r != cudaSuccess) return r;
+    granted[dev & 63] = smem_bytes + pad;
+  }
+  if (smem_bytes_spec > 0 && smem_bytes_spec + pad > granted_spec[dev & 63]) {
+    const cudaError_t r = cudaFuncSetAttribute(yoloface_fused_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_spec + pad);
+    if (r != cudaSuccess) return r;
+    granted_spec[dev & 63] = smem_bytes_spec + pad;
+  }
+  return cudaSuccess;
 }
 
-cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
-                         int sm_count, int* d_err, cudaStream_t s, long long* d_trace) {
-  if (n_img <= 0) return cudaSuccess;
+cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
+  if (L.n_img <= 0) return cudaSuccess;
   FusedArgs a{};
-  a.in = d_in; a.out = d_out; a.params = d_params; a.n_img = n_img; a.nphases = static_cast<int>(F.phases.size());
+  a.in = L.d_in; a.out = L.d_out; a.params = L.d_params; a.phases = L.d_phases; a.n_img = L.n_img;
+  a.nphases = static_cast<int>(F.phases.size()); a.split = F.split;
   a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes; a.desc_off = F.desc_off;
-  a.head_bytes = F.head_bytes; a.err = d_err; a.trace = d_trace; a.in_pf_phase = F.in_pf_phase;
-  a.bars_off = F.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127);
+  a.head_bytes = F.head_bytes; a.err = L.d_err; a.trace = L.d_trace; a.in_pf_phase = F.in_pf_phase;
   { const char* e = getenv("YF_B200_TRACE_PHASE"); a.trace_phase = e ? atoi(e) : 1; }
   // YF_B200_FUSED_PAD (diagnostics): extra dynamic shared memory per CTA, to measure the kernel at lower residency
   static const int pad = [] { const char* e = getenv("YF_B200_FUSED_PAD"); return e ? atoi(e) : 0; }();
-  const int smem = F.smem_bytes + pad;
+  const bool spec = L.use_spec;
+  a.bars_off = spec ? F.desc_off : F.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127);
+  const int smem = (spec ? F.smem_bytes_spec : F.smem_bytes) + pad;
   const int per_sm = smem <= 75 * 1024 ? kFusedCtasPerSm : smem <= 113 * 1024 ? 2 : 1;
-  const int grid = n_img < sm_count * per_sm ? n_img : sm_count * per_sm;
-  yoloface_fused_kernel<<<grid, kFusedThreads, smem, s>>>(a);
+  const int slots = L.sm_count * per_sm;
+  // Pairing: with other launches queued behind this one (`overlapped`) the resident-CTA slots stay full whatever the
+  // grid, so every CTA takes two images and pays the back phases once; a launch running alone keeps one image per CTA
+  // (shortest latency) until there are more images than slots.
+  int grid = L.n_img < slots ? L.n_img : slots;
+  if (L.overlapped && F.split < a.nphases) { const int pairs = (L.n_img + 1) / 2; grid = pairs < slots ? pairs : slots; }
+  if (spec) yoloface_fused_spec_kernel<<<grid, kFusedThreads, smem, L.stream>>>(a);
+  else yoloface_fused_kernel<<<grid, kFusedThreads, smem, L.stream>>>(a);
   return cudaGetLastError();
 }
 

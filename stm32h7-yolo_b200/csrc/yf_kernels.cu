@@ -820,25 +820,52 @@ __global__ void __launch_bounds__(256) lut_kernel(const LutArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Head decode + greedy NMS (rows a13, a14): one warp per image.
-// Candidate order = memory order of the head (cell-major, anchor-minor: yoloface.c:109-116).
+// Head decode + greedy NMS (rows a13, a14).
+// Candidate order = memory order of the head (cell-major, anchor-minor: yoloface.c:109-116); detections come out
+// sorted by (confidence desc, candidate index asc); a candidate survives when sigmoid(conf) >= conf_thr
+// (yoloface.c:123), the greedy pass keeps iou <= iou_thr (yoloface_test.py:148-201).  Anchors and the cell stride are
+// parameters (defaults: yoloface.c:20, input / grid).  NOTHING is truncated before the NMS: the warp kernel is used
+// only when every candidate fits its storage, the block kernel sizes its storage from the head (gh*gw*3).
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxSurvivors = 192;
+constexpr int kWarpCands = 192;          // one warp per image: heads up to 8x8 cells (192 candidates)
 struct Cand { float x1, y1, x2, y2, conf; int idx; };
 
 __device__ __forceinline__ float sigmoid_dev(float x) { return 1.f / (1.f + expf(-x)); }
 
+__device__ __forceinline__ Cand decode_cand(const DecodeArgs& p, const int8_t* head, int k, float conf) {
+  const int cell = k / 3, a = k - cell * 3;
+  const int8_t* q = head + cell * 18 + a * 6;                            // yoloface.c:116
+  const int gy = cell / p.gw, gx = cell - gy * p.gw;                     // :129-130
+  const float zp = static_cast<float>(p.zp);
+  float x = (static_cast<float>(q[0]) - zp) * p.scale, y = (static_cast<float>(q[1]) - zp) * p.scale;
+  float w = (static_cast<float>(q[2]) - zp) * p.scale, h = (static_cast<float>(q[3]) - zp) * p.scale;
+  x = (sigmoid_dev(x) + static_cast<float>(gx)) * p.stride; y = (sigmoid_dev(y) + static_cast<float>(gy)) * p.stride;   // :135-136
+  w = expf(w) * p.anchors[2 * a]; h = expf(h) * p.anchors[2 * a + 1];                                                      // :137-138
+  return Cand{x - w / 2, y - h / 2, x + w / 2, y + h / 2, conf, k};
+}
+// does the kept box `ca` suppress `cb`?  (+1 integer-area convention of yoloface_test.py:172-186 when plus_one)
+__device__ __forceinline__ bool suppresses(const Cand& ca, const Cand& cb, float iou_thr, bool plus_one) {
+  const float one = plus_one ? 1.f : 0.f;
+  float ax1 = ca.x1, ay1 = ca.y1, ax2 = ca.x2, ay2 = ca.y2, bx1 = cb.x1, by1 = cb.y1, bx2 = cb.x2, by2 = cb.y2;
+  if (plus_one) { ax1 = truncf(ax1); ay1 = truncf(ay1); ax2 = truncf(ax2); ay2 = truncf(ay2); bx1 = truncf(bx1); by1 = truncf(by1); bx2 = truncf(bx2); by2 = truncf(by2); }
+  const float area_a = (ax2 - ax1 + one) * (ay2 - ay1 + one), area_b = (bx2 - bx1 + one) * (by2 - by1 + one);
+  const float iw = fmaxf(0.f, fminf(ax2, bx2) - fmaxf(ax1, bx1) + one);
+  const float ih = fmaxf(0.f, fminf(ay2, by2) - fmaxf(ay1, by1) + one);
+  const float inter = iw * ih;
+  const float iou = inter / (area_a + area_b - inter);
+  return !(iou <= iou_thr);
+}
+
 __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs p) {
-  __shared__ Cand s_c[4][kMaxSurvivors];
-  __shared__ int s_order[4][kMaxSurvivors];
-  __shared__ unsigned char s_dead[4][kMaxSurvivors];
+  __shared__ Cand s_c[4][kWarpCands];
+  __shared__ int s_order[4][kWarpCands];
+  __shared__ unsigned char s_dead[4][kWarpCands];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.x * 4 + warp;
   if (img >= p.n_img) return;
   Cand* c = s_c[warp]; int* order = s_order[warp]; unsigned char* dead = s_dead[warp];
   const int8_t* head = p.head + static_cast<long long>(img) * p.gh * p.gw * 18;
-  const int ncand = p.gh * p.gw * 3;
-  const float aw[3] = {9.f, 12.f, 22.f}, ah[3] = {14.f, 17.f, 21.f};   // yoloface.c:20
+  const int ncand = p.gh * p.gw * 3;                          // <= kWarpCands (launch_decode_nms)
   const float zp = static_cast<float>(p.zp);
   int n = 0;
   for (int base = 0; base < ncand; base += 32) {
@@ -851,19 +878,9 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs p) {
     }
     const unsigned mask = __ballot_sync(0xffffffffu, keep);
     const int pos = n + __popc(mask & ((1u << lane) - 1));
-    if (keep && pos < kMaxSurvivors) {
-      const int cell = k / 3, a = k % 3;
-      const int8_t* q = head + cell * 18 + a * 6;
-      const int gx = cell % p.gw, gy = cell / p.gw;
-      float x = (static_cast<float>(q[0]) - zp) * p.scale, y = (static_cast<float>(q[1]) - zp) * p.scale;
-      float w = (static_cast<float>(q[2]) - zp) * p.scale, h = (static_cast<float>(q[3]) - zp) * p.scale;
-      x = (sigmoid_dev(x) + static_cast<float>(gx)) * 8.f; y = (sigmoid_dev(y) + static_cast<float>(gy)) * 8.f;
-      w = expf(w) * aw[a]; h = expf(h) * ah[a];
-      c[pos] = Cand{x - w / 2, y - h / 2, x + w / 2, y + h / 2, conf, k};
-    }
+    if (keep) c[pos] = decode_cand(p, head, k, conf);
     n += __popc(mask);
   }
-  n = min(n, kMaxSurvivors);
   __syncwarp();
   // rank = number of candidates that sort before me (conf desc, index asc); candidates are
   // already in index order so ties resolve by position
@@ -874,7 +891,6 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs p) {
   }
   __syncwarp();
   float* dets = p.dets + static_cast<long long>(img) * p.max_det * 5;
-  const float one = p.plus_one ? 1.f : 0.f;
   int kept = 0;
   for (int a = 0; a < n && kept < p.max_det; ++a) {
     const int ia = order[a];
@@ -883,26 +899,95 @@ __global__ void __launch_bounds__(128) decode_nms_kernel(const DecodeArgs p) {
     if (lane == 0) { float* d = dets + kept * 5; d[0] = ca.x1; d[1] = ca.y1; d[2] = ca.x2; d[3] = ca.y2; d[4] = ca.conf; }
     ++kept;
     if (p.iou_thr >= 0.f) {
-      float ax1 = ca.x1, ay1 = ca.y1, ax2 = ca.x2, ay2 = ca.y2;
-      if (p.plus_one) { ax1 = truncf(ax1); ay1 = truncf(ay1); ax2 = truncf(ax2); ay2 = truncf(ay2); }
-      const float area_a = (ax2 - ax1 + one) * (ay2 - ay1 + one);
       for (int b = a + 1 + lane; b < n; b += 32) {
         const int ib = order[b];
-        if (dead[ib]) continue;
-        float bx1 = c[ib].x1, by1 = c[ib].y1, bx2 = c[ib].x2, by2 = c[ib].y2;
-        if (p.plus_one) { bx1 = truncf(bx1); by1 = truncf(by1); bx2 = truncf(bx2); by2 = truncf(by2); }
-        const float area_b = (bx2 - bx1 + one) * (by2 - by1 + one);
-        const float iw = fmaxf(0.f, fminf(ax2, bx2) - fmaxf(ax1, bx1) + one);
-        const float ih = fmaxf(0.f, fminf(ay2, by2) - fmaxf(ay1, by1) + one);
-        const float inter = iw * ih;
-        const float iou = inter / (area_a + area_b - inter);
-        if (!(iou <= p.iou_thr)) dead[ib] = 1;
+        if (!dead[ib] && suppresses(ca, c[ib], p.iou_thr, p.plus_one != 0)) dead[ib] = 1;
       }
     }
     __syncwarp();
   }
   for (int k = kept * 5 + lane; k < p.max_det * 5; k += 32) dets[k] = 0.f;    // unused slots read as zeros
   if (lane == 0) p.counts[img] = kept;
+}
+
+// Larger heads: one 256-thread block per image, storage for EVERY candidate in dynamic shared memory
+// (8 B sort key + 16 B box + 1 B flag per candidate).  Survivors are compacted in index order, sorted by a bitonic
+// network on the key {conf bits, ~index} (descending = conf desc, index asc), decoded in sorted order, then the same
+// greedy pass runs with the whole block testing one kept box against the rest.
+constexpr int kDecodeBlock = 256;
+__global__ void __launch_bounds__(kDecodeBlock) decode_nms_block_kernel(const DecodeArgs p, int cap_pow2) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(dsm);                       // [cap_pow2]
+  float4* box = reinterpret_cast<float4*>(dsm + static_cast<size_t>(cap_pow2) * 8);          // [cap_pow2]
+  unsigned char* dead = dsm + static_cast<size_t>(cap_pow2) * 24;                             // [cap_pow2]
+  __shared__ int s_n, s_warp_n[kDecodeBlock / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int img = blockIdx.x;
+  const int8_t* head = p.head + static_cast<long long>(img) * p.gh * p.gw * 18;
+  const int ncand = p.gh * p.gw * 3;
+  const float zp = static_cast<float>(p.zp);
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int base = 0; base < ncand; base += kDecodeBlock) {    // ordered compaction: ballot within warps, scan across them
+    const int k = base + tid;
+    bool keep = false; float conf = 0.f;
+    if (k < ncand) {
+      const int8_t* q = head + (k / 3) * 18 + (k % 3) * 6;
+      conf = sigmoid_dev((static_cast<float>(q[4]) - zp) * p.scale);
+      keep = conf >= p.conf_thr;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp_n[warp] = __popc(mask);
+    __syncthreads();
+    int pos = s_n;
+    for (int w = 0; w < warp; ++w) pos += s_warp_n[w];
+    pos += __popc(mask & ((1u << lane) - 1));
+    if (keep) key[pos] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | static_cast<unsigned>(~static_cast<unsigned>(k));
+    __syncthreads();
+    if (tid == 0) { int t = s_n; for (int w = 0; w < kDecodeBlock / 32; ++w) t += s_warp_n[w]; s_n = t; }
+    __syncthreads();
+  }
+  const int n = s_n;
+  int m = 1; while (m < n) m <<= 1;                           // sort the first m >= n keys (padding = 0 sorts last)
+  for (int i = n + tid; i < m; i += kDecodeBlock) key[i] = 0ull;
+  __syncthreads();
+  for (int k2 = 2; k2 <= m; k2 <<= 1)
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < m; i += kDecodeBlock) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = key[i], b = key[l];
+          const bool desc = (i & k2) == 0;                    // descending blocks first
+          if (desc ? a < b : a > b) { key[i] = b; key[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < n; i += kDecodeBlock) {
+    const unsigned long long kk = key[i];
+    const Cand cd = decode_cand(p, head, static_cast<int>(~static_cast<unsigned>(kk & 0xffffffffull)), __uint_as_float(static_cast<unsigned>(kk >> 32)));
+    box[i] = make_float4(cd.x1, cd.y1, cd.x2, cd.y2); dead[i] = 0;
+  }
+  __syncthreads();
+  float* dets = p.dets + static_cast<long long>(img) * p.max_det * 5;
+  int kept = 0;
+  for (int a = 0; a < n && kept < p.max_det; ++a) {
+    if (dead[a]) continue;                                    // block-uniform (shared memory, read after a barrier)
+    const float4 ba = box[a];
+    const Cand ca{ba.x, ba.y, ba.z, ba.w, 0.f, 0};
+    if (tid == 0) { float* d = dets + kept * 5; d[0] = ba.x; d[1] = ba.y; d[2] = ba.z; d[3] = ba.w; d[4] = __uint_as_float(static_cast<unsigned>(key[a] >> 32)); }
+    ++kept;
+    if (p.iou_thr >= 0.f) {
+      for (int b = a + 1 + tid; b < n; b += kDecodeBlock) {
+        if (dead[b]) continue;
+        const float4 bb = box[b];
+        if (suppresses(ca, Cand{bb.x, bb.y, bb.z, bb.w, 0.f, 0}, p.iou_thr, p.plus_one != 0)) dead[b] = 1;
+      }
+      __syncthreads();
+    }
+  }
+  for (int k = kept * 5 + tid; k < p.max_det * 5; k += kDecodeBlock) dets[k] = 0.f;
+  if (tid == 0) p.counts[img] = kept;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1043,9 +1128,18 @@ cudaError_t launch_raise_error(int* d_err, int code, cudaStream_t s) {
   raise_error_kernel<<<1, 1, 0, s>>>(d_err, code);
   return cudaGetLastError();
 }
+int decode_block_smem(int ncand) { int m = 1; while (m < ncand) m <<= 1; return m * 25 + 16; }
 cudaError_t launch_decode_nms(const DecodeArgs& a, cudaStream_t s) {
   if (a.n_img <= 0) return cudaSuccess;
-  decode_nms_kernel<<<(a.n_img + 3) / 4, 128, 0, s>>>(a);
+  const int ncand = a.gh * a.gw * 3;
+  if (ncand <= kWarpCands) {
+    decode_nms_kernel<<<(a.n_img + 3) / 4, 128, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  const int smem = decode_block_smem(ncand);
+  if (smem > kDecodeSmemMax) return cudaErrorInvalidConfiguration;       // heads beyond 50x50 cells: the caller reports it
+  int m = 1; while (m < ncand) m <<= 1;
+  decode_nms_block_kernel<<<a.n_img, kDecodeBlock, smem, s>>>(a, m);
   return cudaGetLastError();
 }
 cudaError_t launch_prep_rgb565(const PrepArgs& a, cudaStream_t s) {
@@ -1066,6 +1160,7 @@ cudaError_t kernels_init() {
   YF_OPTIN(conv_im2col_tcgen05_kernel<32>, im2col_smem_bytes<32>())
   YF_OPTIN(dwconv3x3_band_kernel, 2 * kDwStageBytes + 64 + 512)
   YF_OPTIN(maxpool_band_kernel, kPoolSmemMax)
+  YF_OPTIN(decode_nms_block_kernel, kDecodeSmemMax)
 #undef YF_OPTIN
   return cudaSuccess;
 }

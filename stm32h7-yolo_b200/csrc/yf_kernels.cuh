@@ -8,6 +8,7 @@
 
 namespace yf {
 
+constexpr int kDecodeSmemMax = 220 * 1024;   // decode_nms_block_kernel: 25 B per candidate slot (power of two >= gh*gw*3)
 constexpr int kMaxEpiCh = 832;           // __constant__ EpiCh table entries (26 KB per table)
 
 // Where an epilogue writes (shared by every kernel).  Pointers are to element [row 0, channel 0]
@@ -65,6 +66,8 @@ struct DecodeArgs {
   const int8_t* head;                    // [n, gh, gw, 18]
   int n_img, gh, gw;
   float scale; int zp;
+  float anchors[6];                      // 3 x {w, h} in input pixels (default yoloface.c:20)
+  float stride;                          // input pixels per head cell (input height / gh)
   float conf_thr, iou_thr; int plus_one;
   float* dets;                           // [n, max_det, 5]
   int* counts;                           // [n]
@@ -90,9 +93,19 @@ cudaError_t launch_raise_error(int* d_err, int code, cudaStream_t s);   // test 
 cudaError_t kernels_init();              // opt-in dynamic smem sizes
 
 // fused single-kernel path (yf_fused.cu)
-cudaError_t upload_fused_tables(const EpiCh* epi, int n, const FusedPhase* phases, int nph, cudaStream_t s);
-cudaError_t fused_init(int smem_bytes);
-cudaError_t launch_fused(const FusedProgram& F, const int8_t* d_in, int8_t* d_out, const uint8_t* d_params, int n_img,
-                         int sm_count, int* d_err, cudaStream_t s, long long* d_trace = nullptr);
+struct FusedLaunch {
+  const int8_t* d_in; int8_t* d_out;
+  const uint8_t* d_params;               // parameter blocks (per plan, global memory)
+  const FusedPhase* d_phases;            // phase descriptors (per plan, global memory)
+  int n_img, sm_count;
+  int* d_err;
+  cudaStream_t stream;
+  long long* d_trace;
+  bool use_spec;                         // the plan equals the compiled-in program: run the specialised kernel
+  bool overlapped;                       // other launches are queued around this one (pair the images even when few)
+};
+bool fused_spec_matches(const FusedProgram& F);
+cudaError_t fused_init(int smem_bytes, int smem_bytes_spec);
+cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L);
 
 }  // namespace yf

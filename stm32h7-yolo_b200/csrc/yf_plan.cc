@@ -583,7 +583,42 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   for (int b = 0; b < nb; ++b) padded[b] = has_prod_conv[b] && has_cons[b] && !bad_cons[b] && !P.buffers[b].is_input && !P.buffers[b].is_output;
   for (int i = 0; i < ns; ++i) if ((P.steps[i].kind == STEP_DW || P.steps[i].kind == STEP_MAXPOOL) && !padded[P.steps[i].in_buf])
     return no("depthwise/pool input " + P.steps[i].name + " is not a conv-produced, dw/pool-only buffer");
-  auto cells_of = [&](int b) { const PBuffer& B = P.buffers[b]; return padded[b] ? (B.H + 2) * (B.W + 2) : B.H * B.W; };
+
+  // ---- image pairs: the trailing run of resolution-preserving steps at the head's resolution ("back") is executed
+  //      once for two images stacked into a tall image of 2H+2 rows (two separator rows between them) ----
+  int split = ns;
+  while (split > 1) {
+    const Step& s = P.steps[split - 1];
+    const bool keeps = (s.kind == STEP_CONV1X1 || (s.kind == STEP_DW && s.stride == 1 && s.pad_t == 1 && s.pad_l == 1)) &&
+                       s.Hin == P.GH && s.Win == P.GW && s.Hout == P.GH && s.Wout == P.GW;
+    if (!keeps) break;
+    --split;
+  }
+  std::vector<char> in_back(nb, 0), crossing(nb, 0);
+  auto mark_back = [&]() {
+    std::fill(in_back.begin(), in_back.end(), 0); std::fill(crossing.begin(), crossing.end(), 0);
+    for (int i = split; i < ns; ++i) {
+      const Step& s = P.steps[i];
+      in_back[s.in_buf] = 1; in_back[s.out_buf] = 1; if (s.add_buf >= 0) in_back[s.add_buf] = 1;
+    }
+    for (int i = 0; i < split; ++i) {
+      const Step& s = P.steps[i];
+      if (in_back[s.out_buf]) crossing[s.out_buf] = 1;
+      // a front step READING a buffer the back phases also touch would need the pair addressing too: give up pairing
+      if (in_back[s.in_buf] || (s.add_buf >= 0 && in_back[s.add_buf])) return false;
+    }
+    for (int b = 0; b < nb; ++b) if (crossing[b] && (padded[b] || P.buffers[b].is_output)) return false;
+    return true;
+  };
+  if (split < ns && (ns - split < 2 || !mark_back())) split = ns;
+  if (split == ns) { std::fill(in_back.begin(), in_back.end(), 0); std::fill(crossing.begin(), crossing.end(), 0); }
+  const int Hs = P.GH, Ws = P.GW, Hp = 2 * Hs + 2;        // single image / tall pair image at the head's resolution
+
+  auto cells_of = [&](int b) {
+    const PBuffer& B = P.buffers[b];
+    const int H = in_back[b] ? Hp : B.H;
+    return padded[b] ? (H + 2) * (B.W + 2) : H * B.W;
+  };
   // word-plane stride: cells * 4 bytes, skewed so that the planes of the words one warp touches start
   // 32 / nw banks apart (a warp of the depthwise / pool phases covers ~32 / nw cells of each of its nw words)
   auto plane_stride = [](int cells, int nw) { int w = cells; while (w % 32 != (32 / std::max(nw, 1)) % 32) ++w; return w * 4; };
@@ -601,28 +636,54 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     if (s.kind == STEP_CONV_IM2COL && ((s.Hout * s.Wout + 127) / 128) * s.Npad > kFusedTmemCols)
       return no("accumulator tiles of the first conv exceed TMEM");
   }
-  // first-fit placement in birth order (scratch of phase i is born with the buffers written at i)
+  // first-fit placement in birth order (scratch of phase i is born with the buffers written at i).  Buffers that
+  // cross from the front into the back phases hold image A while image B's front phases run: they are live throughout.
   struct Item { int id, birth, death, size; };          // id >= 0: buffer, id < 0: scratch of phase -id-1
   std::vector<Item> items;
   for (int b = 0; b < nb; ++b) if (!P.buffers[b].is_input && !P.buffers[b].is_output && !P.buffers[b].observer_only && death[b] >= 0)
-    items.push_back(Item{b, birth[b], death[b], bytes_of(b)});
+    items.push_back(Item{b, crossing[b] ? 0 : birth[b], crossing[b] ? ns - 1 : death[b], bytes_of(b)});
   for (int i = 0; i < ns; ++i) if (scratch_size[i]) items.push_back(Item{-i - 1, i, i, (scratch_size[i] + 127) & ~127});
-  std::sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.birth != b.birth ? a.birth < b.birth : a.id > b.id; });
-  struct Live { int off, size, death; };
-  std::vector<Live> live; std::vector<int> off(nb, -1), scratch_off(ns, -1);
-  int arena = 0;
-  for (const Item& it : items) {
-    live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.death < it.birth; }), live.end());
-    std::vector<int> cand{0}; for (const Live& l : live) cand.push_back(l.off + l.size);
-    std::sort(cand.begin(), cand.end());
-    int best = -1;
-    for (int c : cand) {
-      bool clash = false;
-      for (const Live& l : live) if (c < l.off + l.size && l.off < c + it.size) { clash = true; break; }
-      if (!clash) { best = c; break; }
+  // Offsets: place the items one by one at the lowest offset that clears every already placed item whose live range
+  // overlaps.  The result depends on the order; the problem is tiny (~30 items), so several orders are tried -- by
+  // birth, by size, by live-range length, then a fixed pseudo-random sequence of permutations -- and the smallest
+  // arena wins (deterministic: the same plan always yields the same map, which the generated kernel relies on).
+  std::vector<int> off(nb, -1), scratch_off(ns, -1);
+  int arena = 1 << 30;
+  {
+    const int ni = static_cast<int>(items.size());
+    auto place = [&](const std::vector<int>& order, std::vector<int>* offs) {
+      offs->assign(ni, -1);
+      int top = 0;
+      for (int oi = 0; oi < ni; ++oi) {
+        const Item& it = items[order[oi]];
+        std::vector<std::pair<int, int>> busy;               // [off, end) of placed items alive at the same time
+        for (int oj = 0; oj < oi; ++oj) {
+          const Item& ot = items[order[oj]];
+          if (ot.birth <= it.death && it.birth <= ot.death) busy.push_back({(*offs)[order[oj]], (*offs)[order[oj]] + ot.size});
+        }
+        std::sort(busy.begin(), busy.end());
+        int c = 0;
+        for (const auto& b : busy) { if (c + it.size <= b.first) break; c = std::max(c, b.second); }
+        (*offs)[order[oi]] = c; top = std::max(top, c + it.size);
+      }
+      return top;
+    };
+    std::vector<int> order(ni), offs, best_offs;
+    auto consider = [&]() { const int t = place(order, &offs); if (t < arena) { arena = t; best_offs = offs; } };
+    for (int i = 0; i < ni; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return items[x].birth != items[y].birth ? items[x].birth < items[y].birth : items[x].id > items[y].id; });
+    consider();
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return items[x].size > items[y].size; });
+    consider();
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return items[x].death - items[x].birth > items[y].death - items[y].birth; });
+    consider();
+    uint32_t rs = 0x9E3779B9u;
+    for (int trial = 0; trial < 2000; ++trial) {
+      for (int i = ni - 1; i > 0; --i) { rs = rs * 1664525u + 1013904223u; std::swap(order[i], order[(rs >> 8) % static_cast<uint32_t>(i + 1)]); }
+      consider();
     }
-    if (it.id >= 0) off[it.id] = best; else scratch_off[-it.id - 1] = best;
-    live.push_back(Live{best, it.size, it.death}); arena = std::max(arena, best + it.size);
+    if (ni == 0) arena = 0;
+    for (int i = 0; i < ni; ++i) { if (items[i].id >= 0) off[items[i].id] = best_offs[i]; else scratch_off[-items[i].id - 1] = best_offs[i]; }
   }
   // smem map: [input image][arena][parameter slots][phase descriptors][barriers]
   const Step& s0 = P.steps[0];
@@ -632,13 +693,19 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   F->arena_off = (F->in_off + F->in_bytes + 16 + 127) & ~127;
   F->arena_bytes = (arena + 127) & ~127;
   F->slot_off = F->arena_off + F->arena_bytes;
+  F->split = split;
   int overread_end = 0;                          // a 128-row MMA tile reads past the rows (and the K chunks) its buffer holds
   // parameter blocks
   int slot = 0;
   for (int i = 0; i < ns; ++i) {
     const Step& s = P.steps[i];
+    const bool back = i >= split;
     FusedPhase ph{}; ph.kind = s.kind;
-    ph.Hin = s.Hin; ph.Win = s.Win; ph.Hout = s.Hout; ph.Wout = s.Wout; ph.rows_in = s.Hin * s.Win; ph.rows_out = s.Hout * s.Wout;
+    ph.Hin = back ? Hp : s.Hin; ph.Win = s.Win; ph.Hout = back ? Hp : s.Hout; ph.Wout = s.Wout;
+    ph.rows_in = ph.Hin * ph.Win; ph.rows_out = ph.Hout * ph.Wout;
+    ph.pair = back ? 1 : 0;
+    if (back) { ph.sep_y = Hs; ph.rows_a = Hs * Ws; ph.row_b0 = (Hs + 2) * Ws; ph.rows_single = (Hs + 2) * Ws; }
+    else ph.rows_single = ph.rows_out;
     ph.stride = s.stride; ph.pad_t = s.pad_t; ph.pad_l = s.pad_l; ph.ksize = s.kh; ph.in_zp = s.in_zp;
     const PBuffer& ib = P.buffers[s.in_buf]; const PBuffer& ob = P.buffers[s.out_buf];
     ph.in_off = ib.is_input ? F->in_off : F->arena_off + off[s.in_buf];
@@ -651,8 +718,9 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     ph.out_ws = ph.out_wp ? plane_stride(cells_of(s.out_buf), words_of(s.out_buf)) : 0;
     if (ph.out_wp) { for (int j = i + 1; j < ns; ++j) if (P.steps[j].in_buf == s.out_buf) { ph.out_zp = P.steps[j].in_zp; break; } }
     ph.out_off = ob.is_output ? 0 : F->arena_off + off[s.out_buf] + (s.out_coff / 16) * ph.out_cs;
+    if (!back && !ob.is_output && crossing[s.out_buf]) ph.out_pair_shift = (Hs + 2) * Ws * 16;   // image B's rows of the tall buffer
     ph.add_off = -1; ph.scratch_off = scratch_off[i] >= 0 ? F->arena_off + scratch_off[i] : -1;
-    if (s.add.enabled) { ph.add = s.add; ph.add_cs = ph.rows_out * 16; ph.add_off = F->arena_off + off[s.add_buf] + (s.add_coff / 16) * ph.add_cs; }
+    if (s.add.enabled) { ph.add = s.add; ph.add_cs = cells_of(s.add_buf) * 16; ph.add_off = F->arena_off + off[s.add_buf] + (s.add_coff / 16) * ph.add_cs; }
     ph.cout = s.Cout; ph.chunks_out = (s.Cout + 15) / 16; ph.epi_base = s.epi_base; ph.has_lut = s.lut_fused >= 0;
     ph.npad = s.Npad;
     ph.ntiles = (ph.rows_out + 127) / 128;
@@ -667,12 +735,18 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     ph.scratch_ws = s.kind == STEP_MAXPOOL ? plane_stride(s.Hin * s.Wout, ph.nw) : 0;
     if (s.kind == STEP_CONV1X1) {
       if ((ph.ntiles + ph.tpg - 1) / ph.tpg > 4) return no("more than four tile groups in step " + s.name);
-      for (int t0 = 0, g = 0; t0 < ph.ntiles; t0 += ph.tpg, ++g) {
-        const int nt = std::min(ph.tpg, ph.ntiles - t0);
-        int n = fused_has_rows(kFusedCtrlWarp, t0, nt, ph.rows_out, ph.chunks_out) ? 0 : 1;
-        for (int w = 0; w < 4 * kFusedWarpgroups; ++w) n += fused_has_rows(w, t0, nt, ph.rows_out, ph.chunks_out) ? 1 : 0;
-        ph.grp_warps |= static_cast<uint32_t>(n) << (8 * g);
-      }
+      auto meet_counts = [&](int rows) {
+        uint32_t v = 0;
+        for (int t0 = 0, g = 0; t0 < ph.ntiles; t0 += ph.tpg, ++g) {
+          const int nt = std::min(ph.tpg, ph.ntiles - t0);
+          int n = fused_has_rows(kFusedCtrlWarp, t0, nt, rows, ph.chunks_out) ? 0 : 1;
+          for (int w = 0; w < 4 * kFusedWarpgroups; ++w) n += fused_has_rows(w, t0, nt, rows, ph.chunks_out) ? 1 : 0;
+          v |= static_cast<uint32_t>(n) << (8 * g);
+        }
+        return v;
+      };
+      ph.grp_warps = meet_counts(ph.rows_out);
+      ph.grp_warps_single = meet_counts(ph.rows_single);
     }
     {
       // reciprocal multipliers; every quotient the kernel forms has x < 4096
@@ -747,11 +821,13 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   }
   F->slot_bytes = (slot + 127) & ~127;
   F->desc_off = F->slot_off + kFusedParamSlots * F->slot_bytes;
-  F->smem_bytes = F->desc_off + ((static_cast<int>(F->phases.size() * sizeof(FusedPhase)) + 127) & ~127) + 256;
+  F->smem_bytes = F->desc_off + ((static_cast<int>(F->phases.size() * sizeof(FusedPhase)) + 127) & ~127) + 384;   // + barriers, TMEM slot, parameter-block table
   F->smem_bytes = std::max(F->smem_bytes, overread_end);      // the over-read bytes meet zero weights; they only have to exist
+  F->smem_bytes_spec = std::max(F->desc_off + 384, overread_end);
   F->in_pf_phase = 1;                                         // prefetch of the next image rides on the first 1x1 conv phase
   for (int i = 1; i < ns; ++i) if (P.steps[i].kind == STEP_CONV1X1) { F->in_pf_phase = i; break; }
-  F->head_bytes = P.GH * P.GW * 18;
+  if (F->in_pf_phase >= split) return no("no front 1x1 conv phase to carry the input prefetch");
+  F->head_bytes = P.GH * P.GW * P.buffers[P.output_buf].C;
   if (F->smem_bytes > 200 * 1024) return no("activations do not fit shared memory (" + std::to_string(F->smem_bytes) + " bytes)");
   F->ok = true;
   return true;

@@ -187,9 +187,20 @@ struct alignas(16) FusedPhase {
   // conv: byte g = warps meeting at the named barrier that releases tile group g's epilogue (the warps owning
   // accumulator rows plus the control warp), see fused_has_rows()
   uint32_t grp_warps;
-  int32_t pad_[3];
+  // ---- image pairs (see FusedProgram::split) ----
+  // Back phases (pair = 1) run ONCE for two images stacked into one "tall" image of 2H+2 rows: rows [0,H) are image A,
+  // rows H and H+1 are separator rows (they act as A's bottom and B's top zero-point border in bordered buffers and
+  // carry don't-care values elsewhere), rows [H+2, 2H+2) are image B.  Hin/Hout/rows_* above describe the tall image.
+  int32_t pair;
+  int32_t sep_y;                // first separator row (= H of one image)
+  int32_t rows_a, row_b0;       // pixels of image A (H*W) / first pixel row of image B ((H+2)*W)
+  int32_t rows_single;          // rows processed when the pair holds only image A: (H+2)*W (A plus both separator rows)
+  uint32_t grp_warps_single;    // grp_warps for rows_single
+  // front phases whose output crosses into the back phases: byte offset added to out_off for the pair's second image
+  int32_t out_pair_shift;
+  int32_t pad_[2];
 };
-static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied to shared memory with 16-byte loads");
+static_assert(sizeof(FusedPhase) == 72 * 4, "FusedPhase: 72 32-bit words, no holes (copied with 16-byte loads, compared word-wise with the generated table)");
 
 struct FusedProgram {
   bool ok = false;              // false: this resolution/model cannot run fused (use the layered path)
@@ -202,13 +213,17 @@ struct FusedProgram {
   int slot_off = 0, slot_bytes = 0;     // smem: kFusedParamSlots parameter slots
   int desc_off = 0;                     // smem: copy of the phase descriptors
   int in_pf_phase = 1;                  // phase at which the next image's input is prefetched (input buffer free)
-  int smem_bytes = 0;
+  // Phases [0, split) ("front") run per image; phases [split, n) ("back": the layers at the head's resolution, 14 of
+  // which see only 7x7 = 49 rows of a 128-row MMA tile in yoloface) run once per PAIR of images.  split == n: no pairing.
+  int split = 0;
+  int smem_bytes = 0;                   // generic kernel (phase descriptors in shared memory)
+  int smem_bytes_spec = 0;              // specialised kernel (descriptors compiled in): barriers sit at desc_off
   int head_bytes = 0;           // bytes per image of the dense head
 };
 constexpr int kFusedMaxPhases = 32;
 constexpr int kFusedWarpgroups = 2;   // warps = 4 * kFusedWarpgroups (a warp reads the TMEM lane quarter warp % 4)
 constexpr int kFusedWorkerThreads = kFusedWarpgroups * 128;
-constexpr int kFusedParamSlots = 4;
+constexpr int kFusedParamSlots = 3;
 constexpr int kFusedTmemCols = 128;     // per CTA (three CTAs share an SM's 512 columns); larger layers run in tile groups
 constexpr int kFusedCtrlWarp = 4 * kFusedWarpgroups - 1;   // issues the MMAs / bulk copies (lane quarter 3 of the last warpgroup)
 

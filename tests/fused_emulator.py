@@ -13,11 +13,29 @@ from plan_emulator import lut_apply, mbqm, requant
 
 
 def run_fused(F, img, seed=0):
+    """One image (a pair holding only image A) or a list of two images (front phases twice, back phases once on the
+    tall pair image).  Returns the head, or the list of two heads."""
+    imgs = img if isinstance(img, (list, tuple)) else [img]
+    assert 1 <= len(imgs) <= 2
     rng = np.random.default_rng(seed)
     smem = rng.integers(0, 256, F["smem_bytes"] + (1 << 16), dtype=np.uint8)
-    smem[F["in_off"]:F["in_off"] + F["in_bytes"]] = np.ascontiguousarray(img).view(np.uint8).reshape(-1)
     params, epi_all = F["params"], F["epi"]
-    head = None
+    split = F.get("split", len(F["phases"]))
+    heads = [None, None]
+    pair_b = len(imgs) == 2
+    if split == len(F["phases"]):
+        assert len(imgs) == 1, "this program has no pair phases"
+    for k, im in enumerate(imgs):
+        smem[F["in_off"]:F["in_off"] + F["in_bytes"]] = np.ascontiguousarray(im).view(np.uint8).reshape(-1)
+        for ph in F["phases"][:split]:
+            _phase(F, ph, smem, rng, params, epi_all, heads, shift=ph.get("out_pair_shift", 0) if k else 0, pair_b=False)
+        # the front phases of the next image may scribble over everything but the buffers that cross into the back
+    for ph in F["phases"][split:]:
+        _phase(F, ph, smem, rng, params, epi_all, heads, shift=0, pair_b=pair_b)
+    return heads if pair_b else heads[0]
+
+
+def _phase(F, ph, smem, rng, params, epi_all, heads, shift, pair_b):
 
     def chunk_rows(off, cs, chunk, rows):          # -> int8 [rows,16] view of one chunk
         a = off + chunk * cs
@@ -33,9 +51,12 @@ def run_fused(F, img, seed=0):
         assert ph["in_wp"] == W + 2 and ph["in_ws"] >= cells * 4 and ph["in_ws"] % 4 == 0
         return np.concatenate([word_plane(ph["in_off"], ph["in_ws"], w, cells) for w in range(nw)], axis=1).reshape(H + 2, W + 2, nw * 4).astype(np.int64)
 
-    for ph in F["phases"]:
+    if True:
         slot = params[ph["param_off"]:ph["param_off"] + ph["param_bytes"]]
-        kind, rows_o, cout, npad = ph["kind"], ph["rows_out"], ph["cout"], ph["npad"]
+        kind, cout, npad = ph["kind"], ph["cout"], ph["npad"]
+        pair = ph.get("pair", 0)
+        rows_o = ph["rows_out"] if (not pair or pair_b) else ph["rows_single"]     # rows the conv epilogues process
+        rows_dw = ph["rows_out"] if (not pair or pair_b) else ph["rows_a"]         # rows the depthwise phases produce
         lut = slot[ph["lut_off"]:ph["lut_off"] + 256].view(np.int8) if ph["has_lut"] else None
         if ph["scratch_off"] >= 0:      # the kernel scribbles here during this phase: must not alias anything live
             size = 4 * 6144 + 2048 if kind == 0 else ph["nw"] * ph["scratch_ws"]
@@ -98,6 +119,9 @@ def run_fused(F, img, seed=0):
             xp = padded_input(ph, chunks)           # the border must already hold the zero point (written by the producer)
             w = w[:, :xp.shape[2]]
             assert np.all(xp[0, :, :cout] == ph["in_zp"]) and np.all(xp[:, 0, :cout] == ph["in_zp"]) and np.all(xp[-1, :, :cout] == ph["in_zp"]) and np.all(xp[:, -1, :cout] == ph["in_zp"])
+            if pair:                                # the separator rows are image A's bottom / image B's top border
+                assert np.all(xp[ph["sep_y"] + 1, :, :cout] == ph["in_zp"])
+                assert not pair_b or np.all(xp[ph["sep_y"] + 2, :, :cout] == ph["in_zp"])
             oy0, ox0 = 1 - ph["pad_t"], 1 - ph["pad_l"]
             acc = np.zeros((Ho, Wo, xp.shape[2]), np.int64)
             for ky in range(3):
@@ -106,6 +130,7 @@ def run_fused(F, img, seed=0):
             y = np.clip(requant(acc.reshape(Ho * Wo, -1)[:, :cout], epi), -128, 127)
             if lut is not None:
                 y = lut_apply(y, lut)
+            y = y[:rows_dw]
         elif kind == 3:
             chunks = ph["chunks_out"]; cp = chunks * 16
             H, W, Ho, Wo, st, k = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"], ph["ksize"]
@@ -119,23 +144,30 @@ def run_fused(F, img, seed=0):
                 y = lut_apply(y, lut)
         else:
             raise AssertionError(kind)
+        nrows = y.shape[0]
         if ph["to_global"]:
-            head = y.astype(np.int8)
-            continue
-        out = rng.integers(-128, 128, (rows_o, ph["chunks_out"] * 16)).astype(np.int8)   # pad channels: garbage (must meet zero weights)
+            if pair:
+                heads[0] = y[:ph["rows_a"]].astype(np.int8)
+                if pair_b:
+                    heads[1] = y[ph["row_b0"]:ph["row_b0"] + ph["rows_a"]].astype(np.int8)
+            else:
+                heads[0] = y.astype(np.int8)
+            return
+        out = rng.integers(-128, 128, (nrows, ph["chunks_out"] * 16)).astype(np.int8)   # pad channels: garbage (must meet zero weights)
         out[:, :cout] = y
         if ph["out_wp"]:                            # producer writes the interior of a word-planar bordered buffer and fills the border
             Ho, Wo, nw = ph["Hout"], ph["Wout"], ph["nw"]
-            full = np.full((Ho + 2, Wo + 2, nw * 4), ph["out_zp"], np.int8)
-            full[1:-1, 1:-1] = out.reshape(Ho, Wo, -1)[:, :, :nw * 4]
             cells = (Ho + 2) * (Wo + 2)
-            assert ph["out_ws"] >= cells * 4 and ph["out_wp"] == Wo + 2
-            full = full.reshape(cells, nw * 4)
-            for w in range(nw):
+            assert ph["out_ws"] >= cells * 4 and ph["out_wp"] == Wo + 2 and shift == 0
+            for w in range(nw):                     # start from what is there: rows the kernel does not process keep their bytes
                 a = ph["out_off"] + w * ph["out_ws"]
-                smem[a:a + cells * 4] = full[:, w * 4:(w + 1) * 4].reshape(-1).view(np.uint8)
-            continue
+                plane = smem[a:a + cells * 4].view(np.int8).reshape(Ho + 2, Wo + 2, 4)
+                plane[0] = ph["out_zp"]; plane[-1] = ph["out_zp"]; plane[:, 0] = ph["out_zp"]; plane[:, -1] = ph["out_zp"]
+                for r in range(nrows):
+                    yy, xx = divmod(r, Wo)
+                    sep = pair and yy in (ph["sep_y"], ph["sep_y"] + 1)
+                    plane[yy + 1, xx + 1] = ph["out_zp"] if sep else out[r, w * 4:(w + 1) * 4]
+            return
         for g in range(ph["chunks_out"]):
-            a = ph["out_off"] + g * ph["out_cs"]
-            smem[a:a + out.shape[0] * 16] = out[:, g * 16:(g + 1) * 16].reshape(-1).view(np.uint8)
-    return head
+            a = ph["out_off"] + shift + g * ph["out_cs"]
+            smem[a:a + nrows * 16] = out[:, g * 16:(g + 1) * 16].reshape(-1).view(np.uint8)

@@ -126,11 +126,20 @@ def test_fused_program_reproduces_oracle(yf, oracle, golden):
     blocks) emulated on a flat, garbage-filled byte array gives the oracle's head bit-exactly."""
     from fused_emulator import run_fused
     F = yf.fused_program(56, 56)
-    assert F["smem_bytes"] <= 113 * 1024          # two CTAs per SM
-    assert len(F["phases"]) == 26
+    assert F["smem_bytes"] <= 113 * 1024          # two CTAs per SM for the generic kernel (descriptors in smem)
+    assert F["smem_bytes_spec"] <= 75 * 1024      # three for the specialised one
+    assert F["spec"] == 1                         # the compiled-in program IS this plan
+    assert len(F["phases"]) == 26 and F["split"] == 14
     for seed, img in enumerate([vector_a(), vector_b(), golden["images"][5]]):
         head = run_fused(F, img, seed)
         assert np.array_equal(head.reshape(7, 7, 18), oracle.run(img))
+    # image pairs: front phases twice, the twelve 7x7 phases once on the tall 16x7 image
+    for seed, (i, j) in enumerate([(0, 1), (7, 3), (26, 26)]):
+        a, b = golden["images"][i], golden["images"][j]
+        ha, hb = run_fused(F, [a, b], 10 + seed)
+        assert np.array_equal(ha.reshape(7, 7, 18), oracle.run(a)) and np.array_equal(hb.reshape(7, 7, 18), oracle.run(b))
+    ha, hb = run_fused(F, [vector_a(), vector_b()], 5)
+    assert np.array_equal(ha.reshape(7, 7, 18), oracle.run(vector_a())) and np.array_equal(hb.reshape(7, 7, 18), oracle.run(vector_b()))
 
 
 @pytest.mark.parametrize("hw", [(8, 8), (8, 16), (24, 16), (32, 32), (40, 56), (56, 64), (64, 64), (16, 128)])
@@ -140,8 +149,12 @@ def test_fused_program_other_resolutions(yf, oracle, hw):
     from fused_emulator import run_fused
     H, W = hw
     F = yf.fused_program(H, W)
-    img = np.random.default_rng(H * 1000 + W).integers(-128, 128, (H, W, 3), dtype=np.int8)
+    rng = np.random.default_rng(H * 1000 + W)
+    img, img2 = rng.integers(-128, 128, (2, H, W, 3), dtype=np.int8)
     assert np.array_equal(run_fused(F, img, 1).reshape(H // 8, W // 8, 18), oracle.run(img))
+    if F["split"] < len(F["phases"]):
+        ha, hb = run_fused(F, [img, img2], 2)
+        assert np.array_equal(ha.reshape(H // 8, W // 8, 18), oracle.run(img)) and np.array_equal(hb.reshape(H // 8, W // 8, 18), oracle.run(img2))
 
 
 def test_fused_program_limits(yf):

@@ -25,19 +25,34 @@ net.enqueue(x, y, n); net.sync()
 st = net.fused_trace(False, read=True)
 steps = net.steps()
 F = yf.fused_program(56, 56)
-np_ = len(steps)
-for im in range(2 if n > 296 else 1):
-    base = im * (np_ + 1)
-    tot = st[base + np_] - st[base]
-    print("n=%d image #%d of CTA 0: total cycles %d" % (n, im, tot))
-    for i, s in enumerate(steps):
-        d = st[base + i + 1] - st[base + i]
-        print("  %-14s kind %d rows %4d cout %2d  %7d cyc  %5.1f%%" % (s["name"], s["kind"], F["phases"][i]["rows_out"], F["phases"][i]["cout"], d, 100.0 * d / tot))
-inner = st[96:108]
-tph = int(os.environ.get("YF_B200_TRACE_PHASE", "1"))
-if F["phases"][tph]["kind"] == 1:
-    print("phase %d (conv) thread 0: params there -> MMAs committed %d | housekeeping %d | -> accumulators ready %d | epilogue %d | fence %d | barrier %d" % (
-        tph, inner[1] - inner[0], inner[2] - inner[1], inner[3] - inner[2], inner[4] - inner[3], inner[10] - inner[4], inner[11] - inner[10]))
-elif F["phases"][tph]["kind"] == 2:
-    print("phase %d (depthwise) thread 0: entry->setup %d | loop %d | fence %d | barrier %d" % (tph, inner[1] - inner[0], inner[8] - inner[1], inner[10] - inner[8], inner[11] - inner[10]))
+nph, split = len(steps), F["split"]
+# phase order of CTA 0: front(image 0), front(image 1), back(pair), ... (csrc/yf_fused.cu advance_phase); the kernel
+# stamps clock64() at the start of its first 80 phases and once at the end
+slots = 148 * 3
+grid = min(n, slots)
+my_images = (n + grid - 1) // grid
+seq, p, k = [], 0, 0
+while k < my_images and len(seq) < 79:
+    seq.append((p, k))
+    if p == split - 1 and split < nph:
+        if (k & 1) or k == my_images - 1:
+            p = split
+        else:
+            p, k = 0, k + 1
+    elif p == nph - 1:
+        p, k = 0, k + 1
+    else:
+        p += 1
+print("n=%d: CTA 0 runs %d image(s); spec kernel %s; phases shown: %d" % (n, my_images, F.get("spec"), len(seq)))
+tot = st[len(seq)] - st[0] if len(seq) < 80 else st[79] - st[0]
+per_kind = {}
+for i, (p, k) in enumerate(seq[:79]):
+    if i + 1 >= 80:
+        break
+    d = st[i + 1] - st[i]
+    s = steps[p]
+    tag = "back " if p >= split else "front"
+    per_kind[tag] = per_kind.get(tag, 0) + d
+    print("  img %d %s %-14s kind %d rows %4d cout %2d  %7d cyc  %5.1f%%" % (k, tag, s["name"], s["kind"], F["phases"][p]["rows_out"], F["phases"][p]["cout"], d, 100.0 * d / max(tot, 1)))
+print("total %d cycles; %s" % (tot, per_kind))
 net.close()
