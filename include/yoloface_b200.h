@@ -25,13 +25,19 @@ AI_API_DECLARE_BEGIN
 
 /* Optional configuration, passed to ai_network_create() as
  *   ai_buffer cfg = AI_BUFFER_OBJ_INIT(AI_BUFFER_FORMAT_U8, 1, 1, sizeof(yf_b200_config), 1, &config);
- * NULL keeps the defaults (environment: YF_B200_DEVICE, YF_B200_CHUNK, YF_B200_TFLITE). */
+ * NULL keeps the defaults (environment: YF_B200_DEVICE, YF_B200_DEVICES, YF_B200_CHUNK, YF_B200_TFLITE). */
 typedef struct yf_b200_config_ {
   uint32_t magic;          /* YF_B200_CONFIG_MAGIC */
   int32_t device;          /* CUDA ordinal; -1 = YF_B200_DEVICE or the current device */
   uint32_t chunk_images;   /* images processed per pipeline chunk; 0 = default */
   uint32_t flags;          /* YF_B200_FLAG_* */
   const char* tflite_path; /* NULL = model embedded in the library */
+  uint32_t device_mask;    /* bit d set = use CUDA device d.  Two or more bits make ONE handle drive several GPUs: the
+                            * images of every ai_network_run / yf_b200_run / yf_b200_detect call with host buffers are
+                            * split into contiguous ranges, one per device (a worker thread + streams per GPU inside the
+                            * library), results land in the caller's buffers at the ranges' offsets; no collective.
+                            * 0 = the single `device` above.  Read only when the ai_buffer announces a struct this large
+                            * (channels = sizeof(yf_b200_config)); environment: YF_B200_DEVICES=all | 0,1,2 */
 } yf_b200_config;
 
 #define YF_B200_FLAG_OBSERVER 0x1u   /* keep every operator's tensor (slower, more memory) */

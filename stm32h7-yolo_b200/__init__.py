@@ -47,7 +47,7 @@ class AiNetworkParams(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("magic", C.c_uint32), ("device", C.c_int32), ("chunk_images", C.c_uint32), ("flags", C.c_uint32),
-                ("tflite_path", C.c_char_p)]
+                ("tflite_path", C.c_char_p), ("device_mask", C.c_uint32)]
 
 
 class Det(C.Structure):
@@ -206,13 +206,13 @@ def plan(height=56, width=56, blob=None):
         L.yf_b200_plan_blob(height, width, bp, what, raw, k)
         tables.append(raw.raw[:k])
     desc["epi"] = np.frombuffer(tables[0], dtype=np.dtype([("add64", "<i8"), ("mult", "<i4"), ("c2", "<i4"), ("e", "<i4"),
-                                                            ("ls", "<i4"), ("sgn_mask", "<i4"), ("pad", "<i4")]))
+                                                            ("ls", "<i4"), ("sgn_mask", "<i4"), ("acc_bound", "<i4")]))
     desc["luts"] = np.frombuffer(tables[1], dtype=np.int8).reshape(-1, 256)
     desc["wblob"] = np.frombuffer(tables[2], dtype=np.uint8)
     return desc
 
 
-EPI_DTYPE = np.dtype([("add64", "<i8"), ("mult", "<i4"), ("c2", "<i4"), ("e", "<i4"), ("ls", "<i4"), ("sgn_mask", "<i4"), ("pad", "<i4")])
+EPI_DTYPE = np.dtype([("add64", "<i8"), ("mult", "<i4"), ("c2", "<i4"), ("e", "<i4"), ("ls", "<i4"), ("sgn_mask", "<i4"), ("acc_bound", "<i4")])
 
 
 def fused_program(height=56, width=56, blob=None):
@@ -238,14 +238,17 @@ def fused_program(height=56, width=56, blob=None):
 class Network:
     """aiInit()/aiRun() of stm32/X-CUBE-AI/App/yoloface.c:188-240, batch-capable."""
 
-    def __init__(self, device=-1, chunk_images=0, observer=False, tflite_path=None, weights=None, mode="auto", st_activations=False):
+    def __init__(self, device=-1, chunk_images=0, observer=False, tflite_path=None, weights=None, mode="auto", st_activations=False,
+                 devices=None):
+        """devices: list of CUDA ordinals driven by this ONE handle (batches of run()/detect()/ai_run() with host
+        buffers are split by image over them); None = the single `device`."""
         L = self.L = lib()
         self.handle = C.c_void_p()
         flags = (YF_B200_FLAG_OBSERVER if observer else 0) | {"auto": 0, "layered": YF_B200_FLAG_LAYERED,
                                                               "fused": YF_B200_FLAG_FUSED_ONLY}[mode]
         flags |= YF_B200_FLAG_ST_ACTIVATIONS if st_activations else 0
         self._cfg = Config(YF_B200_CONFIG_MAGIC, device, chunk_images, flags,
-                           tflite_path.encode() if tflite_path else None)
+                           tflite_path.encode() if tflite_path else None, sum(1 << d for d in devices) if devices else 0)
         cfgbuf = AiBuffer(AI_BUFFER_FORMAT_U8, 1, 1, 1, C.sizeof(Config), C.cast(C.pointer(self._cfg), C.c_void_p), None)
         err = L.ai_network_create(C.byref(self.handle), C.byref(cfgbuf))
         if err.type != 0:

@@ -6,6 +6,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <thread>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -63,6 +67,22 @@ struct PlanDev {
   }
 };
 
+// One persistent host thread per additional GPU of a multi-GPU context ("internally one worker
+// thread + stream per GPU"): it owns the CUDA device selection of its thread and runs the jobs the caller's thread posts.
+struct Worker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int32_t()> job;
+  int32_t result = 0;
+  std::string text;                     // thread-local error text of the job, handed back to the caller
+  bool pending = false, quit = false;
+  explicit Worker(int device);
+  ~Worker() { { std::lock_guard<std::mutex> lk(mu); quit = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+  void post(std::function<int32_t()> j) { { std::lock_guard<std::mutex> lk(mu); job = std::move(j); pending = true; } cv.notify_all(); }
+  int32_t wait(std::string* t) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !pending; }); if (t) *t = text; return result; }
+};
+
 size_t head_bytes(const PlanDev* pd) { const Plan& P = pd->plan; return static_cast<size_t>(P.GH) * P.GW * P.buffers[P.output_buf].C; }
 
 struct Network {
@@ -94,7 +114,8 @@ struct Network {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined host path
   // Kernel lanes: one fused launch covers 256 of the GPU's 296 CTA slots for one image latency, so
   // independent chunks alternate over two streams and the head of one overlaps the tail of the other.
-  static constexpr int kLanes = 4;      // 4 x 256 queued CTAs keep the 444 resident-CTA slots busy
+  static constexpr int kLanes = 8;      // streams created; `lanes` of them are used (YF_B200_LANES, default below)
+  int lanes = 4;
   cudaStream_t lane[kLanes] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {};
   uint64_t lane_seq = 0;
@@ -102,10 +123,19 @@ struct Network {
   ai_buffer rep_in{}, rep_out{};        // I/O descriptors handed out by ai_network_get_report
   uint64_t launches = 0, images = 0;
   float last_ms = 0.f;
+  // Multi-GPU context (yf_b200_config.device_mask / YF_B200_DEVICES): members[0] is this object, the others are
+  // contexts on the other GPUs owned by it and driven by workers[i]; a member's `owner` points back here.
+  std::vector<Network*> members;
+  std::vector<std::unique_ptr<Worker>> workers;
+  Network* owner = nullptr;
   void latch(int type, int code) { if (err.type == AI_ERROR_NONE) { err.type = type; err.code = code; } }
   // Everything the context owns on its device; shared by ai_network_destroy and the failure paths of ai_network_create
   // (the caller has selected n->device).  Safe on a partially constructed object: every handle starts out null.
   ~Network() {
+    workers.clear();                                        // joins the threads before their contexts go away
+    for (size_t i = 1; i < members.size(); ++i) { cudaSetDevice(members[i]->device); delete members[i]; }
+    if (members.size() > 1) cudaSetDevice(device);
+    members.clear();
     plans.clear();
     if (h_err) cudaFreeHost(h_err);
     if (h_small) cudaFreeHost(h_small);
@@ -119,6 +149,25 @@ struct Network {
     if (ev_fork) cudaEventDestroy(ev_fork);
   }
 };
+
+Worker::Worker(int device) {
+  th = std::thread([this, device] {
+    cudaSetDevice(device);
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return pending || quit; });
+      if (quit) return;
+      std::function<int32_t()> j = std::move(job);
+      lk.unlock();
+      g_text.clear();
+      const int32_t r = j();
+      lk.lock();
+      result = r; text = g_text; pending = false;
+      lk.unlock();
+      cv.notify_all();
+    }
+  });
+}
 
 bool make_lanes(Network* n) {
   for (int l = 0; l < Network::kLanes; ++l)
@@ -396,12 +445,12 @@ bool run_chunks(Network* n, PlanDev* pd, const std::vector<DevChunk>& ch) {
     return true;
   }
   if (!cuda_ok(n, cudaEventRecord(n->ev_fork, n->stream), "fork")) return false;
-  for (int l = 0; l < Network::kLanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
+  for (int l = 0; l < n->lanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
   for (size_t i = 0; i < ch.size(); ++i) {
-    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[i % Network::kLanes], true)) return false;
+    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[i % n->lanes], true)) return false;
     n->last_run_n = ch[i].nb;
   }
-  for (int l = 0; l < Network::kLanes; ++l) {
+  for (int l = 0; l < n->lanes; ++l) {
     cudaEventRecord(n->ev_join[l], n->lane[l]);
     if (!cuda_ok(n, cudaStreamWaitEvent(n->stream, n->ev_join[l], 0), "join")) return false;
   }
@@ -432,7 +481,7 @@ bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_hos
   if (pd->busy[s] && !cuda_ok(n, cudaEventSynchronize(pd->ev_d2h[s]), "ring slot wait")) return false;   // slot's previous user has drained
   if (!cuda_ok(n, cudaMemcpyAsync(pd->r_in[s], in_host, nb * in_sz, cudaMemcpyHostToDevice, n->s_h2d), "H2D input", AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
   cudaEventRecord(pd->ev_h2d[s], n->s_h2d);
-  cudaStream_t ks = uses_fused(n, pd) ? n->lane[n->lane_seq++ % Network::kLanes] : n->stream;
+  cudaStream_t ks = uses_fused(n, pd) ? n->lane[n->lane_seq++ % n->lanes] : n->stream;
   cudaStreamWaitEvent(ks, pd->ev_h2d[s], 0);
   if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb, ks, true)) return false;
   cudaEventRecord(pd->ev_comp[s], ks);
@@ -639,6 +688,79 @@ void fill_report(Network* n, ai_network_report* r) {
   r->signature = 0;
 }
 
+// ---- multi-GPU contexts --------------------------------------------------------------------------------------
+bool is_group(const Network* n) { return n->members.size() > 1; }
+
+// Split `count` images into contiguous ranges, one per member; fn(member, first, n) runs on the calling thread for
+// the primary (whose device lock the caller holds) and on the members' worker threads, each under its own device's
+// lock.  Returns the sum of the results, or -1 with the first failing member's error latched on the primary.
+template <class F>
+int32_t group_dispatch(Network* n, uint32_t count, F fn) {
+  const size_t m = n->members.size();
+  std::vector<uint32_t> first(m + 1, 0);
+  for (size_t i = 0; i < m; ++i) first[i + 1] = first[i] + count / static_cast<uint32_t>(m) + (i < count % m ? 1u : 0u);
+  for (size_t i = 1; i < m; ++i) {
+    Network* c = n->members[i];
+    const uint32_t f0 = first[i], cnt = first[i + 1] - first[i];
+    n->workers[i]->post([c, f0, cnt, fn]() -> int32_t {
+      if (!cnt) return 0;
+      std::lock_guard<std::mutex> lk(g_dev_mu[c->device & 63]);
+      cudaSetDevice(c->device);
+      return fn(c, f0, cnt);
+    });
+  }
+  int32_t total = first[1] ? fn(n, 0u, first[1]) : 0;
+  bool ok = total >= 0;
+  for (size_t i = 1; i < m; ++i) {
+    std::string text;
+    const int32_t r = n->workers[i]->wait(&text);
+    Network* c = n->members[i];
+    if (r < 0) {
+      if (ok) { n->latch(c->err.type != AI_ERROR_NONE ? c->err.type : AI_ERROR_INVALID_STATE, c->err.code); set_text("device " + std::to_string(c->device) + ": " + text); }
+      ok = false;
+    } else if (ok) total += r;
+    c->err = ai_error{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+  }
+  cudaSetDevice(n->device);
+  return ok ? total : -1;
+}
+// run fn(member) on every member (settings that all devices must share); false if any fails
+template <class F>
+bool group_each(Network* n, F fn) {
+  bool ok = fn(n);
+  for (size_t i = 1; i < n->members.size(); ++i) {
+    Network* c = n->members[i];
+    n->workers[i]->post([c, fn]() -> int32_t {
+      std::lock_guard<std::mutex> lk(g_dev_mu[c->device & 63]);
+      cudaSetDevice(c->device);
+      return fn(c) ? 0 : -1;
+    });
+  }
+  for (size_t i = 1; i < n->members.size(); ++i) {
+    std::string text;
+    if (n->workers[i]->wait(&text) < 0) {
+      Network* c = n->members[i];
+      if (ok) { n->latch(c->err.type != AI_ERROR_NONE ? c->err.type : AI_ERROR_INVALID_STATE, c->err.code); set_text("device " + std::to_string(c->device) + ": " + text); }
+      c->err = ai_error{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+      ok = false;
+    }
+  }
+  cudaSetDevice(n->device);
+  return ok;
+}
+// host pointers only: a device pointer belongs to one GPU and the whole call then runs there
+bool splittable(const Network* n, const void* in, const void* out, uint32_t count) {
+  return is_group(n) && count >= 2 * n->members.size() && !is_device_ptr(in) && !(out && is_device_ptr(out));
+}
+Network* member_for_ptr(Network* n, const void* p) {
+  if (!is_group(n) || !p) return n;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return n; }
+  if (a.type != cudaMemoryTypeDevice) return n;
+  for (Network* c : n->members) if (c->device == a.device) return c;
+  return n;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -646,15 +768,9 @@ void fill_report(Network* n, ai_network_report* r) {
 // ============================================================================================
 extern "C" {
 
-AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* network_config) {
-  ai_error err{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
-  if (!network) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return err; }
-  *network = AI_HANDLE_NULL;
-  const yf_b200_config* cfg = nullptr;
-  if (network_config && network_config->data) {
-    cfg = static_cast<const yf_b200_config*>(network_config->data);
-    if (cfg->magic != YF_B200_CONFIG_MAGIC) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; set_text("network_config is not a yf_b200_config"); return err; }
-  }
+// one context on one device (dev_forced >= 0 overrides the configured ordinal: members of a multi-GPU context)
+static Network* create_on_device(const yf_b200_config* cfg, int dev_forced, ai_error* perr) {
+  ai_error& err = *perr;
   std::unique_ptr<Network> n(new Network);
   if (cfg && cfg->chunk_images) n->chunk = cfg->chunk_images;
   else if (const char* e = std::getenv("YF_B200_CHUNK")) n->chunk = static_cast<uint32_t>(std::max(1, std::atoi(e)));
@@ -664,39 +780,40 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
   else if (cfg && (cfg->flags & YF_B200_FLAG_FUSED_ONLY)) n->mode = 2;
   else if (const char* e = std::getenv("YF_B200_MODE")) n->mode = !std::strcmp(e, "layered") ? 1 : (!std::strcmp(e, "fused") ? 2 : 0);
   const char* path = cfg && cfg->tflite_path ? cfg->tflite_path : std::getenv("YF_B200_TFLITE");
-  std::string perr; bool ok;
+  std::string perr_text; bool ok;
   if (path && *path) {
     FILE* f = std::fopen(path, "rb");
-    if (!f) { set_text(std::string("cannot open ") + path); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return err; }
+    if (!f) { set_text(std::string("cannot open ") + path); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return nullptr; }
     std::vector<uint8_t> buf; uint8_t tmp[65536]; size_t k;
     while ((k = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + k);
     std::fclose(f);
-    ok = n->model.parse(buf.data(), buf.size(), &perr);
+    ok = n->model.parse(buf.data(), buf.size(), &perr_text);
   } else {
-    ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr);
+    ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr_text);
   }
-  if (!ok) { set_text("model: " + perr); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; return err; }
+  if (!ok) { set_text("model: " + perr_text); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; return nullptr; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
     set_text("no CUDA device: libyoloface_b200 has no CPU path");
-    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return nullptr;
   }
-  int dev = -1;
-  if (cfg && cfg->device >= 0) dev = cfg->device;
-  else if (const char* e = std::getenv("YF_B200_DEVICE")) dev = std::atoi(e);
+  int dev = dev_forced;
+  if (dev < 0 && cfg && cfg->device >= 0) dev = cfg->device;
+  else if (dev < 0) { if (const char* e = std::getenv("YF_B200_DEVICE")) dev = std::atoi(e); }
   if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
-  if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return err; }
+  if (dev >= ndev) { set_text("CUDA device ordinal out of range"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_OUT_OF_RANGE; return nullptr; }
   std::lock_guard<std::mutex> lk(g_dev_mu[dev & 63]);
   cudaDeviceProp prop{};
   int prev_dev = -1;
   if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
   if (cudaSetDevice(dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
-    set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+    set_text("cannot select CUDA device"); err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return nullptr;
   }
   if (prop.major != 10) {
     set_text("libyoloface_b200 carries sm_100a code only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
-    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return nullptr;
   }
   n->device = dev; n->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&n->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -708,11 +825,63 @@ AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* net
     set_text(std::string("CUDA setup: ") + cudaGetErrorString(cudaGetLastError()));
     n.reset();                                              // ~Network releases whatever was created, on this device
     if (prev_dev >= 0) cudaSetDevice(prev_dev);             // leave the caller's current device as it was
-    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return err;
+    err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_NETWORK; return nullptr;
   }
   n->stream = n->own_stream;
-  { std::lock_guard<std::mutex> rk(g_mu); g_nets.push_back(n.get()); }
-  *network = n.release();
+  if (const char* e = std::getenv("YF_B200_LANES")) n->lanes = std::max(1, std::min(static_cast<int>(Network::kLanes), std::atoi(e)));
+  if (dev_forced >= 0 && prev_dev >= 0) cudaSetDevice(prev_dev);   // members are driven by their own threads
+  return n.release();
+}
+
+// devices of a multi-GPU context: yf_b200_config.device_mask (when the caller's struct carries it), else
+// YF_B200_DEVICES = "all" | "0,1,3"; empty = single device
+static std::vector<int> group_devices(const ai_buffer* network_config, const yf_b200_config* cfg) {
+  std::vector<int> devs;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return devs; }
+  uint64_t mask = 0;
+  const size_t cfg_bytes = network_config ? static_cast<size_t>(network_config->height) * network_config->width * network_config->channels : 0;
+  if (cfg && cfg_bytes >= offsetof(yf_b200_config, device_mask) + sizeof(uint32_t)) mask = cfg->device_mask;
+  if (!mask && !(cfg && cfg->device >= 0)) {
+    if (const char* e = std::getenv("YF_B200_DEVICES")) {
+      if (!std::strcmp(e, "all")) mask = ndev >= 64 ? ~0ull : ((1ull << ndev) - 1);
+      else for (const char* p = e; *p;) { char* q; long d = std::strtol(p, &q, 10); if (q == p) break; if (d >= 0 && d < 64) mask |= 1ull << d; p = *q ? q + 1 : q; }
+    }
+  }
+  for (int d = 0; d < ndev && d < 64; ++d) if (mask & (1ull << d)) devs.push_back(d);
+  if (devs.size() < 2) devs.clear();
+  return devs;
+}
+
+AI_API_ENTRY ai_error ai_network_create(ai_handle* network, const ai_buffer* network_config) {
+  ai_error err{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+  if (!network) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_PTR; return err; }
+  *network = AI_HANDLE_NULL;
+  const yf_b200_config* cfg = nullptr;
+  if (network_config && network_config->data) {
+    cfg = static_cast<const yf_b200_config*>(network_config->data);
+    if (cfg->magic != YF_B200_CONFIG_MAGIC) { err.type = AI_ERROR_CREATE_FAILED; err.code = AI_ERROR_CODE_INVALID_FORMAT; set_text("network_config is not a yf_b200_config"); return err; }
+  }
+  const std::vector<int> devs = group_devices(network_config, cfg);
+  Network* n = create_on_device(cfg, devs.empty() ? -1 : devs[0], &err);
+  if (!n) return err;
+  if (!devs.empty()) {
+    // ONE handle, several GPUs: the caller keeps the reference's single-handle call sequence (yoloface.c:188-240)
+    // and the batch of every run is split by image over the devices (no collective: SURVEY.md 8e).
+    cudaSetDevice(devs[0]);
+    n->members.push_back(n);
+    n->workers.emplace_back(nullptr);
+    for (size_t i = 1; i < devs.size(); ++i) {
+      Network* c = create_on_device(cfg, devs[i], &err);
+      if (!c) { cudaSetDevice(devs[0]); delete n; return err; }
+      c->owner = n;
+      n->members.push_back(c);
+      n->workers.emplace_back(new Worker(devs[i]));
+    }
+    cudaSetDevice(devs[0]);
+  }
+  { std::lock_guard<std::mutex> rk(g_mu); g_nets.push_back(n); }
+  *network = n;
   return err;
 }
 
@@ -724,11 +893,15 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   cudaStreamSynchronize(n->stream);
   for (int l = 0; l < Network::kLanes; ++l) cudaStreamSynchronize(n->lane[l]);
   cudaStreamSynchronize(n->s_d2h);
-  for (auto& kv : n->plans) {
-    if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
+  for (Network* c : n->members.empty() ? std::vector<Network*>{n} : n->members) {
+    if (c != n) { cudaSetDevice(c->device); cudaDeviceSynchronize(); }
+    for (auto& kv : c->plans) {
+      if (g_active_epi[c->device & 63] == kv.second.get()) g_active_epi[c->device & 63] = nullptr;
+    }
   }
+  cudaSetDevice(n->device);
   { std::lock_guard<std::mutex> rk(g_mu); g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end()); }
-  delete n;                                                 // ~Network
+  delete n;                                                 // ~Network (members and their worker threads included)
   return AI_HANDLE_NULL;
 }
 
@@ -762,16 +935,20 @@ AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params*
     const size_t asize = static_cast<size_t>(abuf->height) * abuf->width * abuf->channels;
     if (abuf->data && asize < AI_NETWORK_DATA_ACTIVATIONS_SIZE) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_ACTIVATIONS); set_text("activations buffer too small"); return false; }
   }
-  n->blob.assign(blob, blob + need);
   cudaSetDevice(n->device);
-  for (auto& kv : n->plans) {
-    if (g_active_epi[n->device & 63] == kv.second.get()) g_active_epi[n->device & 63] = nullptr;
-  }
-  n->plans.clear();
-  if (!get_plan(n, n->H, n->W)) return false;
-  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "init synchronize", AI_ERROR_INIT_FAILED)) return false;
-  n->initialized = true;
-  return true;
+  const std::vector<uint8_t> weights(blob, blob + need);
+  auto init_one = [weights](Network* c) {
+    c->blob = weights;
+    for (auto& kv : c->plans) {
+      if (g_active_epi[c->device & 63] == kv.second.get()) g_active_epi[c->device & 63] = nullptr;
+    }
+    c->plans.clear();
+    if (!get_plan(c, c->H, c->W)) return false;
+    if (!cuda_ok(c, cudaStreamSynchronize(c->stream), "init synchronize", AI_ERROR_INIT_FAILED)) return false;
+    c->initialized = true;
+    return true;
+  };
+  return is_group(n) ? group_each(n, init_one) : init_one(n);
 }
 
 static ai_i32 process(ai_handle network, const ai_buffer* input, ai_buffer* output) {
@@ -790,7 +967,19 @@ static ai_i32 process(ai_handle network, const ai_buffer* input, ai_buffer* outp
     if (output->n_batches < input->n_batches) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_BATCH); return 0; }
   }
   cudaSetDevice(n->device);
-  int32_t r = run_images(n, input->data, output ? output->data : nullptr, input->n_batches, false, nullptr);
+  int32_t r;
+  if (splittable(n, input->data, output ? output->data : nullptr, input->n_batches)) {
+    PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return 0;
+    const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
+    const int8_t* in = static_cast<const int8_t*>(input->data); int8_t* out = output ? static_cast<int8_t*>(output->data) : nullptr;
+    r = group_dispatch(n, input->n_batches, [in, out, in_sz, out_sz](Network* c, uint32_t f0, uint32_t cnt) {
+      return run_images(c, in + f0 * in_sz, out ? out + f0 * out_sz : nullptr, cnt, false, nullptr);
+    });
+  } else {
+    Network* c = member_for_ptr(n, input->data);
+    if (c != n) { std::lock_guard<std::mutex> ck(g_dev_mu[c->device & 63]); cudaSetDevice(c->device); r = run_images(c, input->data, output ? output->data : nullptr, input->n_batches, false, nullptr); cudaSetDevice(n->device); }
+    else r = run_images(n, input->data, output ? output->data : nullptr, input->n_batches, false, nullptr);
+  }
   return r < 0 ? 0 : r;
 }
 
@@ -841,9 +1030,8 @@ AI_API_ENTRY ai_bool ai_network_data_params_get(ai_handle network, ai_network_pa
 AI_API_ENTRY int32_t yf_b200_set_input_size(ai_handle network, int32_t height, int32_t width) {
   YF_NET_OR_FAIL(n, network)
   if (height < 8 || width < 8 || height % 8 || width % 8 || height > 4096 || width > 4096) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_SIZE); return -1; }
-  n->H = height; n->W = width;
-  if (n->initialized && !get_plan(n, n->H, n->W)) return -1;
-  return 0;
+  auto set_one = [height, width](Network* c) { c->H = height; c->W = width; return !(c->initialized && !get_plan(c, c->H, c->W)); };
+  return (is_group(n) ? group_each(n, set_one) : set_one(n)) ? 0 : -1;
 }
 
 AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, uint32_t count) {
@@ -852,6 +1040,16 @@ AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, u
   if (!in) { n->latch(AI_ERROR_INVALID_INPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (!out) { n->latch(AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR); return -1; }
   if (count == 0) return 0;
+  if (splittable(n, in, out, count)) {
+    PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+    const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
+    const int8_t* pi = static_cast<const int8_t*>(in); int8_t* po = static_cast<int8_t*>(out);
+    return group_dispatch(n, count, [pi, po, in_sz, out_sz](Network* c, uint32_t f0, uint32_t cnt) {
+      return run_images(c, pi + f0 * in_sz, po + f0 * out_sz, cnt, false, nullptr);
+    });
+  }
+  Network* c = member_for_ptr(n, in);
+  if (c != n) { std::lock_guard<std::mutex> ck(g_dev_mu[c->device & 63]); cudaSetDevice(c->device); const int32_t r = run_images(c, in, out, count, false, nullptr); cudaSetDevice(n->device); return r; }
   return run_images(n, in, out, count, false, nullptr);
 }
 
@@ -952,12 +1150,10 @@ AI_API_ENTRY int32_t yf_b200_decode(ai_handle network, const void* heads, uint32
   return total;
 }
 
-AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t count, float conf_thr, float iou_thr,
-                                    uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det, void* heads_out) {
-  YF_NET_OR_FAIL(n, network)
-  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
-  if (!in || !dets || !counts || !max_det) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
-  if (count == 0) return 0;
+}  // extern "C"
+// inference + decode + NMS of `count` images on ONE context (the caller holds its device's lock and has selected it)
+static int32_t detect_impl(Network* n, const void* in, uint32_t count, float conf_thr, float iou_thr,
+                           uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det, void* heads_out) {
   PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, hsz = head_bytes(pd);
   const bool in_dev = is_device_ptr(in);
@@ -968,11 +1164,12 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
     // neighbours; ONE copy brings all detections back.
     if (!ring_prepare(n, pd) || !ring_wait(n, pd) || !ensure_dets(n, count, max_det)) return -1;   // the slots' head buffers must be idle
     if (!cuda_ok(n, cudaEventRecord(n->ev_fork, n->stream), "fork")) return -1;
-    for (int l = 0; l < Network::kLanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
+    const int nl = std::min(n->lanes, static_cast<int>(PlanDev::kRing));
+    for (int l = 0; l < nl; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
     uint32_t ci = 0;
     for (uint32_t done = 0; done < count; done += pd->cap, ++ci) {
       const uint32_t nb = std::min<uint32_t>(pd->cap, count - done);
-      const int l = static_cast<int>(ci % Network::kLanes);
+      const int l = static_cast<int>(ci % nl);
       int8_t* heads = pd->r_head[l];                           // ring slots 0..3 double as the lanes' head buffers
       if (!run_steps(n, pd, static_cast<const int8_t*>(in) + done * in_sz, heads, nb, n->lane[l], true)) return -1;
       DecodeArgs a{};
@@ -980,7 +1177,7 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
       if (!cuda_ok(n, launch_decode_nms(a, n->lane[l]), "decode_nms")) return -1;
       ++n->launches;
     }
-    for (int l = 0; l < Network::kLanes; ++l) {
+    for (int l = 0; l < nl; ++l) {
       cudaEventRecord(n->ev_join[l], n->lane[l]);
       if (!cuda_ok(n, cudaStreamWaitEvent(n->stream, n->ev_join[l], 0), "join")) return -1;
     }
@@ -1009,6 +1206,34 @@ AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t 
   }
   return total;
 }
+extern "C" {
+
+AI_API_ENTRY int32_t yf_b200_detect(ai_handle network, const void* in, uint32_t count, float conf_thr, float iou_thr,
+                                    uint32_t flags, yf_b200_det* dets, int32_t* counts, uint32_t max_det, void* heads_out) {
+  YF_NET_OR_FAIL(n, network)
+  if (!n->initialized) { n->latch(AI_ERROR_INVALID_STATE, AI_ERROR_CODE_MISSED_INIT); return -1; }
+  if (!in || !dets || !counts || !max_det) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_INVALID_PTR); return -1; }
+  if (count == 0) return 0;
+  if (splittable(n, in, heads_out, count)) {
+    // every device runs inference + decode + NMS on its range of images; only detections (and, if asked for, heads)
+    // come back, each into its range of the caller's arrays -- "only detections are gathered to the host"
+    PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
+    const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, hsz = head_bytes(pd);
+    const int8_t* pi = static_cast<const int8_t*>(in); int8_t* ph = static_cast<int8_t*>(heads_out);
+    return group_dispatch(n, count, [=](Network* c, uint32_t f0, uint32_t cnt) {
+      return detect_impl(c, pi + f0 * in_sz, cnt, conf_thr, iou_thr, flags, dets + static_cast<size_t>(f0) * max_det, counts + f0, max_det,
+                         ph ? ph + f0 * hsz : nullptr);
+    });
+  }
+  Network* c = member_for_ptr(n, in);
+  if (c != n) {
+    std::lock_guard<std::mutex> ck(g_dev_mu[c->device & 63]); cudaSetDevice(c->device);
+    const int32_t r = detect_impl(c, in, count, conf_thr, iou_thr, flags, dets, counts, max_det, heads_out);
+    cudaSetDevice(n->device);
+    return r;
+  }
+  return detect_impl(n, in, count, conf_thr, iou_thr, flags, dets, counts, max_det, heads_out);
+}
 
 AI_API_ENTRY int32_t yf_b200_set_decode_params(ai_handle network, const float* anchors6, float stride) {
   YF_NET_OR_FAIL(n, network)
@@ -1018,6 +1243,7 @@ AI_API_ENTRY int32_t yf_b200_set_decode_params(ai_handle network, const float* a
   }
   if (stride < 0.f) { n->latch(AI_ERROR_INVALID_PARAM, AI_ERROR_CODE_OUT_OF_RANGE); return -1; }
   n->stride = stride;
+  for (size_t i = 1; i < n->members.size(); ++i) { for (int k = 0; k < 6; ++k) n->members[i]->anchors[k] = n->anchors[k]; n->members[i]->stride = stride; }
   return 0;
 }
 
@@ -1086,6 +1312,7 @@ AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* st) {
   YF_NET_OR_FAIL(n, network)
   if (!st) return -1;
   st->kernel_launches = n->launches; st->images = n->images; st->last_run_device_ms = n->last_ms;
+  for (size_t i = 1; i < n->members.size(); ++i) { st->kernel_launches += n->members[i]->launches; st->images += n->members[i]->images; }
   st->device = n->device; st->sm_count = n->sm_count; st->chunk_images = n->chunk;
   auto it = n->plans.find(std::make_pair(n->H, n->W));
   st->steps = it == n->plans.end() ? 0 : static_cast<int32_t>(it->second->plan.steps.size());

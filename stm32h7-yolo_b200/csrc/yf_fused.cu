@@ -210,12 +210,12 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c,
 
 // DEPTHWISE_CONV_2D 3x3
 // requantise the four channels of one word and store it
-__device__ __forceinline__ void dw_store(const int32_t (&acc)[4], const int32_t (&k_mult)[4], const int32_t (&k_c2p)[4], const int32_t (&k_e)[4],
-                                         bool has_lut, const uint8_t* lut, uint8_t* o) {
+__device__ __forceinline__ void dw_store(const int32_t (&acc)[4], const int32_t (&k_bias)[4], const int32_t (&k_mult)[4], const int32_t (&k_c2p)[4],
+                                         const int32_t (&k_e)[4], bool has_lut, const uint8_t* lut, uint8_t* o) {
   uint32_t ow = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
+    const int32_t idx = requant_idx(acc[j], k_bias[j], k_mult[j], k_c2p[j], k_e[j]);
     ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(lut[idx]) : (idx ^ 0x80)) << (8 * j);
   }
   *reinterpret_cast<uint32_t*>(o) = ow;
@@ -228,7 +228,7 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
   int pix = small_div(tid, ph.rcp_nw);
   const int wd = tid - pix * nw, cp = ph.chunks_out * 16, ch0 = wd * 4;
   const uint32_t* w1h = reinterpret_cast<const uint32_t*>(slot + ph.dw_off);
-  const uint8_t* kb = slot + ph.dwepi_off + wd * 16;          // [bias | mult | c2p | e][nw] int4: consecutive words are contiguous
+  const uint8_t* kb = slot + ph.dwepi_off + wd * 16;          // [bias9 | mult | kc | sh][nw] int4 (yf_requant.cuh): consecutive words are contiguous
   const uint8_t* lut = slot + ph.lut_off;
   // The nine one-hot weight vectors stay in the slot (three CTAs per SM leave 80 registers per thread, not room
   // for 36 weight words); every LDS.128 of a tap is shared by the two pixels of a loop step.
@@ -263,8 +263,8 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
     const uint8_t* q = p + dP;
     int oxq = ox + dx;
     if (oxq >= Wout) { oxq -= Wout; q += dWrap; }
-    int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
-    int32_t bcc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+    int32_t acc[4] = {0, 0, 0, 0};
+    int32_t bcc[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       uint32_t xa[3], xb[3];
@@ -286,13 +286,13 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
         bcc[3] = __dp4a(static_cast<int>(xb[kx]), static_cast<int>(w.w), bcc[3]);
       }
     }
-    dw_store(acc, k_mult, k_c2p, k_e, has_lut, lut, o);
-    dw_store(bcc, k_mult, k_c2p, k_e, has_lut, lut, o + dO);
+    dw_store(acc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o);
+    dw_store(bcc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o + dO);
     o += 2 * dO; p = q + dP; ox = oxq + dx;
     if (ox >= Wout) { ox -= Wout; p += dWrap; }
   }
   if (n_it) {
-    int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+    int32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -304,7 +304,7 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
         acc[2] = __dp4a(static_cast<int>(x), static_cast<int>(w.z), acc[2]);
         acc[3] = __dp4a(static_cast<int>(x), static_cast<int>(w.w), acc[3]);
       }
-    dw_store(acc, k_mult, k_c2p, k_e, has_lut, lut, o);
+    dw_store(acc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o);
   }
   YF_STAMP(tp, 8);
 }
@@ -317,8 +317,9 @@ __device__ __forceinline__ uint32_t ev_of(uint32_t x) { return (x ^ 0x80808080u)
 __device__ __forceinline__ uint32_t od_of(uint32_t x) { return (x ^ 0x80808080u) & 0xff00ff00u; }
 __device__ __forceinline__ uint32_t pool_join(uint32_t ev, uint32_t od) { return (ev | od) ^ 0x80808080u; }
 
+// General form (any window / stride): one thread per output of each pass.
 // MAX_POOL_2D (+ QUANTIZE table): separable, max over the in-bounds cells only
-__device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
+__device__ __forceinline__ void pool_phase_loops(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
   const int nw = ph.nw, per = ph.per;
   const bool active = tid < per * nw;
   const int it0 = small_div(tid, ph.rcp_nw), wd = tid - it0 * nw;
@@ -385,6 +386,94 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
       if (ox >= Wout) { ox -= Wout; ++oy; }
     }
   }
+}
+
+// One line of a separable max-pool with window K, stride 2: a thread slides the window along a row (pass 1) or a
+// column (pass 2), keeping the K taps in registers (a ring whose slots are compile-time: the loop body is unrolled over
+// one ring revolution), so every input is loaded once per line -- the window-per-output form loads it K / 2 times.
+// Positions outside [0, len) contribute the identity (0 in the biased form), i.e. the maximum is over in-bounds cells.
+// BIASED_IN: the input already holds x ^ 0x80 per byte (pass 2 reads pass 1's row maxima).  emit(o, biased word).
+template <int K, bool BIASED_IN, class Emit>
+__device__ __forceinline__ void pool_line(const uint8_t* in, int in_step, int len, int pad, int o_begin, int o_end, Emit emit) {
+  constexpr int S = 2, G = K / S;
+  uint32_t ev[K], od[K];
+  auto ld = [&](int x, uint32_t& e, uint32_t& o) {
+    uint32_t v = BIASED_IN ? 0u : 0x80808080u;               // identity
+    if (static_cast<unsigned>(x) < static_cast<unsigned>(len)) v = *reinterpret_cast<const uint32_t*>(in + x * in_step);
+    if (!BIASED_IN) v ^= 0x80808080u;
+    e = v & 0x00ff00ffu; o = v & 0xff00ff00u;
+  };
+  int x = o_begin * S - pad;                                  // first tap of the first window
+#pragma unroll
+  for (int j = 0; j < K - S; ++j) ld(x + j, ev[j], od[j]);
+#pragma unroll 1
+  for (int o = o_begin; o < o_end; o += G) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int t = 0; t < S; ++t) ld(x + K - S + t, ev[(K - S + g * S + t) % K], od[(K - S + g * S + t) % K]);
+      if (o + g < o_end) {
+        uint32_t me = ev[0], mo = od[0];
+#pragma unroll
+        for (int j = 1; j + 1 < K; j += 2) { me = __vimax3_u16x2(me, ev[j], ev[j + 1]); mo = __vimax3_u16x2(mo, od[j], od[j + 1]); }
+        if ((K & 1) == 0) { me = __vmaxu2(me, ev[K - 1]); mo = __vmaxu2(mo, od[K - 1]); }
+        emit(o + g, me | mo);
+      }
+      x += S;
+    }
+  }
+}
+
+// MAX_POOL_2D (+ QUANTIZE table), windows 8 and 4 at stride 2 (the two pools of yoloface): separable, lines in registers.
+// Pass 1: one thread per (input row, 4-channel word, segment of output columns) -> row maxima (biased) in the scratch;
+// pass 2: one thread per (output column, word, segment of output rows) -> table -> chunk-planar output.
+template <int K>
+__device__ __forceinline__ void pool_phase_lines(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
+  const int nw = ph.nw, Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout;
+  const int sws = ph.scratch_ws;
+  {
+    const int lines = Hin * nw, segs = max(1, min(kFusedThreads / lines, (Wout + K / 2 - 1) / (K / 2)));
+    const int seg_len = (Wout + segs - 1) / segs;
+    int t = tid, seg = 0;
+    while (t >= lines && seg < segs) { t -= lines; ++seg; }
+    if (seg < segs) {
+      const int y = small_div(t, ph.rcp_nw), wd = t - y * nw;
+      const uint8_t* in = smem + ph.in_off + wd * ph.in_ws + ((y + 1) * ph.in_wp + 1) * 4;   // cell (y, 0) of the bordered buffer
+      uint8_t* sb = smem + ph.scratch_off + wd * sws + y * Wout * 4;
+      pool_line<K, false>(in, 4, Win, ph.pad_l, seg * seg_len, min(Wout, (seg + 1) * seg_len),
+                          [&](int o, uint32_t m) { *reinterpret_cast<uint32_t*>(sb + o * 4) = m; });
+    }
+  }
+  __syncthreads();
+  {
+    const int lines = Wout * nw, segs = max(1, min(kFusedThreads / lines, (Hout + K / 2 - 1) / (K / 2)));
+    const int seg_len = (Hout + segs - 1) / segs;
+    int t = tid, seg = 0;
+    while (t >= lines && seg < segs) { t -= lines; ++seg; }
+    if (seg < segs) {
+      const int ox = small_div(t, ph.rcp_nw), wd = t - ox * nw;
+      const uint8_t* in = smem + ph.scratch_off + wd * sws + ox * 4;
+      uint8_t* ob = smem + ph.out_off + out_shift + (wd >> 2) * ph.out_cs + (wd & 3) * 4 + ox * 16;
+      const uint8_t* lut = slot + ph.lut_off;
+      const bool has_lut = ph.has_lut != 0;
+      const int row16 = Wout * 16;
+      pool_line<K, true>(in, Wout * 4, Hin, ph.pad_t, seg * seg_len, min(Hout, (seg + 1) * seg_len), [&](int o, uint32_t m) {
+        if (has_lut)
+          m = static_cast<uint32_t>(lut[m & 0xff]) | (static_cast<uint32_t>(lut[(m >> 8) & 0xff]) << 8) |
+              (static_cast<uint32_t>(lut[(m >> 16) & 0xff]) << 16) | (static_cast<uint32_t>(lut[m >> 24]) << 24);
+        else
+          m ^= 0x80808080u;
+        *reinterpret_cast<uint32_t*>(ob + o * row16) = m;
+      });
+    }
+  }
+}
+
+__device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
+  // (the line form needs rows * words <= threads for pass 1 and a window / stride it is instantiated for)
+  if (ph.stride == 2 && ph.ksize == 8 && ph.Hin * ph.nw <= kFusedThreads && ph.Wout * ph.nw <= kFusedThreads) pool_phase_lines<8>(ph, smem, slot, tid, out_shift);
+  else if (ph.stride == 2 && ph.ksize == 4 && ph.Hin * ph.nw <= kFusedThreads && ph.Wout * ph.nw <= kFusedThreads) pool_phase_lines<4>(ph, smem, slot, tid, out_shift);
+  else pool_phase_loops(ph, smem, slot, tid, out_shift);
 }
 
 // first conv: every thread builds one A row (3 x 16-byte chunks) of tile 2r + (tid >> 7)
@@ -692,8 +781,9 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   // Pairing: with other launches queued behind this one (`overlapped`) the resident-CTA slots stay full whatever the
   // grid, so every CTA takes two images and pays the back phases once; a launch running alone keeps one image per CTA
   // (shortest latency) until there are more images than slots.
+  static const int pair_env = [] { const char* e = getenv("YF_B200_PAIR"); return e ? atoi(e) : -1; }();   // diagnostics: 0 never, 1 always
   int grid = L.n_img < slots ? L.n_img : slots;
-  if (L.overlapped && F.split < a.nphases) { const int pairs = (L.n_img + 1) / 2; grid = pairs < slots ? pairs : slots; }
+  if ((pair_env < 0 ? L.overlapped : pair_env != 0) && F.split < a.nphases) { const int pairs = (L.n_img + 1) / 2; grid = pairs < slots ? pairs : slots; }
   if (spec) yoloface_fused_spec_kernel<<<grid, kFusedThreads, smem, L.stream>>>(a);
   else yoloface_fused_kernel<<<grid, kFusedThreads, smem, L.stream>>>(a);
   return cudaGetLastError();

@@ -23,10 +23,9 @@ __constant__ EpiCh c_epi[kMaxEpiCh];
 __constant__ EpiChF c_epif[kMaxEpiCh];   // the same channels in the lean form of yf_requant.cuh (zero where it does not apply)
 
 bool epi_lean_form(const EpiCh& k, int32_t* bias) {
-  if (k.ls != 0 || k.e < 1 || k.mult == 0 || (k.add64 - (1LL << 30)) % k.mult != 0) return false;
-  const long long b = (k.add64 - (1LL << 30)) / k.mult;
-  if (b > 0x3fffffffLL || b < -0x40000000LL) return false;
-  *bias = static_cast<int32_t>(b);
+  int32_t w4[4];
+  if (!epi_lean_words(k, w4)) return false;
+  *bias = w4[0] / 512;
   return true;
 }
 
@@ -36,9 +35,9 @@ cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   std::vector<EpiChF> lean(static_cast<size_t>(std::max(n, 1)));   // not static: contexts on different devices upload concurrently
   for (int i = 0; i < n; ++i) {
-    int32_t b = 0;
+    int32_t w4[4];
     lean[i] = EpiChF{};
-    if (epi_lean_form(host[i], &b)) lean[i] = EpiChF{b, host[i].mult, host[i].c2 + (128 << host[i].e), host[i].e};
+    if (epi_lean_words(host[i], w4)) lean[i] = EpiChF{w4[0], w4[1], w4[2], w4[3]};
   }
   e = cudaMemcpyToSymbolAsync(c_epif, lean.data(), sizeof(EpiChF) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
@@ -536,11 +535,11 @@ __global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w1h + t * p.in_pitch + c0));
     w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
   }
-  int32_t k_bias[4], k_mult[4], k_c2p[4], k_e[4];
+  int32_t k_bias[4], k_mult[4], k_c2p[4], k_e[4];                 // bias9 | mult | kc | sh of yf_requant.cuh
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const EpiChF k = c0 + j < p.eo.cout ? c_epif[p.eo.epi_base + c0 + j] : EpiChF{0, 0, 0, 0};
-    k_bias[j] = k.bias; k_mult[j] = k.mult; k_c2p[j] = k.c2p; k_e[j] = k.e;
+    k_bias[j] = k.bias9; k_mult[j] = k.mult; k_c2p[j] = k.kc; k_e[j] = k.sh;
   }
   const uint32_t keep = c0 + 4 <= p.eo.cout ? 0xffffffffu : (c0 < p.eo.cout ? (1u << (8 * (p.eo.cout - c0))) - 1u : 0u);
   const int lim = max(p.eo.cout, p.eo.fill_to);
@@ -579,7 +578,7 @@ __global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int
       int r = pix0 / p.Wout, ox = pix0 - r * p.Wout;
       for (int pi = pix0; pi < npix; pi += per) {
         const int oy = oy0 + r, iy0 = oy * p.stride - p.pad_t, ix0 = ox * p.stride - p.pad_l;
-        int32_t acc[4] = {k_bias[0], k_bias[1], k_bias[2], k_bias[3]};
+        int32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const int iy = iy0 + ky;
@@ -596,7 +595,7 @@ __global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int
         uint32_t ow = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int32_t idx = requant_idx(acc[j], k_mult[j], k_c2p[j], k_e[j]);
+          const int32_t idx = requant_idx(acc[j], k_bias[j], k_mult[j], k_c2p[j], k_e[j]);
           ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(sLut[idx]) : (idx ^ 0x80)) << (8 * j);
         }
         ow &= keep;

@@ -122,6 +122,18 @@ int32_t mbqm_host(int32_t x, int32_t mult, int shift) {
   return (t + half + (t >> 31)) >> rs;                            // == RoundingDivideByPOT
 }
 
+bool epi_lean_words(const EpiCh& k, int32_t out[4]) {
+  if (k.ls != 0 || k.e < 1 || k.e > 13 || k.sgn_mask != -1 || k.mult <= (1 << 30)) return false;
+  if ((k.add64 - (1LL << 30)) % k.mult != 0) return false;
+  const long long b = (k.add64 - (1LL << 30)) / k.mult;           // bias'
+  if (k.acc_bound >= (1 << 22) || b >= (1 << 22) || b <= -(1 << 22)) return false;
+  const long long c2p = static_cast<long long>(k.c2) + (128LL << k.e);
+  const long long kc = 128 + 256 * c2p;
+  if (kc >= (1LL << 30) || kc <= -(1LL << 30)) return false;
+  out[0] = static_cast<int32_t>(b * 512); out[1] = k.mult; out[2] = static_cast<int32_t>(kc); out[3] = 8 + k.e;
+  return true;
+}
+
 static int round_up(int v, int a) { return (v + a - 1) / a * a; }
 static int out_dim(bool same, int in, int k, int s) { return same ? (in + s - 1) / s : (in - k + s) / s; }
 static int pad_before(int in, int k, int s, int out) { int t = (out - 1) * s + k - in; return t > 0 ? t / 2 : 0; }
@@ -261,7 +273,7 @@ struct Builder {
   }
 
   // kernel_util.cc::PopulateConvolutionQuantizationParams, folded for the epilogue (yf_plan.h)
-  bool make_epi(int op, int cout, const std::vector<int64_t>& wsum, Step* s) {
+  bool make_epi(int op, int cout, const std::vector<int64_t>& wsum, const std::vector<int64_t>& wabs, Step* s) {
     const TflOperator& O = m.ops[op];
     const TflTensor& tin = m.tensors[O.in[0]]; const TflTensor& tf = m.tensors[O.in[1]]; const TflTensor& tout = m.tensors[O.out];
     const int32_t* bs = bias(op);
@@ -275,9 +287,12 @@ struct Builder {
       if (e.e > 24 || e.ls > 8) return fail("requant shift out of the folded-epilogue range on op " + std::to_string(op));
       int64_t biasf = static_cast<int64_t>(bs ? bs[c] : 0) - static_cast<int64_t>(zin) * wsum[c];
       if (std::llabs(biasf) > (1LL << 28)) return fail("folded bias too large on op " + std::to_string(op));
+      // (bias' << ls) * mult must stay inside int64 with room for the accumulator's share: |bias' << ls| < 2^31
+      if ((std::llabs(biasf) << e.ls) >= (1LL << 31)) return fail("left-shifted folded bias overflows on op " + std::to_string(op));
       e.add64 = (biasf << e.ls) * static_cast<int64_t>(mult) + (1LL << 30);
       e.c2 = (e.e > 0 ? (1 << (e.e - 1)) : 0) + zout * (1 << e.e);
       e.sgn_mask = e.e > 0 ? -1 : 0;
+      e.acc_bound = static_cast<int32_t>(std::min<int64_t>(0x7fffffff, 128 * wabs[c] + std::llabs(biasf)));
       P.epi.push_back(e);
     }
     return true;
@@ -367,9 +382,11 @@ struct Builder {
     s.Hout = th[O.out]; s.Wout = tw[O.out];
     if (O.padding_same) { s.pad_t += pad_before(s.Hin, kh, s.stride, s.Hout); s.pad_l += pad_before(s.Win, kw, s.stride, s.Wout); }
     const int8_t* w = weights(i);
-    std::vector<int64_t> wsum(cout, 0);
-    for (int o = 0; o < cout; ++o) for (int k = 0; k < kh * kw * cin; ++k) wsum[o] += w[static_cast<size_t>(o) * kh * kw * cin + k];
-    if (!make_epi(i, cout, wsum, &s)) return false;
+    std::vector<int64_t> wsum(cout, 0), wabs(cout, 0);
+    for (int o = 0; o < cout; ++o) for (int k = 0; k < kh * kw * cin; ++k) {
+      const int v = w[static_cast<size_t>(o) * kh * kw * cin + k]; wsum[o] += v; wabs[o] += v < 0 ? -v : v;
+    }
+    if (!make_epi(i, cout, wsum, wabs, &s)) return false;
     s.Npad = round_up(cout, 16);
     const PBuffer& ib = P.buffers[s.in_buf];
     std::vector<uint8_t> img;
@@ -413,12 +430,13 @@ struct Builder {
     int kh = fs[1], kw = fs[2], c = fs[3];
     if (O.depth_mult != 1 || kh != 3 || kw != 3 || O.stride_h != O.stride_w) return fail("depthwise: only 3x3, multiplier 1");
     if (P.buffers[s.in_buf].is_input || s.in_coff != 0) return fail("depthwise on input/concat slot unsupported");
+    if (!concat_view_is_dense(src)) return fail("depthwise on a concat output whose slots are padded apart (op " + std::to_string(i) + ")");
     s.kh = kh; s.kw = kw; s.stride = O.stride_h; s.Cout = c; s.Hout = th[O.out]; s.Wout = tw[O.out];
     if (O.padding_same) { s.pad_t += pad_before(s.Hin, kh, s.stride, s.Hout); s.pad_l += pad_before(s.Win, kw, s.stride, s.Wout); }
     const int8_t* w = weights(i);
-    std::vector<int64_t> wsum(c, 0);
-    for (int t = 0; t < 9; ++t) for (int ch = 0; ch < c; ++ch) wsum[ch] += w[static_cast<size_t>(t) * c + ch];
-    if (!make_epi(i, c, wsum, &s)) return false;
+    std::vector<int64_t> wsum(c, 0), wabs(c, 0);
+    for (int t = 0; t < 9; ++t) for (int ch = 0; ch < c; ++ch) { const int v = w[static_cast<size_t>(t) * c + ch]; wsum[ch] += v; wabs[ch] += v < 0 ? -v : v; }
+    if (!make_epi(i, c, wsum, wabs, &s)) return false;
     // one-hot dp4a words: word[tap][ch] = (uint8)w << 8*(ch%4)
     int cp = P.buffers[s.in_buf].CP;
     std::vector<uint8_t> img(static_cast<size_t>(9) * cp * 4, 0);
@@ -437,6 +455,7 @@ struct Builder {
     s.name = "maxpool_" + std::to_string(i);
     int src; if (!resolve_input(O, &s, &src)) return false;
     if (P.buffers[s.in_buf].is_input || s.in_coff != 0) return fail("maxpool on input/concat slot unsupported");
+    if (!concat_view_is_dense(src)) return fail("maxpool on a concat output whose slots are padded apart (op " + std::to_string(i) + ")");
     if (O.stride_h != O.stride_w) return fail("anisotropic stride");
     s.kh = O.filter_h; s.kw = O.filter_w; s.stride = O.stride_h; s.Cout = s.Cin; s.Hout = th[O.out]; s.Wout = tw[O.out];
     if (O.padding_same) { s.pad_t = pad_before(s.Hin, s.kh, s.stride, s.Hout); s.pad_l = pad_before(s.Win, s.kw, s.stride, s.Wout); }
@@ -457,6 +476,15 @@ struct Builder {
   // concat bookkeeping: output tensor -> list of (physical channel offset, channels)
   std::map<int, std::vector<std::pair<int, int>>> concat_slots;
   bool consumers_are_concat_slots(int t) const { return concat_slots.count(t) != 0; }
+  // Only the 1x1 conv maps physical to logical channels (p2l); every other reader needs the concat view to be the
+  // plain channel sequence, i.e. slot k must start where slot k-1 ends.
+  bool concat_view_is_dense(int t) const {
+    auto it = concat_slots.find(t);
+    if (it == concat_slots.end()) return true;
+    int next = 0;
+    for (const auto& sl : it->second) { if (sl.first != next) return false; next = sl.first + sl.second; }
+    return true;
+  }
   bool plan_concats() {
     for (size_t i = 0; i < m.ops.size(); ++i) {
       const TflOperator& O = m.ops[i]; if (O.opcode != OP_CONCATENATION) continue;
@@ -553,8 +581,8 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   const int ns = static_cast<int>(P.steps.size());
   if (ns > kFusedMaxPhases) return no("too many steps");
   for (const EpiCh& e : P.epi) {
-    if (e.e < 1 || e.ls != 0) return no("requant shift outside the fused epilogue's range");
-    if (e.mult == 0 || (e.add64 - (1LL << 30)) % e.mult != 0) return no("requant addend is not bias * multiplier + 2^30");
+    int32_t w4[4];
+    if (!epi_lean_words(e, w4)) return no("a channel's requantisation is outside the lean epilogue's range (shift, multiplier or accumulator bound)");
   }
   // live range of every buffer: first writer .. last reader (in step order)
   const int nb = static_cast<int>(P.buffers.size());
@@ -767,15 +795,11 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     // block: [weights][table][depthwise constants]
     std::vector<uint8_t> blk;
     auto put = [&](const void* src, size_t n) { size_t o = blk.size(); blk.resize((o + n + 15) & ~size_t(15), 0); std::memcpy(blk.data() + o, src, n); return static_cast<int>(o); };
-    // The 64-bit addend of the folded requant is bias' * mult + 2^30 (no left shift on this path), so the
-    // kernel adds the int32 bias' to the accumulator instead and keeps 16 bytes per channel.
-    auto bias_of = [&](const EpiCh& k) { return static_cast<int32_t>((k.add64 - (1LL << 30)) / k.mult); };
-    auto put_epi = [&]() {     // {bias', mult, c2p = c2 + (128 << e), e} per output channel, padded to whole chunks
+    auto put_epi = [&]() {     // lean requant constants (epi_lean_words) per output channel, padded to whole chunks
       std::vector<uint8_t> e(static_cast<size_t>(ph.chunks_out) * 16 * 16, 0);
       for (int c = 0; c < s.Cout; ++c) {
-        const EpiCh& k = P.epi[s.epi_base + c]; uint8_t* b = e.data() + static_cast<size_t>(c) * 16;
-        const int32_t c2p = k.c2 + (128 << k.e), bf = bias_of(k);
-        std::memcpy(b, &bf, 4); std::memcpy(b + 4, &k.mult, 4); std::memcpy(b + 8, &c2p, 4); std::memcpy(b + 12, &k.e, 4);
+        int32_t w4[4]; epi_lean_words(P.epi[s.epi_base + c], w4);
+        std::memcpy(e.data() + static_cast<size_t>(c) * 16, w4, 16);
       }
       return put(e.data(), e.size());
     };
@@ -799,16 +823,14 @@ bool build_fused(const Plan& P, FusedProgram* F) {
       ph.epi_off = put_epi();
     } else if (s.kind == STEP_DW) {
       ph.dw_off = put(P.wblob.data() + s.w_off, s.w_bytes);             // [9][CP] one-hot words
-      // four arrays [bias' | mult | c2p | e], each [nw words][4 channels] int32, c2p = c2 + (128 << e): the threads of
+      // four arrays [bias9 | mult | kc | sh] (epi_lean_words), each [nw words][4 channels] int32: the threads of
       // a warp (consecutive words) read consecutive 16-byte groups of one array
       const size_t arr = static_cast<size_t>(ph.nw) * 16;
       std::vector<uint8_t> e(arr * 4, 0);
       for (int c = 0; c < s.Cout; ++c) {
-        const EpiCh& k = P.epi[s.epi_base + c];
+        int32_t w4[4]; epi_lean_words(P.epi[s.epi_base + c], w4);
         uint8_t* b = e.data() + static_cast<size_t>(c) * 4;
-        const int32_t c2p = k.c2 + (128 << k.e), bf = bias_of(k);
-        std::memcpy(b, &bf, 4); std::memcpy(b + arr, &k.mult, 4);
-        std::memcpy(b + 2 * arr, &c2p, 4); std::memcpy(b + 3 * arr, &k.e, 4);
+        for (int f = 0; f < 4; ++f) std::memcpy(b + f * arr, &w4[f], 4);
       }
       ph.dwepi_off = put(e.data(), e.size());
     }

@@ -58,9 +58,12 @@ struct alignas(16) EpiCh {
   int32_t e;
   int32_t ls;
   int32_t sgn_mask;
-  int32_t pad_;
+  int32_t acc_bound;            // max |acc + bias'| over every possible int8 input: 128 * sum|w| + |bias'| (saturated)
 };
 static_assert(sizeof(EpiCh) == 32, "EpiCh layout");
+// The 16-byte form the kernels' lean epilogues evaluate (yf_requant.cuh): {bias' << 9, m, 2^7 + 256 * c2p, 8 + e}.
+// False when the channel needs the general form (left shift, e outside 1..13, m == 2^30, |acc + bias'| >= 2^22).
+bool epi_lean_words(const EpiCh& k, int32_t out[4]);
 
 // ADD (add.cc::Prepare): left_shift 20, three Q31 multipliers
 struct AddParams {

@@ -1,8 +1,15 @@
 // yf_requant.cuh -- the folded TFLite requantisation as both kernel families use it (device code only).
 //
 //   y = clamp(RoundingDivideByPOT(SaturatingRoundingDoublingHighMul(acc + bias', m), e) + zp_out)
-// with the identities of DESIGN.md section 2:  t = ((acc + bias') * m + 2^30) >> 31;  y = (t + c2 + (t >> 31)) >> e.
-// Valid for e >= 1 and no left shift (checked on the host before a kernel is given this form).
+// With x = acc + bias' (|x| < 2^22, checked on the host from the weights: x * 512 fits an int32) and 2^30 < m < 2^31:
+//   t  = (x*m + 2^30) >> 31                      SRDHM
+//      = (h + 2^7) >> 8        with h = (x * 512 * m) >> 32 = mulhi(x << 9, m)       (nested floor divisions)
+//   y' = (t + c2p - [t < 0]) >> e                RoundingDivideByPOT + zp_out + 128 (c2p = 2^(e-1) + (zp_out + 128) << e)
+//      = (h + 2^7 + 256 * c2p - 256 * [x < 0]) >> (8 + e)                            ([t < 0] == [x < 0] because m > 2^30)
+// i.e. IMAD (x << 9 from the raw accumulator and the pre-shifted bias), IMAD.HI with the constant folded into its addend,
+// one sign correction, one shift, one clamp -- and no 64-bit product (IMAD.WIDE issues at a quarter of the IMAD rate on
+// this part, IMAD.HI at half: tools/microbench/pipes.cu).  tests/test_oracle_golden.py proves the identity against
+// the literal TFLite form with Python integers.  Valid for 1 <= e <= 13 and no left shift (epi_lean_form, on the host).
 #pragma once
 #include <stdint.h>
 
@@ -11,15 +18,23 @@
 namespace yf {
 
 // per-channel requant constants as they travel in the parameter blocks (yf_plan.cc::build_fused)
-struct alignas(16) EpiChF { int32_t bias; int32_t mult; int32_t c2p; int32_t e; };
+struct alignas(16) EpiChF { int32_t bias9; int32_t mult; int32_t kc; int32_t sh; };   // bias' << 9 | m | 2^7 + 256 * c2p | 8 + e
 static_assert(sizeof(EpiChF) == 16, "EpiChF layout");
 
 // ---- fixed-point pieces -------------------------------------------------------------------------
-// returns the int8 result + 128 clamped to [0,255]; acc already holds the folded bias; c2p = half + (zp_out + 128) << e; needs e >= 1
-__device__ __forceinline__ int32_t requant_idx(int32_t acc, int32_t mult, int32_t c2p, int32_t e) {
-  const long long p = static_cast<long long>(acc) * static_cast<long long>(mult) + (1ll << 30);
-  const int32_t t = static_cast<int32_t>(p >> 31);
-  return __vimin_s32_relu((t + c2p + (t >> 31)) >> e, 255);
+// returns the int8 result + 128 clamped to [0,255] (a table index); acc is the raw accumulator (no bias)
+// (written in PTX so that the sign correction stays folded into the IMAD.HI addend: IMAD, SHF, IMAD, IMAD.HI, SHF, VIMNMX --
+//  left to itself the compiler re-associates it into eight instructions)
+__device__ __forceinline__ int32_t requant_idx(int32_t acc, int32_t bias9, int32_t mult, int32_t kc, int32_t sh) {
+  int32_t y;
+  asm("{\n\t.reg .s32 a, sg, hi, u;\n\t"
+      "mad.lo.s32 a, %1, 512, %2;\n\t"         // a = (acc + bias') << 9
+      "shr.s32 sg, a, 31;\n\t"                 // -[a < 0]
+      "mad.lo.s32 hi, sg, 256, %4;\n\t"        // 2^7 + 256 * c2p - 256 * [a < 0]
+      "mad.hi.s32 u, a, %3, hi;\n\t"           // mulhi(a, m) + ...
+      "shr.s32 %0, u, %5;\n\t}"
+      : "=r"(y) : "r"(acc), "r"(bias9), "r"(mult), "r"(kc), "r"(sh));
+  return __vimin_s32_relu(y, 255);
 }
 __device__ __forceinline__ int32_t mbqm_f(int32_t x, int32_t m, int s) {
   const long long ab = static_cast<long long>(x) * static_cast<long long>(m);
@@ -47,7 +62,7 @@ __device__ __forceinline__ void requant_words(const uint32_t (&v)[16], const Epi
 #pragma unroll
   for (int c = 0; c < NW * 4; ++c) {
     const EpiChF k = ek[c];
-    idx[c] = requant_idx(static_cast<int32_t>(v[c]) + k.bias, k.mult, k.c2p, k.e);
+    idx[c] = requant_idx(static_cast<int32_t>(v[c]), k.bias9, k.mult, k.kc, k.sh);
   }
 #pragma unroll
   for (int wi = 0; wi < NW; ++wi) {

@@ -12,6 +12,19 @@ import numpy as np
 from plan_emulator import lut_apply, mbqm, requant
 
 
+def lean_to_epi(bias9, mult, kc, sh, dtype):
+    """the kernels' 16-byte requant constants (csrc/yf_requant.cuh: bias' << 9, m, 2^7 + 256 * c2p, 8 + e) -> EpiCh records"""
+    n = len(mult)
+    epi = np.zeros(n, dtype)
+    assert np.all(bias9 % 512 == 0) and np.all((kc - 128) % 256 == 0) and np.all(sh >= 9)
+    epi["mult"] = mult
+    epi["add64"] = (bias9.astype(np.int64) // 512) * mult.astype(np.int64) + (1 << 30)
+    epi["e"] = sh - 8
+    epi["c2"] = (kc.astype(np.int64) - 128) // 256 - (128 << epi["e"].astype(np.int64))
+    epi["sgn_mask"] = -1
+    return epi
+
+
 def run_fused(F, img, seed=0):
     """One image (a pair holding only image A) or a list of two images (front phases twice, back phases once on the
     tall pair image).  Returns the head, or the list of two heads."""
@@ -83,12 +96,9 @@ def _phase(F, ph, smem, rng, params, epi_all, heads, shift, pair_b):
                     for ky in range(3):
                         A[r, ky * 16:ky * 16 + 9] = flat[2 * oy + ky, (2 * ox) * 3:(2 * ox) * 3 + 9]
             acc = A @ wmat
-            raw = slot[ph["epi_off"]:ph["epi_off"] + cout * 16].reshape(cout, 16)      # constants travel in the block: {bias', mult, c2p, e}
-            epi = np.zeros(cout, epi_all.dtype)
-            epi["mult"] = raw[:, 4:8].copy().view("<i4").reshape(-1)
-            epi["add64"] = raw[:, 0:4].copy().view("<i4").reshape(-1).astype(np.int64) * epi["mult"].astype(np.int64) + (1 << 30)
-            epi["e"] = raw[:, 12:16].copy().view("<i4").reshape(-1)
-            epi["c2"] = raw[:, 8:12].copy().view("<i4").reshape(-1) - (128 << epi["e"]); epi["sgn_mask"] = -1
+            raw = slot[ph["epi_off"]:ph["epi_off"] + cout * 16].reshape(cout, 16)      # constants travel in the block: {bias' << 9, mult, kc, 8 + e}
+            epi = lean_to_epi(raw[:, 0:4].copy().view("<i4").reshape(-1), raw[:, 4:8].copy().view("<i4").reshape(-1),
+                              raw[:, 8:12].copy().view("<i4").reshape(-1), raw[:, 12:16].copy().view("<i4").reshape(-1), epi_all.dtype)
             ref = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
             assert all(np.array_equal(epi[f], ref[f]) for f in ("add64", "mult", "e", "c2"))
             y = np.clip(requant(acc[:, :cout], epi), -128, 127)
@@ -105,14 +115,8 @@ def _phase(F, ph, smem, rng, params, epi_all, heads, shift, pair_b):
             for c in range(cp):
                 w[:, c] = ((w1h[:, c] >> (8 * (c % 4))) & 0xFF).astype(np.uint8).view(np.int8)
             nch = ph["nw"] * 4
-            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + nch * 16].copy().view("<i4").reshape(4, nch)   # [bias' | mult | c2p | e][nw*4]
-            epi = np.zeros(nch, epi_all.dtype)
-            epi["mult"] = raw[1]
-            epi["add64"] = raw[0].astype(np.int64) * raw[1].astype(np.int64) + (1 << 30)
-            epi["e"] = raw[3]
-            epi["c2"] = raw[2] - (128 << epi["e"])
-            epi["sgn_mask"] = -1
-            epi = epi[:cout]
+            raw = slot[ph["dwepi_off"]:ph["dwepi_off"] + nch * 16].copy().view("<i4").reshape(4, nch)   # [bias9 | mult | kc | sh][nw*4]
+            epi = lean_to_epi(raw[0][:cout], raw[1][:cout], raw[2][:cout], raw[3][:cout], epi_all.dtype)
             ref = epi_all[ph["epi_base"]:ph["epi_base"] + cout]
             assert all(np.array_equal(epi[f], ref[f]) for f in ("add64", "mult", "e", "c2"))
             H, W, Ho, Wo, st = ph["Hin"], ph["Win"], ph["Hout"], ph["Wout"], ph["stride"]

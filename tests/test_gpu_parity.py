@@ -193,6 +193,68 @@ def test_decode_and_nms_match_oracle(net, oracle, golden):
     assert np.array_equal(c1, c2) and np.array_equal(d1, d2)
 
 
+def synthetic_heads(rng, n, gh, gw):
+    """Heads with many confident candidates: x/y logits uniform, w/h logits bounded (finite boxes), confidence bytes
+    below the range where float32 sigmoid saturates (equal bytes tie exactly, different bytes never do)."""
+    h = rng.integers(-128, 128, (n, gh * gw, 3, 6))
+    h[..., 2:4] = rng.integers(-64, 17, (n, gh * gw, 3, 2))
+    h[..., 4] = rng.integers(-128, 81, (n, gh * gw, 3))
+    return h.reshape(n, gh, gw, 18).astype(np.int8)
+
+
+def check_dets(got, cnt, ref):
+    assert cnt == len(ref), (cnt, len(ref))
+    if len(ref):
+        scale = np.maximum(1.0, np.abs(ref[:, :4]))          # boxes of synthetic heads reach 1e3 pixels: relative tolerance
+        assert np.all(np.abs(got[:cnt, :4] - ref[:, :4]) <= COORD_TOL * scale)
+        assert np.all(np.abs(got[:cnt, 4] - ref[:, 4]) <= CONF_TOL)
+
+
+def test_decode_large_heads_are_not_truncated(yf, oracle):
+    """Rows a13/a14 beyond the 7x7 head (BASELINE config 4: 28x28 = 2,352 candidates): every candidate above the
+    threshold takes part in the NMS -- round 1 kept the first 192 in memory order.  Heads above 8x8 cells run the
+    block-per-image kernel (bitonic sort), the others the warp kernel; both against the oracle, identical keep-sets."""
+    n = yf.Network(chunk_images=64)
+    try:
+        rng = np.random.default_rng(2352)
+        for H, W in ((224, 224), (112, 112), (64, 64), (96, 160)):
+            n.set_input_size(H, W)
+            gh, gw = H // 8, W // 8
+            heads = synthetic_heads(rng, 5, gh, gw)
+            ncand = gh * gw * 3
+            # threshold only: thousands of survivors, order = (conf desc, index asc)
+            dets, counts = n.decode(heads, 0.7, -1.0, False, max_det=ncand)
+            for i in range(len(heads)):
+                ref = oracle.decode_nms(heads[i], 0.7, -1.0, False)
+                check_dets(dets[i], counts[i], ref)
+            if ncand > 192:
+                assert counts.min() > 192, counts              # the old limit is exceeded on every image
+            # greedy NMS on a few hundred survivors (float IoU decisions stay far from ulp-level ties), both area conventions
+            thr = 0.99997 if ncand > 600 else 0.9          # ~ 11 % / 39 % of the candidates
+            for iou, plus_one in ((0.4, False), (0.4, True), (0.1, True)):
+                dets, counts = n.decode(heads, thr, iou, plus_one, max_det=ncand)
+                for i in range(len(heads)):
+                    check_dets(dets[i], counts[i], oracle.decode_nms(heads[i], thr, iou, plus_one))
+            # max_det cuts the kept list, it does not change which boxes lead it
+            dets, counts = n.decode(heads, 0.7, 0.4, True, max_det=40)
+            for i in range(len(heads)):
+                check_dets(dets[i], counts[i], oracle.decode_nms(heads[i], 0.7, 0.4, True, max_det=40))
+        # anchors and stride are parameters of the context, not constants of the kernel
+        n.set_input_size(112, 112)
+        heads = synthetic_heads(rng, 4, 14, 14)
+        anchors = [[5.0, 7.5], [16.0, 11.0], [30.0, 41.0]]
+        n.set_decode_params(anchors, 4.0)
+        dets, counts = n.decode(heads, 0.9, 0.4, False, max_det=588)
+        for i in range(len(heads)):
+            check_dets(dets[i], counts[i], oracle.decode_nms(heads[i], 0.9, 0.4, False, anchors=anchors, stride=4.0))
+        n.set_decode_params([[9, 14], [12, 17], [22, 21]], 0.0)
+        dets, counts = n.decode(heads, 0.9, 0.4, False, max_det=588)
+        for i in range(len(heads)):
+            check_dets(dets[i], counts[i], oracle.decode_nms(heads[i], 0.9, 0.4, False))
+    finally:
+        n.close()
+
+
 def test_rgb565_preprocessing_bit_exact(net, oracle):
     """yoloface.c:26-93 on device."""
     frames = np.random.default_rng(4).integers(0, 256, (9, 112 * 112 * 2), dtype=np.uint8)

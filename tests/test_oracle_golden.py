@@ -138,6 +138,39 @@ def test_fixed_point_primitives_match_python_bigint(oracle, seed):
             assert lib.yfo_rdivpot(x, e) == (x >> e) + (1 if rem > thr else 0)
 
 
+def test_kernel_requant_form_is_exact(oracle):
+    """The 32-bit form the CUDA epilogues evaluate (csrc/yf_requant.cuh):
+        a = (acc + bias') << 9;  u = mulhi(a, m) + 2^7 + 256 * c2p - 256 * [a < 0];  idx = clamp(u >> (8 + e), 0, 255)
+    equals clamp(MultiplyByQuantizedMultiplier(acc + bias', m, -e) + zp_out + 128, 0, 255) of the oracle for every
+    |acc + bias'| < 2^22, 2^30 < m < 2^31, 1 <= e <= 13 -- the ranges csrc/yf_plan.cc::epi_lean_words admits."""
+    rng = np.random.default_rng(2026)
+    lib = oracle.lib
+    edge = [0, 1, -1, 2, -2, 2**22 - 1, -(2**22 - 1), 255, -255, 4096, -4096]
+    n = 0
+    for e in range(1, 14):
+        for m in [2**30 + 1, 2**31 - 1] + [int(v) for v in rng.integers(2**30 + 1, 2**31, 12)]:
+            for zp in (-128, -15, 0, 127, int(rng.integers(-128, 128))):
+                c2p = (1 << (e - 1)) + ((zp + 128) << e)
+                kc = 128 + 256 * c2p
+                # values around every rounding boundary of the two-stage rounding as well as random ones
+                xs = edge + [int(v) for v in rng.integers(-(2**22) + 1, 2**22, 60)]
+                for t in rng.integers(-300, 300, 6):                       # x with SRDHM(x, m) ~ t * 2^e +- half
+                    base = (int(t) << e) + (1 << (e - 1))
+                    x0 = (base << 31) // m
+                    xs += [x0 - 1, x0, x0 + 1, -x0 - 1, -x0, -x0 + 1]
+                for x in xs:
+                    if abs(x) >= 2**22:
+                        continue
+                    a = x * 512
+                    u = ((a * m) >> 32) + kc - (256 if a < 0 else 0)          # mulhi = floor(a * m / 2^32)
+                    got = min(255, max(0, u >> (8 + e)))
+                    want = min(255, max(0, lib.yfo_mbqm(x, m, -e) + zp + 128))
+                    assert got == want, (x, m, e, zp)
+                    assert -2**31 <= u < 2**31 and -2**31 <= a < 2**31
+                    n += 1
+    assert n > 50000
+
+
 def test_quantize_multiplier_known_answers(oracle):
     import ctypes as C
     m, s = C.c_int32(), C.c_int()
