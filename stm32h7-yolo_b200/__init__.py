@@ -255,7 +255,9 @@ class Network:
             raise AiRuntimeError("ai_network_create", err, L.yf_b200_last_error_text().decode())
         # yoloface.c:198-201: weights handle from network_data, caller-owned activations arena
         self._activations = (C.c_uint8 * AI_NETWORK_DATA_ACTIVATIONS_SIZE)()
-        if weights is None:
+        if weights is None and tflite_path:
+            wptr = None                                # a model given by path keeps the weights of its own flatbuffer
+        elif weights is None:
             wptr = L.ai_network_data_weights_get()
         else:
             self._weights = C.create_string_buffer(bytes(weights), len(weights))

@@ -95,6 +95,7 @@ struct Network {
   bool observer = false, step_profiling = false;
   int mode = 0;                         // 0 auto (fused when possible), 1 layer-by-layer, 2 fused only
   bool st_act = false;                  // ST-style LeakyReLU tables instead of TFLite's
+  bool custom_model = false;            // the model came from a file (tflite_path / YF_B200_TFLITE), not from the library
   int H = 56, W = 56;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -115,7 +116,7 @@ struct Network {
   // Kernel lanes: one fused launch covers 256 of the GPU's 296 CTA slots for one image latency, so
   // independent chunks alternate over two streams and the head of one overlaps the tail of the other.
   static constexpr int kLanes = 8;      // streams created; `lanes` of them are used (YF_B200_LANES, default below)
-  int lanes = 4;
+  int lanes = 8;                        // 20 queued 256-image batches: 4 lanes 6.37 M img/s, 6 lanes 6.58 M, 8 lanes 6.62 M (profiles/r02_lanes_pairing.txt)
   cudaStream_t lane[kLanes] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kLanes] = {};
   uint64_t lane_seq = 0;
@@ -788,6 +789,7 @@ static Network* create_on_device(const yf_b200_config* cfg, int dev_forced, ai_e
     while ((k = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + k);
     std::fclose(f);
     ok = n->model.parse(buf.data(), buf.size(), &perr_text);
+    n->custom_model = true;
   } else {
     ok = n->model.parse(yf_embedded_model, yf_embedded_model_len, &perr_text);
   }
@@ -926,17 +928,21 @@ AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params*
     abuf = (params->map_activations.buffer && params->map_activations.size) ? &params->map_activations.buffer[0] : nullptr;
   }
   const uint8_t* blob = resolve_weights(wbuf->data);
-  if (!blob) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); set_text("weights handle is NULL"); return false; }
-  const size_t wsize = static_cast<size_t>(wbuf->height) * wbuf->width * wbuf->channels;
   size_t need = 0; st_blob_layout(n->model, &need);
-  if (wsize < need) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); set_text("weights buffer smaller than the model's blob"); return false; }
+  if (!blob && !n->custom_model) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); set_text("weights handle is NULL"); return false; }
+  // A model given by path (yf_b200_config.tflite_path) carries its own weights: a NULL weights handle keeps them.  A
+  // non-NULL handle must be that model's blob in ST's layout (conv operators in graph order, weights then bias).
+  if (blob) {
+    const size_t wsize = static_cast<size_t>(wbuf->height) * wbuf->width * wbuf->channels;
+    if (wsize < need) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_WEIGHTS); set_text("weights buffer smaller than the model's blob"); return false; }
+  }
   if (abuf) {
     // caller-owned arena: validated like ST's runtime does, but unused (activations live in HBM)
     const size_t asize = static_cast<size_t>(abuf->height) * abuf->width * abuf->channels;
     if (abuf->data && asize < AI_NETWORK_DATA_ACTIVATIONS_SIZE) { n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK_ACTIVATIONS); set_text("activations buffer too small"); return false; }
   }
   cudaSetDevice(n->device);
-  const std::vector<uint8_t> weights(blob, blob + need);
+  const std::vector<uint8_t> weights = blob ? std::vector<uint8_t>(blob, blob + need) : std::vector<uint8_t>();
   auto init_one = [weights](Network* c) {
     c->blob = weights;
     for (auto& kv : c->plans) {
@@ -1372,10 +1378,26 @@ AI_API_ENTRY int32_t yf_b200_set_step_profiling(ai_handle network, int32_t enabl
 }
 
 // ---- plan introspection (host only) ------------------------------------------------------
+// the model the host-only introspection calls describe: YF_B200_TFLITE (a path, re-read on every call) or the embedded one
+static bool host_model(TflModel* m) {
+  std::string e;
+  const char* path = std::getenv("YF_B200_TFLITE");
+  if (path && *path) {
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { set_text(std::string("cannot open ") + path); return false; }
+    std::vector<uint8_t> buf; uint8_t tmp[65536]; size_t k;
+    while ((k = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + k);
+    std::fclose(f);
+    if (!m->parse(buf.data(), buf.size(), &e)) { set_text("model: " + e); return false; }
+    return true;
+  }
+  if (!m->parse(yf_embedded_model, yf_embedded_model_len, &e)) { set_text("model: " + e); return false; }
+  return true;
+}
+
 static bool host_plan(int32_t H, int32_t W, const void* blob, Plan* P) {
-  static TflModel model; static std::once_flag once; static bool ok = false;
-  std::call_once(once, [] { std::string e; ok = model.parse(yf_embedded_model, yf_embedded_model_len, &e); if (!ok) set_text("model: " + e); });
-  if (!ok) return false;
+  TflModel model;
+  if (!host_model(&model)) return false;
   size_t need = 0; st_blob_layout(model, &need);
   std::string perr;
   const bool st = std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS"));
@@ -1429,9 +1451,8 @@ AI_API_ENTRY int64_t yf_b200_plan_json(int32_t H, int32_t W, const void* blob, c
 }
 
 static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedProgram* F) {
-  static TflModel model; static std::once_flag once; static bool ok = false;
-  std::call_once(once, [] { std::string e; ok = model.parse(yf_embedded_model, yf_embedded_model_len, &e); });
-  if (!ok) return false;
+  TflModel model;
+  if (!host_model(&model)) return false;
   size_t need = 0; st_blob_layout(model, &need);
   std::string perr;
   const bool st = std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS"));

@@ -594,7 +594,7 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     if (s.kind != STEP_CONV_IM2COL && P.buffers[s.in_buf].is_input) return no("network input read by a non-im2col step");
     if (P.buffers[s.out_buf].is_output && (s.kind != STEP_CONV1X1 || i != ns - 1)) return no("head not produced by the last 1x1 conv");
     if (s.out_coff % 16 || s.in_coff != 0 || s.add_coff % 16) return no("unaligned channel slot");
-    if ((s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && s.Npad > 48) return no("N > 48");
+    if ((s.kind == STEP_CONV1X1 || s.kind == STEP_CONV_IM2COL) && s.Npad > 64) return no("N > 64");
     if (s.kind == STEP_CONV_IM2COL && s.Npad != 16) return no("first conv with more than 16 output channels");
     death[s.in_buf] = std::max(death[s.in_buf], i);
     if (s.add_buf >= 0) death[s.add_buf] = std::max(death[s.add_buf], i);
