@@ -23,14 +23,16 @@ def pack_detections(dets, counts):
     return dets[keep].reshape(-1, 5), counts
 
 
-def gather_detections(flat, counts, dist=None, dst=0):
+def gather_detections(flat, counts, dist=None, dst=0, group=None):
     """Gather every rank's packed detections on `dst` in image order.  Returns (flat, counts) on dst,
-    None elsewhere.  Without an initialised process group this is the identity (single GPU)."""
+    None elsewhere.  Without an initialised process group this is the identity (single GPU).
+    `group`: the process group to use -- pass a HOST (gloo) group when the default group is NCCL: the detections are
+    already in host memory and go from host to host, no GPU collective is involved."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return flat, counts
     world, rank = dist.get_world_size(), dist.get_rank()
     bucket = [None] * world if rank == dst else None
-    dist.gather_object((flat, counts), bucket, dst=dst)
+    dist.gather_object((flat, counts), bucket, dst=dst, group=group)
     if rank != dst:
         return None
     return (np.concatenate([b[0] for b in bucket], axis=0), np.concatenate([b[1] for b in bucket], axis=0))

@@ -1,14 +1,12 @@
-mkdir -p gpurun_out/r2e
-for cfg in "4 -1" "8 -1" "6 -1" "8 0" "4 0" "8 1"; do
-  set -- $cfg
-  YF_B200_LANES=$1 YF_B200_PAIR=$2 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r2e/bench_l$1_p$2.json 2> gpurun_out/r2e/bench_l$1_p$2.err
-done
-YF_B200_LANES=8 timeout 300 python bench.py --steps 200 --warmup 5 --no-cpu --no-extra > gpurun_out/r2e/bench_l8_s200.json 2>/dev/null
+mkdir -p gpurun_out/r2g
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2g/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2g/pytest.log
+tail -4 gpurun_out/r2g/pytest.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2g/bench.json 2> gpurun_out/r2g/bench.err; echo "bench rc $?"; tail -3 gpurun_out/r2g/bench.err
 python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/r2e/bench_*.json")):
-    try:
-        d=json.load(open(f)); print(f.split("/")[-1], round(d["value"]/1e6,3), round(d["ms_per_step"]*1e3,1), "e2e", round(d["e2e"]["value"]/1e6,3), "serial", round(d["serial"]["value"]/1e6,3), "launch_ms", round(d["roofline"]["launch_ms"],4), "1img_us", round(d["e2e"]["single_image_call_us"],1))
-    except Exception as e: print(f, "ERR", e)
+import json
+d=json.load(open("gpurun_out/r2g/bench.json"))
+print("value", d["value"], d["ms_per_step"], d["value_spread"]); print("e2e", d["e2e"]["value"], d["e2e"]["spread"], d["e2e"]["blocking"]["value"])
+print("clocks", d["clocks"]); print("roofline", d["roofline"]); print("issue", d["roofline_issue"]); print("cpu", d["cpu_baseline"])
+print("config4", d["config4"]); print("config5", d["config5"]); print("config3", d["config3"]); print("extra", d["extra"])
 PY
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:yoloface_fused -s 2 -c 1 -o gpurun_out/r2g/fused_v9_b256 -f python tools/run_once.py 256 fused 3 > gpurun_out/r2g/ncu256.log 2>&1
