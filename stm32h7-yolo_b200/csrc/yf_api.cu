@@ -17,6 +17,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/network.h"
@@ -24,6 +25,7 @@
 #include "../../include/yoloface_b200.h"
 #include "yf_kernels.cuh"
 #include "yf_plan.h"
+#include "yf_requant.cuh"
 
 // the .tflite the reference deploys (yoloface/tflite/yoloface_int8.tflite), embedded at build time
 extern "C" const unsigned char yf_embedded_model[];
@@ -43,7 +45,18 @@ struct PlanDev {
   bool observer = false;
   uint8_t* d_wblob = nullptr;
   uint8_t* d_luts = nullptr;
-  uint8_t* d_arena = nullptr;
+  uint8_t* d_arena = nullptr;           // activation arena of lane 0 (= d_arena_l[0])
+  // Layer-by-layer path: independent chunks run side by side on up to kLayerLanes streams, each with its own arena and
+  // TMA descriptors (allocated on first use), and every (input, output, images, lane) combination is captured once in
+  // a CUDA graph so that a chunk costs one graph launch instead of 26 kernel launches.
+  static constexpr int kLayerLanes = 4;
+  uint8_t* d_arena_l[kLayerLanes] = {};
+  std::vector<CUtensorMap> tmaps_l[kLayerLanes];
+  struct GraphKey { const void* in; void* out; uint32_t nb; int lane;
+                    bool operator<(const GraphKey& o) const { return std::tie(in, out, nb, lane) < std::tie(o.in, o.out, o.nb, o.lane); } };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  EpiCh* d_epi = nullptr;               // this plan's requant tables (general and 16-byte form)
+  EpiChF* d_epif = nullptr;
   int8_t* d_in = nullptr;               // staging of the synchronous paths for host inputs [cap,H,W,3] (never a ring slot)
   int8_t* d_head = nullptr;             // staging of the synchronous paths for heads [cap,GH,GW,C]
   static constexpr int kRing = 6;       // pipelined host path: slots of (input, head) staging + events
@@ -61,6 +74,9 @@ struct PlanDev {
   FusedPhase* d_fphases = nullptr;      // this plan's phase descriptors (global memory: nothing is shared between plans)
   bool fused_spec = false;              // the plan is the one the specialised kernel was generated from
   ~PlanDev() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    for (int l = 1; l < kLayerLanes; ++l) cudaFree(d_arena_l[l]);
+    cudaFree(d_epi); cudaFree(d_epif);
     cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams); cudaFree(d_fphases);
     for (int i = 0; i < kRing; ++i) { cudaFree(r_in[i]); cudaFree(r_head[i]); }
     for (int i = 0; i < kRing; ++i) { if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]); if (ev_comp[i]) cudaEventDestroy(ev_comp[i]); if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]); }
@@ -177,15 +193,16 @@ bool make_lanes(Network* n) {
   return cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) == cudaSuccess;
 }
 
-// Locking: g_mu guards the registry of live contexts only.  Work on a device is serialised by that device's mutex
-// (contexts on one GPU share its __constant__ tables and take turns anyway); contexts on different GPUs driven from
-// different host threads run in parallel.  One context must not be used from two threads at once (same as ST).
+// Locking: g_mu guards the registry of live contexts only.  Host-side work on a device is serialised by that device's
+// mutex (API calls are short: they queue work and return, or wait for their own streams); contexts on different GPUs
+// driven from different host threads run in parallel.  No device-side state is shared between contexts -- phase
+// descriptors, requant tables and weights are per plan in global memory -- so two models on one GPU interleave freely.
+// One context must not be used from two threads at once (same as ST).
 std::mutex g_mu;
 std::mutex g_dev_mu[64];
 // ST's runtime has one static context (g_network, network.c:36); a GPU process may want one per
 // device or per configuration, so every create returns a fresh context and all stay valid.
 std::vector<Network*> g_nets;
-const void* g_active_epi[64] = {};      // per device: whose EpiCh table sits in __constant__ memory
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -231,13 +248,42 @@ bool is_pageable_ptr(const void* p) {
   return a.type == cudaMemoryTypeUnregistered;
 }
 
+// arena (cleared once: pad channels of every buffer must read as defined bytes) + TMA descriptors of one layer lane
+bool prepare_layer_lane(Network* n, PlanDev* pd, int lane) {
+  const Plan& P = pd->plan;
+  const size_t per_img = pd->observer ? P.arena_bytes_per_image_observer : P.arena_bytes_per_image;
+  if (!pd->d_arena_l[lane] && !cuda_ok(n, cudaMalloc(&pd->d_arena_l[lane], per_img * pd->cap + 1024), "cudaMalloc arena", AI_ERROR_ALLOCATION_FAILED, AI_ERROR_CODE_NETWORK_ACTIVATIONS)) return false;
+  if (!pd->tmaps_l[lane].empty()) return true;
+  if (!cuda_ok(n, cudaMemsetAsync(pd->d_arena_l[lane], 0, per_img * pd->cap + 1024, n->stream), "clear arena")) return false;
+  // TMA descriptors of the 1x1-conv A operands: 2-D [rows = cap*H*W, CP bytes], box 128 rows x 16 B
+  std::vector<CUtensorMap> tm(P.steps.size());
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_text("cuTensorMapEncodeTiled entry point unavailable"); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return false; }
+  for (size_t i = 0; i < P.steps.size(); ++i) {
+    const Step& s = P.steps[i];
+    if (s.kind != STEP_CONV1X1) continue;
+    const PBuffer& b = P.buffers[s.in_buf];
+    void* base = pd->d_arena_l[lane] + b.offset * pd->cap;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(b.CP), static_cast<cuuint64_t>(pd->cap) * b.H * b.W};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(b.CP)};
+    cuuint32_t box[2] = {16, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_text("cuTensorMapEncodeTiled failed for step " + s.name + " (CUresult " + std::to_string(r) + ")");
+      n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_TENSOR); return false; }
+  }
+  if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "clear arena")) return false;   // the lanes' streams use it next
+  pd->tmaps_l[lane] = std::move(tm);
+  return true;
+}
+
 // ---- plan instantiation ------------------------------------------------------------------
 PlanDev* get_plan(Network* n, int H, int W) {
   auto key = std::make_pair(H, W);
   auto it = n->plans.find(key);
   if (it != n->plans.end() && it->second->observer == n->observer && it->second->cap == n->chunk) return it->second.get();
   if (it != n->plans.end()) {
-    if (g_active_epi[n->device & 63] == it->second.get()) g_active_epi[n->device & 63] = nullptr;
     n->plans.erase(it);
   }
   std::unique_ptr<PlanDev> pd(new PlanDev);
@@ -246,7 +292,6 @@ PlanDev* get_plan(Network* n, int H, int W) {
     set_text("plan: " + perr); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr;
   }
   Plan& P = pd->plan;
-  if (P.epi.size() > static_cast<size_t>(kMaxEpiCh)) { set_text("too many output channels for the constant table"); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_LAYER); return nullptr; }
   pd->cap = n->chunk; pd->observer = n->observer;
   const size_t per_img = n->observer ? P.arena_bytes_per_image_observer : P.arena_bytes_per_image;
   const int al = AI_ERROR_ALLOCATION_FAILED, ac = AI_ERROR_CODE_NETWORK_ACTIVATIONS;
@@ -257,25 +302,15 @@ PlanDev* get_plan(Network* n, int H, int W) {
   if (!cuda_ok(n, cudaMalloc(&pd->d_head, head_bytes(pd.get()) * pd->cap), "cudaMalloc head staging", al, ac)) return nullptr;
   if (!cuda_ok(n, cudaMemcpyAsync(pd->d_wblob, P.wblob.data(), P.wblob.size(), cudaMemcpyHostToDevice, n->stream), "upload weights")) return nullptr;
   if (!P.luts.empty() && !cuda_ok(n, cudaMemcpyAsync(pd->d_luts, P.luts.data(), P.luts.size(), cudaMemcpyHostToDevice, n->stream), "upload luts")) return nullptr;
-  // pad channels of every buffer must read as defined bytes: clear the arena once
-  if (!cuda_ok(n, cudaMemsetAsync(pd->d_arena, 0, per_img * pd->cap + 1024, n->stream), "clear arena")) return nullptr;
-  // TMA descriptors of the 1x1-conv A operands: 2-D [rows = cap*H*W, CP bytes], box 128 rows x 16 B
-  pd->tmaps.resize(P.steps.size());
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_text("cuTensorMapEncodeTiled entry point unavailable"); n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_NETWORK); return nullptr; }
-  for (size_t i = 0; i < P.steps.size(); ++i) {
-    const Step& s = P.steps[i];
-    if (s.kind != STEP_CONV1X1) continue;
-    const PBuffer& b = P.buffers[s.in_buf];
-    void* base = pd->d_arena + b.offset * pd->cap;
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(b.CP), static_cast<cuuint64_t>(pd->cap) * b.H * b.W};
-    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(b.CP)};
-    cuuint32_t box[2] = {16, 128};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&pd->tmaps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_text("cuTensorMapEncodeTiled failed for step " + s.name + " (CUresult " + std::to_string(r) + ")");
-      n->latch(AI_ERROR_INIT_FAILED, AI_ERROR_CODE_TENSOR); return nullptr; }
+  pd->d_arena_l[0] = pd->d_arena;
+  if (!prepare_layer_lane(n, pd.get(), 0)) return nullptr;
+  {
+    const std::vector<EpiChF> lean = lean_epi_table(P.epi.data(), static_cast<int>(P.epi.size()));
+    if (!cuda_ok(n, cudaMalloc(&pd->d_epi, std::max<size_t>(P.epi.size(), 1) * sizeof(EpiCh)), "cudaMalloc requant table", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+    if (!cuda_ok(n, cudaMalloc(&pd->d_epif, lean.size() * sizeof(EpiChF)), "cudaMalloc requant table", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+    if (!P.epi.empty() && !cuda_ok(n, cudaMemcpyAsync(pd->d_epi, P.epi.data(), P.epi.size() * sizeof(EpiCh), cudaMemcpyHostToDevice, n->stream), "upload requant table")) return nullptr;
+    if (!cuda_ok(n, cudaMemcpyAsync(pd->d_epif, lean.data(), lean.size() * sizeof(EpiChF), cudaMemcpyHostToDevice, n->stream), "upload requant table")) return nullptr;
+    if (!cuda_ok(n, cudaStreamSynchronize(n->stream), "upload requant table")) return nullptr;      // `lean` dies with this scope
   }
   pd->step_ms.assign(P.steps.size(), -1.f);
   // fused single-kernel program (falls back to the layered path when it cannot be built)
@@ -301,29 +336,30 @@ PlanDev* get_plan(Network* n, int H, int W) {
   return raw;
 }
 
-int8_t* buf_ptr(const PlanDev* pd, int buf, const int8_t* in, int8_t* head) {
+int8_t* buf_ptr(const PlanDev* pd, int buf, const int8_t* in, int8_t* head, int lane = 0) {
   if (buf < 0) return nullptr;
   const PBuffer& b = pd->plan.buffers[buf];
   if (b.is_input) return const_cast<int8_t*>(in);
   if (b.is_output) return head;
   if (b.observer_only && !pd->observer) return nullptr;
-  return reinterpret_cast<int8_t*>(pd->d_arena + b.offset * pd->cap);
+  return reinterpret_cast<int8_t*>(pd->d_arena_l[lane] + b.offset * pd->cap);
 }
 
-EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* head) {
+EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* head, int lane = 0) {
   const Plan& P = pd->plan;
   EpiOut eo{};
   const PBuffer& ob = P.buffers[s.out_buf];
-  eo.out = buf_ptr(pd, s.out_buf, in, head); eo.out_pitch = ob.CP; eo.out_coff = s.out_coff; eo.cout = s.Cout;
+  eo.epi_tab = pd->d_epi; eo.epif_tab = pd->d_epif;
+  eo.out = buf_ptr(pd, s.out_buf, in, head, lane); eo.out_pitch = ob.CP; eo.out_coff = s.out_coff; eo.cout = s.Cout;
   // the step owns the pad channels of a buffer it writes from channel 0 alone
   eo.fill_to = (s.out_coff == 0 && ob.C == s.Cout && !ob.is_output) ? ob.CP : s.Cout;
   eo.epi_base = s.epi_base;
   const bool obs = pd->observer;
-  if (obs && s.raw_buf >= 0) { eo.raw = buf_ptr(pd, s.raw_buf, in, head); eo.raw_pitch = P.buffers[s.raw_buf].CP; }
-  if (obs && s.mid_buf >= 0) { eo.mid = buf_ptr(pd, s.mid_buf, in, head); eo.mid_pitch = P.buffers[s.mid_buf].CP; }
-  if (obs && s.pre_add_buf >= 0) { eo.pre_add = buf_ptr(pd, s.pre_add_buf, in, head); eo.pre_add_pitch = P.buffers[s.pre_add_buf].CP; }
+  if (obs && s.raw_buf >= 0) { eo.raw = buf_ptr(pd, s.raw_buf, in, head, lane); eo.raw_pitch = P.buffers[s.raw_buf].CP; }
+  if (obs && s.mid_buf >= 0) { eo.mid = buf_ptr(pd, s.mid_buf, in, head, lane); eo.mid_pitch = P.buffers[s.mid_buf].CP; }
+  if (obs && s.pre_add_buf >= 0) { eo.pre_add = buf_ptr(pd, s.pre_add_buf, in, head, lane); eo.pre_add_pitch = P.buffers[s.pre_add_buf].CP; }
   if (s.add.enabled) {
-    eo.add = s.add; eo.add_in = buf_ptr(pd, s.add_buf, in, head); eo.add_pitch = P.buffers[s.add_buf].CP; eo.add_coff = s.add_coff;
+    eo.add = s.add; eo.add_in = buf_ptr(pd, s.add_buf, in, head, lane); eo.add_pitch = P.buffers[s.add_buf].CP; eo.add_coff = s.add_coff;
   }
   if (obs) {
     eo.lut1 = s.lut1 >= 0 ? pd->d_luts + static_cast<size_t>(s.lut1) * 256 : nullptr;
@@ -348,8 +384,69 @@ EpiOut make_epi_out(const PlanDev* pd, const Step& s, const int8_t* in, int8_t* 
 // independent chunks may then run concurrently)
 bool uses_fused(const Network* n, const PlanDev* pd) { return !pd->observer && !n->step_profiling && n->mode != 1 && pd->fprog.ok; }
 
+// the 26 (yoloface) layer kernels of one chunk, queued on `st`; with `timed`, every step between its own events
+bool launch_layer_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb, cudaStream_t st, int lane, bool timed) {
+  const Plan& P = pd->plan;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+  bool ok = true;
+  for (size_t i = 0; i < P.steps.size() && ok; ++i) {
+    const Step& s = P.steps[i];
+    EpiOut eo = make_epi_out(pd, s, d_in, d_head, lane);
+    eo.err_word = n->d_err;
+    cudaError_t e = cudaSuccess;
+    if (timed) cudaEventRecord(e0, st);
+    switch (s.kind) {
+      case STEP_CONV1X1: {
+        Conv1x1Args a{};
+        a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
+        a.nchunk = P.buffers[s.in_buf].CP / 16; a.nk = s.Kpad / 32;
+        a.M = static_cast<long long>(nb) * s.Hout * s.Wout; a.num_tiles = static_cast<int>((a.M + 127) / 128);
+        a.eo = eo; a.err = n->d_err;
+        e = launch_conv1x1(pd->tmaps_l[lane][i], a, s.Npad, n->sm_count, st);
+        break; }
+      case STEP_CONV_IM2COL: {
+        ConvIm2colArgs a{};
+        a.in = d_in; a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
+        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
+        a.band_rows = s.band_rows; a.bands = s.bands; a.in_zp = s.in_zp; a.eo = eo; a.err = n->d_err;
+        e = launch_conv_im2col(a, s.Npad, n->sm_count, st);
+        break; }
+      case STEP_DW: {
+        DwArgs a{};
+        a.in = buf_ptr(pd, s.in_buf, d_in, d_head, lane); a.in_pitch = P.buffers[s.in_buf].CP;
+        a.w1h = reinterpret_cast<const uint32_t*>(pd->d_wblob + s.w_off);
+        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
+        a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.in_zp = s.in_zp; a.words = (s.Cout + 3) / 4; a.eo = eo;
+        e = launch_dw(a, st);
+        break; }
+      case STEP_MAXPOOL: {
+        PoolArgs a{};
+        a.in = buf_ptr(pd, s.in_buf, d_in, d_head, lane); a.in_pitch = P.buffers[s.in_buf].CP;
+        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
+        a.k = s.kh; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.words = (s.Cout + 3) / 4; a.eo = eo;
+        e = launch_pool(a, st);
+        break; }
+      case STEP_LUT: {
+        LutArgs a{};
+        a.in = buf_ptr(pd, s.in_buf, d_in, d_head, lane); a.in_pitch = P.buffers[s.in_buf].CP; a.in_coff = s.in_coff;
+        a.rows = static_cast<long long>(nb) * s.Hout * s.Wout; a.words = (s.Cout + 3) / 4; a.eo = eo;
+        e = launch_lut(a, st);
+        break; }
+    }
+    if (!cuda_ok(n, e, s.name.c_str())) { ok = false; break; }
+    if (timed) {
+      cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); pd->step_ms[i] = ms;
+    }
+  }
+  if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  return ok;
+}
+
 // overlapped: the caller queues further launches around this one (kernel lanes / the pipelined host ring)
-bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb, cudaStream_t st = nullptr, bool overlapped = false) {
+// lane: which activation arena the layer kernels use (independent chunks on different lanes run side by side)
+bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint32_t nb, cudaStream_t st = nullptr, bool overlapped = false, int lane = 0) {
   const Plan& P = pd->plan;
   if (!st) st = n->stream;
   if (uses_fused(n, pd)) {
@@ -361,66 +458,31 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
     ++n->launches;
     return true;
   }
-  if (g_active_epi[n->device & 63] != pd) {
-    // the table is shared by every context on this device: order the overwrite after prior work
-    if (!cuda_ok(n, cudaDeviceSynchronize(), "synchronize before table switch")) return false;
-    if (!cuda_ok(n, upload_epi_table(P.epi.data(), static_cast<int>(P.epi.size()), st), "upload epilogue table")) return false;
-    g_active_epi[n->device & 63] = pd;
+  if (!prepare_layer_lane(n, pd, lane)) return false;
+  static const bool graphs_on = [] { const char* e = std::getenv("YF_B200_GRAPH"); return !(e && !std::atoi(e)); }();
+  if (!graphs_on || n->step_profiling || pd->observer) {
+    if (!launch_layer_steps(n, pd, d_in, d_head, nb, st, lane, n->step_profiling)) return false;
+    n->launches += P.steps.size();
+    return true;
   }
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (n->step_profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
-  for (size_t i = 0; i < P.steps.size(); ++i) {
-    const Step& s = P.steps[i];
-    EpiOut eo = make_epi_out(pd, s, d_in, d_head);
-    eo.err_word = n->d_err;
-    cudaError_t e = cudaSuccess;
-    if (n->step_profiling) cudaEventRecord(e0, st);
-    switch (s.kind) {
-      case STEP_CONV1X1: {
-        Conv1x1Args a{};
-        a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
-        a.nchunk = P.buffers[s.in_buf].CP / 16; a.nk = s.Kpad / 32;
-        a.M = static_cast<long long>(nb) * s.Hout * s.Wout; a.num_tiles = static_cast<int>((a.M + 127) / 128);
-        a.eo = eo; a.err = n->d_err;
-        e = launch_conv1x1(pd->tmaps[i], a, s.Npad, n->sm_count, st);
-        break; }
-      case STEP_CONV_IM2COL: {
-        ConvIm2colArgs a{};
-        a.in = d_in; a.w_img = pd->d_wblob + s.w_off; a.w_bytes = static_cast<int>(s.w_bytes);
-        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
-        a.band_rows = s.band_rows; a.bands = s.bands; a.in_zp = s.in_zp; a.eo = eo; a.err = n->d_err;
-        e = launch_conv_im2col(a, s.Npad, n->sm_count, st);
-        break; }
-      case STEP_DW: {
-        DwArgs a{};
-        a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP;
-        a.w1h = reinterpret_cast<const uint32_t*>(pd->d_wblob + s.w_off);
-        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
-        a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.in_zp = s.in_zp; a.words = (s.Cout + 3) / 4; a.eo = eo;
-        e = launch_dw(a, st);
-        break; }
-      case STEP_MAXPOOL: {
-        PoolArgs a{};
-        a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP;
-        a.n_img = static_cast<int>(nb); a.Hin = s.Hin; a.Win = s.Win; a.Hout = s.Hout; a.Wout = s.Wout;
-        a.k = s.kh; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l; a.words = (s.Cout + 3) / 4; a.eo = eo;
-        e = launch_pool(a, st);
-        break; }
-      case STEP_LUT: {
-        LutArgs a{};
-        a.in = buf_ptr(pd, s.in_buf, d_in, d_head); a.in_pitch = P.buffers[s.in_buf].CP; a.in_coff = s.in_coff;
-        a.rows = static_cast<long long>(nb) * s.Hout * s.Wout; a.words = (s.Cout + 3) / 4; a.eo = eo;
-        e = launch_lut(a, st);
-        break; }
-    }
-    if (!cuda_ok(n, e, s.name.c_str())) return false;
-    ++n->launches;
-    if (n->step_profiling) {
-      cudaEventRecord(e1, st); cudaEventSynchronize(e1);
-      float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); pd->step_ms[i] = ms;
-    }
+  // One CUDA graph per (input, output, images, lane): the first use captures the launches, every later use replays
+  // them with one call.  A caller cycling through more buffers than the cache holds just re-captures.
+  const PlanDev::GraphKey key{d_in, d_head, nb, lane};
+  auto it = pd->graphs.find(key);
+  if (it == pd->graphs.end()) {
+    if (pd->graphs.size() >= 512) { for (auto& kv : pd->graphs) cudaGraphExecDestroy(kv.second); pd->graphs.clear(); }
+    cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+    if (!cuda_ok(n, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "graph capture")) return false;
+    const bool ok = launch_layer_steps(n, pd, d_in, d_head, nb, st, lane, false);
+    const cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (!ok || !cuda_ok(n, ce, "graph capture")) { if (g) cudaGraphDestroy(g); return false; }
+    const cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (!cuda_ok(n, ie, "graph instantiate")) return false;
+    it = pd->graphs.emplace(key, ge).first;
   }
-  if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  if (!cuda_ok(n, cudaGraphLaunch(it->second, st), "graph launch")) return false;
+  n->launches += P.steps.size();
   return true;
 }
 
@@ -441,17 +503,22 @@ bool check_device_err(Network* n) {
 // ---- independent device-resident chunks: fork from n->stream over the kernel lanes, join back ----
 struct DevChunk { const int8_t* in; int8_t* out; uint32_t nb; };
 bool run_chunks(Network* n, PlanDev* pd, const std::vector<DevChunk>& ch) {
-  if (ch.size() < 2 || !uses_fused(n, pd)) {
+  const bool fused = uses_fused(n, pd);
+  const bool layer_lanes = !fused && !pd->observer && !n->step_profiling;      // every lane has its own activation arena
+  if (ch.size() < 2 || (!fused && !layer_lanes)) {
     for (const DevChunk& c : ch) { if (!run_steps(n, pd, c.in, c.out, c.nb)) return false; n->last_run_n = c.nb; }
     return true;
   }
+  const int nl = fused ? n->lanes : std::min<int>(n->lanes, std::min<int>(PlanDev::kLayerLanes, static_cast<int>(ch.size())));
+  if (!fused) for (int l = 0; l < nl; ++l) if (!prepare_layer_lane(n, pd, l)) return false;
   if (!cuda_ok(n, cudaEventRecord(n->ev_fork, n->stream), "fork")) return false;
-  for (int l = 0; l < n->lanes; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
+  for (int l = 0; l < nl; ++l) cudaStreamWaitEvent(n->lane[l], n->ev_fork, 0);
   for (size_t i = 0; i < ch.size(); ++i) {
-    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[i % n->lanes], true)) return false;
+    const int l = static_cast<int>(i % nl);
+    if (!run_steps(n, pd, ch[i].in, ch[i].out, ch[i].nb, n->lane[l], true, fused ? 0 : l)) return false;
     n->last_run_n = ch[i].nb;
   }
-  for (int l = 0; l < n->lanes; ++l) {
+  for (int l = 0; l < nl; ++l) {
     cudaEventRecord(n->ev_join[l], n->lane[l]);
     if (!cuda_ok(n, cudaStreamWaitEvent(n->stream, n->ev_join[l], 0), "join")) return false;
   }
@@ -897,9 +964,6 @@ AI_API_ENTRY ai_handle ai_network_destroy(ai_handle network) {
   cudaStreamSynchronize(n->s_d2h);
   for (Network* c : n->members.empty() ? std::vector<Network*>{n} : n->members) {
     if (c != n) { cudaSetDevice(c->device); cudaDeviceSynchronize(); }
-    for (auto& kv : c->plans) {
-      if (g_active_epi[c->device & 63] == kv.second.get()) g_active_epi[c->device & 63] = nullptr;
-    }
   }
   cudaSetDevice(n->device);
   { std::lock_guard<std::mutex> rk(g_mu); g_nets.erase(std::remove(g_nets.begin(), g_nets.end(), n), g_nets.end()); }
@@ -945,9 +1009,6 @@ AI_API_ENTRY ai_bool ai_network_init(ai_handle network, const ai_network_params*
   const std::vector<uint8_t> weights = blob ? std::vector<uint8_t>(blob, blob + need) : std::vector<uint8_t>();
   auto init_one = [weights](Network* c) {
     c->blob = weights;
-    for (auto& kv : c->plans) {
-      if (g_active_epi[c->device & 63] == kv.second.get()) g_active_epi[c->device & 63] = nullptr;
-    }
     c->plans.clear();
     if (!get_plan(c, c->H, c->W)) return false;
     if (!cuda_ok(c, cudaStreamSynchronize(c->stream), "init synchronize", AI_ERROR_INIT_FAILED)) return false;

@@ -19,8 +19,9 @@
 
 namespace yf {
 
-__constant__ EpiCh c_epi[kMaxEpiCh];
-__constant__ EpiChF c_epif[kMaxEpiCh];   // the same channels in the lean form of yf_requant.cuh (zero where it does not apply)
+// The per-channel requant tables live in the plan's own global memory (EpiOut::epi_tab / epif_tab): nothing is shared
+// between contexts on one GPU, so two models never wait for each other.  Every kernel copies its channels to shared
+// memory (or registers) once per CTA.
 
 bool epi_lean_form(const EpiCh& k, int32_t* bias) {
   int32_t w4[4];
@@ -29,19 +30,15 @@ bool epi_lean_form(const EpiCh& k, int32_t* bias) {
   return true;
 }
 
-cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s) {
-  if (n > kMaxEpiCh) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_epi, host, sizeof(EpiCh) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return e;
-  std::vector<EpiChF> lean(static_cast<size_t>(std::max(n, 1)));   // not static: contexts on different devices upload concurrently
+// host: the lean (16-byte) form of every channel, zero where it does not apply (the kernels then use the general form)
+std::vector<EpiChF> lean_epi_table(const EpiCh* host, int n) {
+  std::vector<EpiChF> lean(static_cast<size_t>(std::max(n, 1)));
   for (int i = 0; i < n; ++i) {
     int32_t w4[4];
     lean[i] = EpiChF{};
     if (epi_lean_words(host[i], w4)) lean[i] = EpiChF{w4[0], w4[1], w4[2], w4[3]};
   }
-  e = cudaMemcpyToSymbolAsync(c_epif, lean.data(), sizeof(EpiChF) * static_cast<size_t>(n), 0, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(s);       // `lean` dies with this frame
+  return lean;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -176,10 +173,10 @@ template <int NPAD>
 __device__ __forceinline__ void load_epi(EpiCh* sEpi, const EpiOut& eo, int tid, int nthreads) {
   if (eo.fast) {                          // the same smem region holds the 16-byte records
     EpiChF* f = reinterpret_cast<EpiChF*>(sEpi);
-    for (int i = tid; i < NPAD; i += nthreads) f[i] = i < eo.cout ? c_epif[eo.epi_base + i] : EpiChF{0, 0, 0, 0};
+    for (int i = tid; i < NPAD; i += nthreads) f[i] = i < eo.cout ? eo.epif_tab[eo.epi_base + i] : EpiChF{0, 0, 0, 0};
     return;
   }
-  for (int i = tid; i < NPAD; i += nthreads) sEpi[i] = c_epi[eo.epi_base + (i < eo.cout ? i : 0)];
+  for (int i = tid; i < NPAD; i += nthreads) sEpi[i] = eo.epi_tab[eo.epi_base + (i < eo.cout ? i : 0)];
 }
 __device__ __forceinline__ void load_luts(uint8_t* sLut, const EpiOut& eo, int tid, int nthreads) {
   for (int i = tid; i < 128; i += nthreads) {
@@ -538,7 +535,7 @@ __global__ void __launch_bounds__(320) dwconv3x3_band_kernel(const DwArgs p, int
   int32_t k_bias[4], k_mult[4], k_c2p[4], k_e[4];                 // bias9 | mult | kc | sh of yf_requant.cuh
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const EpiChF k = c0 + j < p.eo.cout ? c_epif[p.eo.epi_base + c0 + j] : EpiChF{0, 0, 0, 0};
+    const EpiChF k = c0 + j < p.eo.cout ? p.eo.epif_tab[p.eo.epi_base + c0 + j] : EpiChF{0, 0, 0, 0};
     k_bias[j] = k.bias9; k_mult[j] = k.mult; k_c2p[j] = k.kc; k_e[j] = k.sh;
   }
   const uint32_t keep = c0 + 4 <= p.eo.cout ? 0xffffffffu : (c0 < p.eo.cout ? (1u << (8 * (p.eo.cout - c0))) - 1u : 0u);
@@ -615,7 +612,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwArgs p) {
   __shared__ DwSmem sm;
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
     EpiCh k{};
-    if (i < p.eo.cout) k = c_epi[p.eo.epi_base + i];
+    if (i < p.eo.cout) k = p.eo.epi_tab[p.eo.epi_base + i];
     sm.k[DWK_ADD_LO][i] = static_cast<int32_t>(static_cast<unsigned long long>(k.add64) & 0xffffffffull);
     sm.k[DWK_ADD_HI][i] = static_cast<int32_t>(static_cast<unsigned long long>(k.add64) >> 32);
     sm.k[DWK_MULT][i] = k.mult; sm.k[DWK_C2][i] = k.c2; sm.k[DWK_E][i] = k.e; sm.k[DWK_LS][i] = k.ls; sm.k[DWK_SGN][i] = k.sgn_mask;

@@ -9,7 +9,6 @@
 namespace yf {
 
 constexpr int kDecodeSmemMax = 220 * 1024;   // decode_nms_block_kernel: 25 B per candidate slot (power of two >= gh*gw*3)
-constexpr int kMaxEpiCh = 832;           // __constant__ EpiCh table entries (26 KB per table)
 
 // Where an epilogue writes (shared by every kernel).  Pointers are to element [row 0, channel 0]
 // of the destination buffer; a row is one pixel, `*_pitch` bytes apart.
@@ -21,6 +20,8 @@ struct EpiOut {
   const int8_t* add_in; int add_pitch; int add_coff;
   AddParams add;
   int epi_base;
+  const EpiCh* epi_tab;                 // the plan's requant tables (global memory), indexed by epi_base + channel
+  const struct EpiChF* epif_tab;
   const uint8_t* lut1;                  // device pointers to 256-byte tables (nullptr = none)
   const uint8_t* lut2;
   int fast;                             // lean epilogue (no observer outputs, one table XOR ADD, lean requant form)
@@ -80,7 +81,11 @@ struct PrepArgs {                        // yoloface.c:26-93 on device
   int n_img;
 };
 
-cudaError_t upload_epi_table(const EpiCh* host, int n, cudaStream_t s);
+struct EpiChF;
+}  // namespace yf
+#include <vector>
+namespace yf {
+std::vector<EpiChF> lean_epi_table(const EpiCh* host, int n);   // 16-byte form of every channel (zeros where it does not apply)
 bool epi_lean_form(const EpiCh& k, int32_t* bias);     // can this channel's requant use the 16-byte form of yf_requant.cuh?
 cudaError_t launch_conv1x1(const CUtensorMap& tmapA, const Conv1x1Args& a, int npad, int sm_count, cudaStream_t s);
 cudaError_t launch_conv_im2col(const ConvIm2colArgs& a, int npad, int sm_count, cudaStream_t s);

@@ -259,8 +259,21 @@ struct Builder {
     quantize_multiplier(static_cast<double>(m.tensors[O.in[0]].scale[0]) / static_cast<double>(m.tensors[O.out].scale[0]), &mult, &shift);
     int32_t zin = static_cast<int32_t>(m.tensors[O.in[0]].zp[0]), zout = static_cast<int32_t>(m.tensors[O.out].zp[0]);
     int8_t tab[256];
-    for (int q = -128; q < 128; ++q)
-      tab[q + 128] = static_cast<int8_t>(std::min(127, std::max(-128, mbqm_host(q - zin, mult, shift) + zout)));
+    for (int q = -128; q < 128; ++q) {
+      int32_t u;
+      if (st_act) {
+        // ST folds the QUANTIZE operators into forward_concat (network.c:2307-2313, 2631-2637), whose arithmetic is
+        // inside the closed library.  The one int8 -> int8 rescaling rule of ST's generator that IS visible -- the
+        // activation tables, network.c:2218..2902 -- is float32 with round-half-to-even; the ST mode applies the same
+        // rule here.  A plausible reading, not a pinned one.
+        volatile float v = (static_cast<float>(q) - static_cast<float>(zin)) * m.tensors[O.in[0]].scale[0];
+        v = v / m.tensors[O.out].scale[0];
+        u = static_cast<int32_t>(std::nearbyintf(v)) + zout;
+      } else {
+        u = mbqm_host(q - zin, mult, shift) + zout;
+      }
+      tab[q + 128] = static_cast<int8_t>(std::min(127, std::max(-128, u)));
+    }
     return add_lut(tab);
   }
   int compose_luts(int a, int b) {   // b o a

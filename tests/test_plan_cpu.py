@@ -183,6 +183,24 @@ def test_st_activation_mode_reproduces_st_tables(yf, oracle, golden, monkeypatch
     assert sorted(stm) == sorted(st)
     for op in st:
         assert np.array_equal(stm[op], st[op]), op
+    # the three QUANTIZE operators ST folds into forward_concat (network.c:2307-2313, 2631-2637): the ST mode builds their
+    # tables with the same float32 / round-half-even rule as ST's activation tables (a reading, not a pin: the concat's
+    # own arithmetic is inside the closed library)
+    def quant_tables(P):
+        out = {}
+        for s in P["steps"]:
+            qs = [op for op in s["ops"] if oracle.op(op)["opcode"] == 114]
+            if qs:
+                out[qs[0]] = P["luts"][s["lut2"] if s["lut2"] >= 0 else s["lut1"]]
+        return out
+    qst = quant_tables(yf.plan(56, 56))
+    assert sorted(qst) == [21, 44, 45]
+    for op, tab in qst.items():
+        o = oracle.op(op); ti, to = oracle.tensor(o["inputs"][0]), oracle.tensor(o["output"])
+        q = np.arange(-128, 128, dtype=np.float32)
+        v = ((q - np.float32(ti["zp"][0])) * np.float32(ti["scale"][0])) / np.float32(to["scale"][0])
+        want = np.clip(np.rint(v).astype(np.int64) + to["zp"][0], -128, 127).astype(np.int8)
+        assert np.array_equal(tab.view(np.int8), want), op
     # and the plan still executes: heads move by a few LSB at most relative to TFLite mode
     img = golden["images"][2]
     a = Emulator(yf.plan(56, 56)).run(img, observer=False)

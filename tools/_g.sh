@@ -1,12 +1,14 @@
-mkdir -p gpurun_out/r2g
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2g/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2g/pytest.log
-tail -4 gpurun_out/r2g/pytest.log
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2g/bench.json 2> gpurun_out/r2g/bench.err; echo "bench rc $?"; tail -3 gpurun_out/r2g/bench.err
+mkdir -p gpurun_out/r2i
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2i/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2i/pytest.log
+tail -6 gpurun_out/r2i/pytest.log
+YF_B200_MODE=layered timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r2i/bench_layered.json 2> gpurun_out/r2i/bench_layered.err; echo "rc $?"; tail -2 gpurun_out/r2i/bench_layered.err
+YF_B200_MODE=layered YF_B200_GRAPH=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r2i/bench_layered_nograph.json 2> gpurun_out/r2i/bench_layered_nograph.err
 python - <<'PY'
 import json
-d=json.load(open("gpurun_out/r2g/bench.json"))
-print("value", d["value"], d["ms_per_step"], d["value_spread"]); print("e2e", d["e2e"]["value"], d["e2e"]["spread"], d["e2e"]["blocking"]["value"])
-print("clocks", d["clocks"]); print("roofline", d["roofline"]); print("issue", d["roofline_issue"]); print("cpu", d["cpu_baseline"])
-print("config4", d["config4"]); print("config5", d["config5"]); print("config3", d["config3"]); print("extra", d["extra"])
+for f in ("bench_layered","bench_layered_nograph"):
+    try:
+        d=json.load(open("gpurun_out/r2i/%s.json"%f)); print(f, "value", round(d["value"]/1e6,3), "serial", round(d["serial"]["value"]/1e6,3), "e2e", round(d["e2e"]["value"]/1e6,3), "launch_ms", d["roofline"].get("launch_ms"), d.get("path"))
+        if d.get("config4"): print(" config4", d["config4"]["batch_16"], d["config4"]["batch_4096"])
+        if d.get("extra"): print(" extra", d["extra"])
+    except Exception as e: print(f, "ERR", e)
 PY
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:yoloface_fused -s 2 -c 1 -o gpurun_out/r2g/fused_v9_b256 -f python tools/run_once.py 256 fused 3 > gpurun_out/r2g/ncu256.log 2>&1
