@@ -1,14 +1,6 @@
-mkdir -p gpurun_out/r2i
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2i/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2i/pytest.log
-tail -6 gpurun_out/r2i/pytest.log
-YF_B200_MODE=layered timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r2i/bench_layered.json 2> gpurun_out/r2i/bench_layered.err; echo "rc $?"; tail -2 gpurun_out/r2i/bench_layered.err
-YF_B200_MODE=layered YF_B200_GRAPH=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r2i/bench_layered_nograph.json 2> gpurun_out/r2i/bench_layered_nograph.err
-python - <<'PY'
-import json
-for f in ("bench_layered","bench_layered_nograph"):
-    try:
-        d=json.load(open("gpurun_out/r2i/%s.json"%f)); print(f, "value", round(d["value"]/1e6,3), "serial", round(d["serial"]["value"]/1e6,3), "e2e", round(d["e2e"]["value"]/1e6,3), "launch_ms", d["roofline"].get("launch_ms"), d.get("path"))
-        if d.get("config4"): print(" config4", d["config4"]["batch_16"], d["config4"]["batch_4096"])
-        if d.get("extra"): print(" extra", d["extra"])
-    except Exception as e: print(f, "ERR", e)
-PY
+mkdir -p gpurun_out/r2j
+YF_B200_GRAPH=0 timeout 300 python tools/layer_roofline.py 512 5 gpurun_out/r2j/layers_224_b512 224 > gpurun_out/r2j/layers224.log 2>&1
+YF_B200_GRAPH=0 timeout 300 python tools/layer_roofline.py 8192 5 gpurun_out/r2j/layers_56_b8192 56 > gpurun_out/r2j/layers56.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none --csv --log-file gpurun_out/r2j/layered_224_b256_ncu.csv python tools/run_once.py 256 layered 1 224 > gpurun_out/r2j/ncu224.log 2>&1
+python tools/h2d_ceiling.py > gpurun_out/r2j/h2d_n1.json 2>&1
+cat gpurun_out/r2j/layers_224_b512.md | head -40; cat gpurun_out/r2j/h2d_n1.json
