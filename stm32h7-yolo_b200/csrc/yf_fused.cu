@@ -72,25 +72,33 @@ __device__ __forceinline__ void epi_bar_sync(int threads) { asm volatile("bar.sy
 __device__ __forceinline__ void epi_bar_arrive(int threads) { asm volatile("bar.arrive 1, %0;" ::"r"(threads) : "memory"); }
 
 // ---- per-thread state shared by every phase --------------------------------------------------------------------
+// lead thread only: where the stream of parameter blocks stands.  Block j may be requested once block
+// j - kFusedParamSlots (the slot's previous tenant) belongs to a finished phase, i.e. j < pc + kFusedParamSlots.
+// Lives in shared memory: one thread touches it a few times per phase, and 255 threads do not pay registers for it.
+struct Producer { uint32_t pc_next; int pnext, knext, pad_; };
 struct Cx {
   uint8_t* smem;
-  uint32_t smem_base, in_full, par_full, mma_done, tmem_base;
+  uint32_t smem_base, tmem_base;
   int tid, warp, lane;
   bool ctrl, lead, ok;
   uint32_t use0, use1, in_uses;                // completed waits on mma_done[0/1], in_full
-  // lead thread: parameter blocks go round the slots; block j may be requested once block j - kFusedParamSlots (the
-  // slot's previous tenant) belongs to a finished phase, i.e. j < pc + kFusedParamSlots
-  uint32_t pc_next, total_pc;
-  int pnext, knext, my_images;
-  const int2* pb;                              // smem: {param_off, param_bytes} per phase
+  uint32_t total_pc;
+  int my_images;
+  // mbarriers (shared-space addresses, 8 bytes each): input image landed | [kFusedParamSlots] parameter slot landed |
+  // [2] accumulators ready; then the TMEM base word, the producer state and the parameter-block table
+  __device__ __forceinline__ uint32_t in_full(const FusedArgs& a) const { return smem_base + a.bars_off; }
+  __device__ __forceinline__ uint32_t par_full(const FusedArgs& a) const { return smem_base + a.bars_off + 8; }
+  __device__ __forceinline__ uint32_t mma_done(const FusedArgs& a) const { return smem_base + a.bars_off + 8 + 8 * kFusedParamSlots; }
+  __device__ __forceinline__ Producer* producer(const FusedArgs& a) const { return reinterpret_cast<Producer*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots) + 8); }
+  __device__ __forceinline__ const int2* pb(const FusedArgs& a) const { return reinterpret_cast<const int2*>(smem + a.bars_off + 96); }   // {param_off, param_bytes} per phase
 };
 // what changes from one execution of a phase to the next
 struct Rt {
   uint32_t pc;                                 // running count of executed phases (parameter slot / barrier parity)
   int out_shift;                               // front phases feeding the back: byte offset of this image's rows in the tall buffer
   bool pair_b;                                 // back phases: the pair holds a second image
-  int8_t* ghead_a; int8_t* ghead_b;            // back phases: where the two heads go
-  const int8_t* next_in;                       // front phases: next image of this CTA (input prefetch), or null
+  int img_a, img_b;                            // back phases: the images whose heads this pair produces
+  int next_img;                                // front phases: next image of this CTA (input prefetch), or -1
 };
 
 __device__ __forceinline__ void wait_bar(Cx& c, const FusedArgs& a, uint32_t bar, uint32_t parity, int code) {
@@ -104,22 +112,25 @@ __device__ __forceinline__ void advance_phase(int& p, int& k, int split, int nph
   else ++p;
 }
 __device__ __forceinline__ void refill(Cx& c, const FusedArgs& a, uint32_t pc_now) {
+  Producer* pr = c.producer(a);
+  uint32_t pc_next = pr->pc_next; int pnext = pr->pnext, knext = pr->knext;
 #pragma unroll 1
-  while (c.pc_next < c.total_pc && c.pc_next < pc_now + kFusedParamSlots) {
-    const int2 e = c.pb[c.pnext];
-    const uint32_t s = c.pc_next % kFusedParamSlots, bar = c.par_full + 8 * s;
+  while (pc_next < c.total_pc && pc_next < pc_now + kFusedParamSlots) {
+    const int2 e = c.pb(a)[pnext];
+    const uint32_t s = pc_next % kFusedParamSlots, bar = c.par_full(a) + 8 * s;
     mbar_arrive_expect_tx(bar, static_cast<uint32_t>(e.y));
     bulk_load_1d(c.smem_base + a.slot_off + s * a.slot_bytes, a.params + e.x, static_cast<uint32_t>(e.y), bar);
-    ++c.pc_next;
-    advance_phase(c.pnext, c.knext, a.split, a.nphases, c.my_images);
+    ++pc_next;
+    advance_phase(pnext, knext, a.split, a.nphases, c.my_images);
   }
+  pr->pc_next = pc_next; pr->pnext = pnext; pr->knext = knext;
 }
 // lead thread, off the critical path: refill the slot the previous phase released, prefetch the next image
 __device__ __forceinline__ void housekeeping(Cx& c, const FusedArgs& a, const Rt& rt, bool prefetch_image) {
   refill(c, a, rt.pc);
-  if (prefetch_image && rt.next_in) {                        // the image buffer is free after phase 0
-    mbar_arrive_expect_tx(c.in_full, static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(c.smem_base + a.in_off, rt.next_in, static_cast<uint32_t>(a.in_bytes), c.in_full);
+  if (prefetch_image && rt.next_img >= 0) {                  // the image buffer is free after phase 0
+    mbar_arrive_expect_tx(c.in_full(a), static_cast<uint32_t>(a.in_bytes));
+    bulk_load_1d(c.smem_base + a.in_off, a.in + static_cast<long long>(rt.next_img) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), c.in_full(a));
   }
 }
 
@@ -140,7 +151,7 @@ __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem,
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
-                                          int row, int g, int rows, const Rt& rt) {
+                                          int row, int g, int rows, const Rt& rt, const FusedArgs& a) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   tmem_ld_wait();
@@ -162,12 +173,12 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
     }
   }
   if (ph.to_global) {                                        // dense [pixels][cout] int8 head, 2-byte aligned rows
-    int8_t* gh = rt.ghead_a; int r = row;
+    int img = rt.img_a, r = row;
     if (ph.pair) {                                           // tall image: rows [0, rows_a) image A, [row_b0, ..) image B
-      if (row >= ph.row_b0) { gh = rt.ghead_b; r = row - ph.row_b0; }
+      if (row >= ph.row_b0) { img = rt.img_b; r = row - ph.row_b0; }
       else if (row >= ph.rows_a) return;                     // separator rows
     }
-    uint16_t* o = reinterpret_cast<uint16_t*>(gh + r * ph.cout + g * 16);
+    uint16_t* o = reinterpret_cast<uint16_t*>(a.out + static_cast<long long>(img) * a.head_bytes + r * ph.cout + g * 16);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
@@ -188,7 +199,7 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
 
 // all (tile, chunk) units of a conv phase, split across the worker warps (no divisions)
 // (tiles t0 .. t0+nt-1 are the group whose accumulators sit in TMEM, tile t at column (t - t0) * npad)
-__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt) {
+__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt, const FusedArgs& a) {
   const int q = c.warp & 3, chunks = ph.chunks_out;
   const uint8_t* lut = slot + ph.lut_off;
   const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
@@ -198,13 +209,13 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c,
     for (int t = c.warp >> 2; t < nt; t += kFusedWarpgroups) {
       const int row0 = (t0 + t) * 128 + q * 32;
       if (row0 >= rows) continue;                            // this warp's 32 rows are all padding
-      for (int g = 0; g < chunks; ++g) conv_unit(ph, c.smem, lut, epi, tq + t * ph.npad + g * 16, row0 + c.lane, g, rows, rt);
+      for (int g = 0; g < chunks; ++g) conv_unit(ph, c.smem, lut, epi, tq + t * ph.npad + g * 16, row0 + c.lane, g, rows, rt, a);
     }
   } else {
     // a single tile: split its chunks across the warpgroups
     const int row0 = t0 * 128 + q * 32;
     if (row0 < rows)
-      for (int g = c.warp >> 2; g < chunks; g += kFusedWarpgroups) conv_unit(ph, c.smem, lut, epi, tq + g * 16, row0 + c.lane, g, rows, rt);
+      for (int g = c.warp >> 2; g < chunks; g += kFusedWarpgroups) conv_unit(ph, c.smem, lut, epi, tq + g * 16, row0 + c.lane, g, rows, rt, a);
   }
 }
 
@@ -512,7 +523,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
   // rows that carry data: a pair phase holding only image A stops after the separator rows
   const int rows = ph.pair ? (rt.pair_b ? ph.rows_out : ph.rows_single) : ph.rows_out;
   const uint32_t s_idx = rt.pc % kFusedParamSlots;
-  const uint32_t par_bar = c.par_full + 8 * s_idx, par_parity = (rt.pc / kFusedParamSlots) & 1;
+  const uint32_t par_bar = c.par_full(a) + 8 * s_idx, par_parity = (rt.pc / kFusedParamSlots) & 1;
   const uint8_t* slot = smem + a.slot_off + s_idx * a.slot_bytes;
   const bool pf_here = p == a.in_pf_phase;
   if (kind == STEP_CONV1X1) {
@@ -534,12 +545,12 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
           for (int k = 0; k < ph.nk; ++k)
             if (el) mma_i8(c.tmem_base + t * ph.npad, mk_desc(ph.adesc_lo, sA + (t0 + t) * 2048 + k * 2 * ph.in_cs),
                            mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16), static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
-        if (el) mma_commit(c.mma_done);
+        if (el) mma_commit(c.mma_done(a));
         __syncwarp();
         if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
         // the control warp alone polls the accumulator barrier and then releases the row owners through a
         // hardware barrier, where waiting costs no issue slots
-        wait_bar(c, a, c.mma_done, c.use0 & 1, 301);
+        wait_bar(c, a, c.mma_done(a), c.use0 & 1, 301);
         tc_fence_before();
         if (has_rows) epi_bar_sync(meet); else epi_bar_arrive(meet);
         if (c.lead && t0 == 0 && !ctrl_busy) housekeeping(c, a, rt, pf_here);
@@ -551,7 +562,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
       ++c.use0;
       if (has_rows) {
         tc_fence_after();
-        conv_epilogue(ph, c, slot, t0, nt, rows, rt);
+        conv_epilogue(ph, c, slot, t0, nt, rows, rt, a);
         tc_fence_before();
       }
       if (t0 + tpg < ntiles) __syncthreads();                // the next group overwrites these TMEM columns
@@ -561,11 +572,11 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
     const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off;
     if (ph.out_wp) fill_border(ph, smem, tid);
     wait_bar(c, a, par_bar, par_parity, 302);
-    wait_bar(c, a, c.in_full, c.in_uses & 1, 303); ++c.in_uses;
+    wait_bar(c, a, c.in_full(a), c.in_uses & 1, 303); ++c.in_uses;
     const int rounds = (ntiles + 1) >> 1;
     for (int r = 0; r < rounds; ++r) {
       if (r >= 2) {                                          // the A stages of round r-2 must have been consumed
-        if (r & 1) { wait_bar(c, a, c.mma_done + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done, c.use0 & 1, 304); ++c.use0; }
+        if (r & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 304); ++c.use0; }
       }
       im2col_build(ph, smem, tid, r);
       fence_proxy_async_smem();
@@ -581,22 +592,22 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
             if (el) mma_i8(c.tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
                            static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
         }
-        if (el) mma_commit(c.mma_done + 8 * (r & 1));
+        if (el) mma_commit(c.mma_done(a) + 8 * (r & 1));
         __syncwarp();
       }
     }
     for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
-      if (r & 1) { wait_bar(c, a, c.mma_done + 8, c.use1 & 1, 305); ++c.use1; } else { wait_bar(c, a, c.mma_done, c.use0 & 1, 305); ++c.use0; }
+      if (r & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 305); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 305); ++c.use0; }
     }
     tc_fence_after();
-    conv_epilogue(ph, c, slot, 0, ntiles, rows, rt);
+    conv_epilogue(ph, c, slot, 0, ntiles, rows, rt, a);
     tc_fence_before();
     if (c.lead) housekeeping(c, a, rt, pf_here);
   } else {
     wait_bar(c, a, par_bar, par_parity, 302);
     if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, (ph.pair && !rt.pair_b) ? ph.rows_a : ph.rows_out, rt.out_shift, tp);
     else if (kind == STEP_MAXPOOL) pool_phase(ph, smem, slot, tid, rt.out_shift);
-    if (c.lead && c.pc_next <= rt.pc + 1) housekeeping(c, a, rt, pf_here);   // only when the next phase's block is not even requested yet
+    if (c.lead && c.producer(a)->pc_next <= rt.pc + 1) housekeeping(c, a, rt, pf_here);   // only when the next phase's block is not even requested yet
   }
   fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
 #ifdef YF_TRACE
@@ -611,7 +622,6 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
 // ---- prologue / epilogue shared by the two kernels ---------------------------------------------------------------
 __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* smem) {
   c.smem = smem; c.smem_base = smem_u32(smem);
-  c.in_full = c.smem_base + a.bars_off; c.par_full = c.in_full + 8; c.mma_done = c.par_full + 8 * kFusedParamSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots));
   c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
   c.ctrl = c.warp == kCtrlWarp; c.lead = c.tid == kCtrlWarp * 32; c.ok = true;
@@ -619,11 +629,11 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   if (c.tid == 0) {
     for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
     fence_mbar_init();
+    *c.producer(a) = Producer{0u, 0, 0, 0};
   }
   if (c.warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
-  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 64);           // parameter block table (<= kFusedMaxPhases entries)
+  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 96);           // parameter block table (<= kFusedMaxPhases entries)
   for (int i = c.tid; i < a.nphases; i += kFusedThreads) pb[i] = make_int2(a.phases[i].param_off, a.phases[i].param_bytes);
-  c.pb = pb;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -631,10 +641,9 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   c.my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int nback = a.nphases - a.split;
   c.total_pc = static_cast<uint32_t>(c.my_images * a.split + ((c.my_images + 1) >> 1) * nback);
-  c.pc_next = 0u; c.pnext = 0; c.knext = 0;
   if (c.lead && c.my_images > 0) {
-    mbar_arrive_expect_tx(c.in_full, static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(c.smem_base + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), c.in_full);
+    mbar_arrive_expect_tx(c.in_full(a), static_cast<uint32_t>(a.in_bytes));
+    bulk_load_1d(c.smem_base + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), c.in_full(a));
     refill(c, a, 0u);
   }
 }
@@ -645,15 +654,15 @@ __device__ __forceinline__ void cta_teardown(const Cx& c) {
 }
 // the image-dependent part of Rt for front phases of the CTA's k-th image / for the back phases that follow it
 __device__ __forceinline__ void rt_front(Rt& rt, const FusedArgs& a, int k, int my_images) {
-  const long long img = static_cast<long long>(blockIdx.x) + static_cast<long long>(k) * gridDim.x;
-  rt.pair_b = false; rt.ghead_a = nullptr; rt.ghead_b = nullptr;
-  rt.next_in = (k + 1 < my_images) ? a.in + (img + gridDim.x) * a.in_bytes : nullptr;
+  const int img = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+  rt.pair_b = false; rt.img_a = img; rt.img_b = img;
+  rt.next_img = (k + 1 < my_images) ? img + static_cast<int>(gridDim.x) : -1;
 }
 __device__ __forceinline__ void rt_back(Rt& rt, const FusedArgs& a, int k) {
-  const long long img = static_cast<long long>(blockIdx.x) + static_cast<long long>(k) * gridDim.x;
-  rt.pair_b = (k & 1) != 0; rt.out_shift = 0; rt.next_in = nullptr;
-  rt.ghead_b = a.out + img * a.head_bytes;                               // only used when pair_b
-  rt.ghead_a = rt.pair_b ? a.out + (img - gridDim.x) * a.head_bytes : rt.ghead_b;
+  const int img = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+  rt.pair_b = (k & 1) != 0; rt.out_shift = 0; rt.next_img = -1;
+  rt.img_b = img;                                                        // only used when pair_b
+  rt.img_a = rt.pair_b ? img - static_cast<int>(gridDim.x) : img;
 }
 
 #ifdef YF_TRACE
