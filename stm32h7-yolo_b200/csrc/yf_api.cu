@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <thread>
@@ -792,6 +793,55 @@ int32_t group_dispatch(Network* n, uint32_t count, F fn) {
   cudaSetDevice(n->device);
   return ok ? total : -1;
 }
+// Host -> host inference over several GPUs with DYNAMIC balancing: the GPUs of a box do not get equal shares of the
+// host's copy bandwidth (measured: 20 to 28 GB/s per GPU with eight copying at once), so a static equal split waits for
+// the slowest one.  Every member pulls the next chunk from a shared counter and queues it on its pipelined ring
+// (ring_submit returns at once unless all of that GPU's staging slots are busy -- which is the back-pressure that does the
+// balancing); heads land at the chunk's offset in the caller's buffer.
+int32_t group_run_dynamic(Network* n, const int8_t* in, int8_t* out, uint32_t count, size_t in_sz, size_t out_sz) {
+  std::atomic<uint32_t> next{0};
+  std::atomic<uint32_t>* pnext = &next;
+  auto body = [pnext, in, out, count, in_sz, out_sz](Network* c) -> int32_t {
+    PlanDev* pd = get_plan(c, c->H, c->W);
+    if (!pd) return -1;
+    uint32_t mine = 0;
+    for (;;) {
+      const uint32_t f0 = pnext->fetch_add(pd->cap);
+      if (f0 >= count) break;
+      const uint32_t nb = std::min<uint32_t>(pd->cap, count - f0);
+      if (!ring_submit(c, pd, in + static_cast<size_t>(f0) * in_sz, out + static_cast<size_t>(f0) * out_sz, nb, nullptr)) { ring_drain(c, pd); return -1; }
+      mine += nb;
+    }
+    if (!ring_wait(c, pd) || !check_mirrored_err(c)) return -1;
+    c->images += mine; c->last_ms = 0.f;
+    return static_cast<int32_t>(mine);
+  };
+  const size_t m = n->members.size();
+  for (size_t i = 1; i < m; ++i) {
+    Network* c = n->members[i];
+    n->workers[i]->post([c, body]() -> int32_t {
+      std::lock_guard<std::mutex> lk(g_dev_mu[c->device & 63]);
+      cudaSetDevice(c->device);
+      return body(c);
+    });
+  }
+  int32_t total = body(n);
+  bool ok = total >= 0;
+  for (size_t i = 1; i < m; ++i) {
+    std::string text;
+    const int32_t r = n->workers[i]->wait(&text);
+    Network* c = n->members[i];
+    if (r < 0) {
+      if (ok) { n->latch(c->err.type != AI_ERROR_NONE ? c->err.type : AI_ERROR_INVALID_STATE, c->err.code); set_text("device " + std::to_string(c->device) + ": " + text); }
+      ok = false;
+    } else if (ok) total += r;
+    c->err = ai_error{AI_ERROR_NONE, AI_ERROR_CODE_NONE};
+  }
+  cudaSetDevice(n->device);
+  return ok ? total : -1;
+}
+bool dynamic_ok(const Network* n) { return !n->step_profiling && !n->observer; }
+
 // run fn(member) on every member (settings that all devices must share); false if any fails
 template <class F>
 bool group_each(Network* n, F fn) {
@@ -1039,7 +1089,8 @@ static ai_i32 process(ai_handle network, const ai_buffer* input, ai_buffer* outp
     PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return 0;
     const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
     const int8_t* in = static_cast<const int8_t*>(input->data); int8_t* out = output ? static_cast<int8_t*>(output->data) : nullptr;
-    r = group_dispatch(n, input->n_batches, [in, out, in_sz, out_sz](Network* c, uint32_t f0, uint32_t cnt) {
+    if (out && dynamic_ok(n) && input->n_batches >= 2 * pd->cap) r = group_run_dynamic(n, in, out, input->n_batches, in_sz, out_sz);
+    else r = group_dispatch(n, input->n_batches, [in, out, in_sz, out_sz](Network* c, uint32_t f0, uint32_t cnt) {
       return run_images(c, in + f0 * in_sz, out ? out + f0 * out_sz : nullptr, cnt, false, nullptr);
     });
   } else {
@@ -1111,6 +1162,7 @@ AI_API_ENTRY int32_t yf_b200_run(ai_handle network, const void* in, void* out, u
     PlanDev* pd = get_plan(n, n->H, n->W); if (!pd) return -1;
     const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
     const int8_t* pi = static_cast<const int8_t*>(in); int8_t* po = static_cast<int8_t*>(out);
+    if (dynamic_ok(n) && count >= 2 * pd->cap) return group_run_dynamic(n, pi, po, count, in_sz, out_sz);
     return group_dispatch(n, count, [pi, po, in_sz, out_sz](Network* c, uint32_t f0, uint32_t cnt) {
       return run_images(c, pi + f0 * in_sz, po + f0 * out_sz, cnt, false, nullptr);
     });

@@ -37,6 +37,7 @@
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
 #include "yf_requant.cuh"
+#include "yf_pool.cuh"
 
 namespace yf {
 
@@ -199,11 +200,14 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
 
 // all (tile, chunk) units of a conv phase, split across the worker warps (no divisions)
 // (tiles t0 .. t0+nt-1 are the group whose accumulators sit in TMEM, tile t at column (t - t0) * npad)
-__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt, const FusedArgs& a) {
+// tcol0: TMEM column of the group's first tile (0 for the 1x1 layers, whose groups reuse the columns; the first conv
+// keeps every tile in its own columns)
+__device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt, const FusedArgs& a,
+                                              int tcol0 = 0) {
   const int q = c.warp & 3, chunks = ph.chunks_out;
   const uint8_t* lut = slot + ph.lut_off;
   const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
-  const uint32_t tq = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const uint32_t tq = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tcol0);
   if (nt >= kFusedWarpgroups) {
     // several tiles: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
     for (int t = c.warp >> 2; t < nt; t += kFusedWarpgroups) {
@@ -399,42 +403,6 @@ __device__ __forceinline__ void pool_phase_loops(const FusedPhase& ph, uint8_t* 
   }
 }
 
-// One line of a separable max-pool with window K, stride 2: a thread slides the window along a row (pass 1) or a
-// column (pass 2), keeping the K taps in registers (a ring whose slots are compile-time: the loop body is unrolled over
-// one ring revolution), so every input is loaded once per line -- the window-per-output form loads it K / 2 times.
-// Positions outside [0, len) contribute the identity (0 in the biased form), i.e. the maximum is over in-bounds cells.
-// BIASED_IN: the input already holds x ^ 0x80 per byte (pass 2 reads pass 1's row maxima).  emit(o, biased word).
-template <int K, bool BIASED_IN, class Emit>
-__device__ __forceinline__ void pool_line(const uint8_t* in, int in_step, int len, int pad, int o_begin, int o_end, Emit emit) {
-  constexpr int S = 2, G = K / S;
-  uint32_t ev[K], od[K];
-  auto ld = [&](int x, uint32_t& e, uint32_t& o) {
-    uint32_t v = BIASED_IN ? 0u : 0x80808080u;               // identity
-    if (static_cast<unsigned>(x) < static_cast<unsigned>(len)) v = *reinterpret_cast<const uint32_t*>(in + x * in_step);
-    if (!BIASED_IN) v ^= 0x80808080u;
-    e = v & 0x00ff00ffu; o = v & 0xff00ff00u;
-  };
-  int x = o_begin * S - pad;                                  // first tap of the first window
-#pragma unroll
-  for (int j = 0; j < K - S; ++j) ld(x + j, ev[j], od[j]);
-#pragma unroll 1
-  for (int o = o_begin; o < o_end; o += G) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-#pragma unroll
-      for (int t = 0; t < S; ++t) ld(x + K - S + t, ev[(K - S + g * S + t) % K], od[(K - S + g * S + t) % K]);
-      if (o + g < o_end) {
-        uint32_t me = ev[0], mo = od[0];
-#pragma unroll
-        for (int j = 1; j + 1 < K; j += 2) { me = __vimax3_u16x2(me, ev[j], ev[j + 1]); mo = __vimax3_u16x2(mo, od[j], od[j + 1]); }
-        if ((K & 1) == 0) { me = __vmaxu2(me, ev[K - 1]); mo = __vmaxu2(mo, od[K - 1]); }
-        emit(o + g, me | mo);
-      }
-      x += S;
-    }
-  }
-}
-
 // MAX_POOL_2D (+ QUANTIZE table), windows 8 and 4 at stride 2 (the two pools of yoloface): separable, lines in registers.
 // Pass 1: one thread per (input row, 4-channel word, segment of output columns) -> row maxima (biased) in the scratch;
 // pass 2: one thread per (output column, word, segment of output rows) -> table -> chunk-planar output.
@@ -573,35 +541,38 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
     if (ph.out_wp) fill_border(ph, smem, tid);
     wait_bar(c, a, par_bar, par_parity, 302);
     wait_bar(c, a, c.in_full(a), c.in_uses & 1, 303); ++c.in_uses;
+    // Software pipeline over rounds of two tiles: build the A rows of round r, issue its MMAs, then requantise the
+    // tiles of round r-1 while those MMAs run (one tile per warpgroup).  Waiting for round r-1's accumulators also
+    // frees the A stages round r+1 will overwrite (stage = tile & 3).
     const int rounds = (ntiles + 1) >> 1;
-    for (int r = 0; r < rounds; ++r) {
-      if (r >= 2) {                                          // the A stages of round r-2 must have been consumed
-        if (r & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 304); ++c.use0; }
-      }
-      im2col_build(ph, smem, tid, r);
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (c.ctrl) {
-        tc_fence_after();
-        const bool el = elect_one();
-        for (int h = 0; h < 2; ++h) {
-          const int tt = 2 * r + h;
-          if (tt >= ntiles) break;
-          const uint32_t sS = c.smem_base + ph.scratch_off + (tt & 3) * 6144;
-          for (int k = 0; k < 2; ++k)
-            if (el) mma_i8(c.tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
-                           static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
+    for (int r = 0; r <= rounds; ++r) {
+      if (r < rounds) {
+        im2col_build(ph, smem, tid, r);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (c.ctrl) {
+          tc_fence_after();
+          const bool el = elect_one();
+          for (int h = 0; h < 2; ++h) {
+            const int tt = 2 * r + h;
+            if (tt >= ntiles) break;
+            const uint32_t sS = c.smem_base + ph.scratch_off + (tt & 3) * 6144;
+            for (int k = 0; k < 2; ++k)
+              if (el) mma_i8(c.tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
+                             static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
+          }
+          if (el) mma_commit(c.mma_done(a) + 8 * (r & 1));
+          __syncwarp();
         }
-        if (el) mma_commit(c.mma_done(a) + 8 * (r & 1));
-        __syncwarp();
+      }
+      if (r >= 1) {
+        const int rp = r - 1;
+        if (rp & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 304); ++c.use0; }
+        tc_fence_after();
+        conv_epilogue(ph, c, slot, 2 * rp, min(2, ntiles - 2 * rp), rows, rt, a, 2 * rp * ph.npad);
+        tc_fence_before();
       }
     }
-    for (int r = (rounds >= 2 ? rounds - 2 : 0); r < rounds; ++r) {   // drain the last (up to) two rounds
-      if (r & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 305); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 305); ++c.use0; }
-    }
-    tc_fence_after();
-    conv_epilogue(ph, c, slot, 0, ntiles, rows, rt, a);
-    tc_fence_before();
     if (c.lead) housekeeping(c, a, rt, pf_here);
   } else {
     wait_bar(c, a, par_bar, par_parity, 302);

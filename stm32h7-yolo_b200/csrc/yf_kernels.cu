@@ -16,6 +16,7 @@
 #include "yf_kernels.cuh"
 #include "yf_ptx.cuh"
 #include "yf_requant.cuh"
+#include "yf_pool.cuh"
 
 namespace yf {
 
@@ -724,6 +725,46 @@ __global__ void __launch_bounds__(512) maxpool_band_kernel(const PoolArgs p, int
     int lo, hi; rows_of(b, &lo, &hi);
     const int oy0 = b * band, nrows = min(p.Hout, oy0 + band) - oy0, rin = hi - lo;
     const uint8_t* sin = stage0 + st * stage_bytes;
+    if (p.stride == 2 && (p.k == 8 || p.k == 4)) {
+      // Windows 8 / 4 at stride 2 (the pools of this model family): a thread slides the window along a LINE with the taps
+      // in registers (yf_pool.cuh), so every input is loaded once per line instead of k / 2 times; row maxima travel in
+      // the biased (x ^ 0x80) form.  pass 1: item = (staged input row, word, segment of 8 output columns)
+      const int segs1 = (p.Wout + 7) >> 3, n1 = ok ? rin * words * segs1 : 0;
+      for (int i = tid; i < n1; i += blockDim.x) {
+        const int wq = i % words, t = i / words, seg = t % segs1, r = t / segs1;
+        uint32_t* sc = reinterpret_cast<uint32_t*>(scratch) + static_cast<size_t>(r) * p.Wout * words + wq;
+        auto emit = [&](int o, uint32_t m) { sc[o * words] = m; };
+        const uint8_t* in = sin + r * row_bytes + wq * 4;
+        if (p.k == 8) pool_line<8, false>(in, p.in_pitch, p.Win, p.pad_l, seg * 8, min(p.Wout, seg * 8 + 8), emit);
+        else pool_line<4, false>(in, p.in_pitch, p.Win, p.pad_l, seg * 8, min(p.Wout, seg * 8 + 8), emit);
+      }
+      __syncthreads();
+      // pass 2: item = (output column, word, segment of 8 output rows of the band); rows are addressed relative to the
+      // first staged row `lo` (the window of every output row of the band lies inside the staged rows)
+      const int segs2 = (nrows + 7) >> 3, n2 = ok ? p.Wout * words * segs2 : 0;
+      for (int i = tid; i < n2; i += blockDim.x) {
+        const int wq = i % words, t = i / words, ox = t % p.Wout, seg = t / p.Wout;
+        const int c0 = wq * 4;
+        const uint8_t* in = scratch + (static_cast<size_t>(ox) * words + wq) * 4;
+        auto emit = [&](int oy, uint32_t m) {
+          if (p.eo.lut1)
+            m = static_cast<uint32_t>(sLut[m & 0xff]) | (static_cast<uint32_t>(sLut[(m >> 8) & 0xff]) << 8) |
+                (static_cast<uint32_t>(sLut[(m >> 16) & 0xff]) << 16) | (static_cast<uint32_t>(sLut[m >> 24]) << 24);
+          else
+            m ^= neg;
+          if (c0 + 4 > p.eo.cout) m &= c0 < p.eo.cout ? (1u << (8 * (p.eo.cout - c0))) - 1u : 0u;      // pad channels: 0
+          const long long row = (static_cast<long long>(img) * p.Hout + oy) * p.Wout + ox;
+          int8_t* o = p.eo.out + row * p.eo.out_pitch + p.eo.out_coff + c0;
+          if (c0 + 4 <= lim && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t*>(o) = m;
+          else for (int j = 0; j < 4; ++j) if (c0 + j < lim) o[j] = static_cast<int8_t>((m >> (8 * j)) & 0xff);
+        };
+        const int ob = oy0 + seg * 8, oe = min(oy0 + nrows, ob + 8);
+        if (p.k == 8) pool_line<8, true>(in, p.Wout * words * 4, rin, p.pad_t + lo, ob, oe, emit);
+        else pool_line<4, true>(in, p.Wout * words * 4, rin, p.pad_t + lo, ob, oe, emit);
+      }
+      __syncthreads();                                        // stage and scratch are free again
+      continue;
+    }
     // pass 1: item = (staged input row, output column, word)
     const int n1 = ok ? rin * p.Wout * words : 0;
     for (int i = tid; i < n1; i += blockDim.x) {

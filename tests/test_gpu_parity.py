@@ -99,6 +99,19 @@ def test_ragged_batches(net, oracle, golden, n):
     assert np.array_equal(net.run(x), oracle.run_batch(x, threads=os.cpu_count()))
 
 
+@pytest.mark.parametrize("n", [445, 889, 1333, 2049, 4096])
+def test_many_images_per_cta(yf, oracle, golden, n):
+    """One launch with more images than resident CTA slots (444): every CTA of the fused kernel walks
+    front(A), front(B), back(A+B), front(C), ... -- pairs, a trailing single image when its count is odd, parameter
+    blocks streamed in that order -- and the strided image assignment must put every head where it belongs."""
+    big = yf.Network(chunk_images=4096, mode="fused")
+    try:
+        x = real_batch(golden, n, 1000 + n)
+        assert np.array_equal(big.run(x), oracle.run_batch(x, threads=os.cpu_count()))
+    finally:
+        big.close()
+
+
 def test_large_batch_properties(net, oracle, golden):
     """Full-size check through size-independent properties: a 16,384-image batch built by tiling
     64 distinct images must give the tiled 64 heads (batch independence), and a permutation of the

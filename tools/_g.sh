@@ -1,33 +1,15 @@
-mkdir -p gpurun_out/r2k
-nvidia-smi topo -m > gpurun_out/r2k/topo.txt 2>&1
-for n in 2 4 8; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 tools/h2d_ceiling.py > gpurun_out/r2k/h2d_n$n.json 2> gpurun_out/r2k/h2d_n$n.err
-done
-cat gpurun_out/r2k/h2d_n*.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2k/bench_n8.json 2> gpurun_out/r2k/bench_n8.err; echo "bench8 rc $?"
-timeout 300 python -m pytest tests/test_multi_gpu_handle.py -m gpu -x -q > gpurun_out/r2k/pytest_mg8.log 2>&1; tail -3 gpurun_out/r2k/pytest_mg8.log
+mkdir -p gpurun_out/r2o
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2o/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2o/pytest.log
+tail -4 gpurun_out/r2o/pytest.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2o/bench.json 2> gpurun_out/r2o/bench.err; echo "bench rc $?"; tail -2 gpurun_out/r2o/bench.err
 python - <<'PY'
 import json
-d=json.load(open("gpurun_out/r2k/bench_n8.json"))
-print("N8 value", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"].get("bounds"), "config3", d.get("config3"))
+d=json.load(open("gpurun_out/r2o/bench.json"))
+print("value", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["sustained_aggregate"]["value"], d["e2e"]["bounds"]["box_fed_images_per_s"], "serial", d["serial"]["value"], "1img", d["e2e"]["single_image_call_us"])
+print("config4", d["config4"]["batch_16"]["images_per_s"], d["config4"]["batch_4096"]["images_per_s"], d["config4"]["dominant_kernel"])
+print("extra", d["extra"])
 PY
-# one handle over 8 GPUs, host buffers: throughput of a single blocking call
-python - <<'PY' > gpurun_out/r2k/one_handle.log 2>&1
-import sys, time, numpy as np, torch
-sys.path.insert(0, "tests")
-import pkg
-yf = pkg.load()
-for devs in ([0], [0, 1], [0, 1, 2, 3], list(range(8))):
-    net = yf.Network(devices=devs, chunk_images=1024)
-    n = 65536
-    x = torch.randint(-128, 128, (n, 56, 56, 3), dtype=torch.int8).pin_memory()
-    y = torch.empty((n, 7, 7, 18), dtype=torch.int8).pin_memory()
-    net.run(x, y, n=n)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        net.run(x, y, n=n)
-    dt = (time.perf_counter() - t0) / 3
-    print("devices", len(devs), "yf_b200_run(65536 pinned host images): %.2f M img/s (%.1f ms)" % (n / dt / 1e6, dt * 1e3))
-    net.close()
-PY
-cat gpurun_out/r2k/one_handle.log
+YF_B200_MODE=layered timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r2o/bench_layered.json 2> gpurun_out/r2o/bench_layered.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2o/bench_layered.json')); print('layered value', d['value'], 'serial', d['serial']['value'])"
+YF_B200_LIB=stm32h7-yolo_b200/libyoloface_b200_trace.so timeout 120 python tools/fused_trace.py 8192 > gpurun_out/r2o/trace8192.log 2>&1; grep "img 1 front conv3x3\|img 1 front conv1x1_6\|^total" gpurun_out/r2o/trace8192.log

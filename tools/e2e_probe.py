@@ -8,6 +8,7 @@ aggregate images/s (or the images/s a raw copy rate could feed) per variant:
   raw_h2d_64M        pinned -> device copies of 64 MiB blocks (tools/h2d_ceiling.py: the box ceiling)
   raw_h2d_2M4        the same with 2.4 MB blocks (one 256-image batch) from a ring of 64 buffers
   raw_h2d_2M4+d2h    ... while a second stream copies 226 KB blocks device -> pinned host (the heads)
+  raw_h2d_2M4_2streams   2.4 MB blocks alternating over two streams
   submit_256         yf_b200_submit per 256-image step, continuous (one yf_b200_wait at the end of the variant)
   submit_256_x20     the bench's e2e region: 20 submits + yf_b200_wait, repeated
   submit_1024        yf_b200_submit per 1,024-image step, continuous
@@ -76,6 +77,18 @@ def main():
         dt = time.perf_counter() - t0
         barrier()
         res["raw_h2d_2M4+d2h" if with_d2h else "raw_h2d_2M4"] = total(k * 256 / dt)
+    # two copy streams alternating: does the set-up of one copy hide behind the transfer of the other?
+    barrier()
+    t0 = time.perf_counter(); k = 0
+    while time.perf_counter() - t0 < SECONDS:
+        for _ in range(16):
+            with torch.cuda.stream(s1 if k & 1 else s2):
+                d_in[k % 8].copy_(h_in[k % 64], non_blocking=True)
+            k += 1
+        s1.synchronize(); s2.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    res["raw_h2d_2M4_2streams"] = total(k * 256 / dt)
     # ---- the library ----
     yf = pkg.load()
     net = yf.Network(device=local, chunk_images=1024)
