@@ -76,7 +76,16 @@ __device__ __forceinline__ void epi_bar_arrive(int threads) { asm volatile("bar.
 // lead thread only: where the stream of parameter blocks stands.  Block j may be requested once block
 // j - kFusedParamSlots (the slot's previous tenant) belongs to a finished phase, i.e. j < pc + kFusedParamSlots.
 // Lives in shared memory: one thread touches it a few times per phase, and 255 threads do not pay registers for it.
-struct Producer { uint32_t pc_next; int pnext, knext, pad_; };
+struct Producer {
+  uint32_t pc_next; int pnext, knext;          // state: next block to request, its phase, that phase's image index
+  uint32_t total_pc;                           // the rest: launch / CTA constants, so that the out-of-line housekeeping
+  int my_images, split, nphases;               // routine needs three scalar arguments and no kernel parameter
+  uint32_t slots_addr; int slot_bytes;         // shared address of slot 0, bytes per slot
+  uint32_t in_addr; int in_bytes;              // shared address of the input image buffer
+  int pad_;
+  const uint8_t* params; const int8_t* in;
+};
+static_assert(sizeof(Producer) <= 72, "Producer must fit between the TMEM word and the parameter-block table");
 struct Cx {
   uint8_t* smem;
   uint32_t smem_base, tmem_base;
@@ -91,7 +100,7 @@ struct Cx {
   __device__ __forceinline__ uint32_t par_full(const FusedArgs& a) const { return smem_base + a.bars_off + 8; }
   __device__ __forceinline__ uint32_t mma_done(const FusedArgs& a) const { return smem_base + a.bars_off + 8 + 8 * kFusedParamSlots; }
   __device__ __forceinline__ Producer* producer(const FusedArgs& a) const { return reinterpret_cast<Producer*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots) + 8); }
-  __device__ __forceinline__ const int2* pb(const FusedArgs& a) const { return reinterpret_cast<const int2*>(smem + a.bars_off + 96); }   // {param_off, param_bytes} per phase
+  __device__ __forceinline__ const int2* pb(const FusedArgs& a) const { return reinterpret_cast<const int2*>(smem + a.bars_off + 128); }   // {param_off, param_bytes} per phase
 };
 // what changes from one execution of a phase to the next
 struct Rt {
@@ -112,27 +121,33 @@ __device__ __forceinline__ void advance_phase(int& p, int& k, int split, int nph
   } else if (p == nph - 1) { p = 0; ++k; }
   else ++p;
 }
-__device__ __forceinline__ void refill(Cx& c, const FusedArgs& a, uint32_t pc_now) {
-  Producer* pr = c.producer(a);
+// Lead thread, off the critical path: refill the slot the previous phase released and (next_img >= 0) prefetch the next
+// image into the input buffer, which is free after phase 0.  Deliberately OUT OF LINE: one thread runs it two or three
+// times per phase, and inlined at every call site it was ~18 % of the specialised kernel's code (instruction-cache
+// misses are the largest stall of an isolated launch).  `bars` = shared address of the barrier region.
+static __device__ __noinline__ void housekeeping_out(uint32_t bars, uint32_t pc_now, int next_img) {
+  Producer* pr = reinterpret_cast<Producer*>(__cvta_shared_to_generic(bars + 8 * (3 + kFusedParamSlots) + 8));
+  const int2* pb = reinterpret_cast<const int2*>(__cvta_shared_to_generic(bars + 128));
   uint32_t pc_next = pr->pc_next; int pnext = pr->pnext, knext = pr->knext;
+  const uint32_t total_pc = pr->total_pc, par_full = bars + 8;
+  const int split = pr->split, nph = pr->nphases, my_images = pr->my_images;
 #pragma unroll 1
-  while (pc_next < c.total_pc && pc_next < pc_now + kFusedParamSlots) {
-    const int2 e = c.pb(a)[pnext];
-    const uint32_t s = pc_next % kFusedParamSlots, bar = c.par_full(a) + 8 * s;
+  while (pc_next < total_pc && pc_next < pc_now + kFusedParamSlots) {
+    const int2 e = pb[pnext];
+    const uint32_t s = pc_next % kFusedParamSlots, bar = par_full + 8 * s;
     mbar_arrive_expect_tx(bar, static_cast<uint32_t>(e.y));
-    bulk_load_1d(c.smem_base + a.slot_off + s * a.slot_bytes, a.params + e.x, static_cast<uint32_t>(e.y), bar);
+    bulk_load_1d(pr->slots_addr + s * pr->slot_bytes, pr->params + e.x, static_cast<uint32_t>(e.y), bar);
     ++pc_next;
-    advance_phase(pnext, knext, a.split, a.nphases, c.my_images);
+    advance_phase(pnext, knext, split, nph, my_images);
   }
   pr->pc_next = pc_next; pr->pnext = pnext; pr->knext = knext;
-}
-// lead thread, off the critical path: refill the slot the previous phase released, prefetch the next image
-__device__ __forceinline__ void housekeeping(Cx& c, const FusedArgs& a, const Rt& rt, bool prefetch_image) {
-  refill(c, a, rt.pc);
-  if (prefetch_image && rt.next_img >= 0) {                  // the image buffer is free after phase 0
-    mbar_arrive_expect_tx(c.in_full(a), static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(c.smem_base + a.in_off, a.in + static_cast<long long>(rt.next_img) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), c.in_full(a));
+  if (next_img >= 0) {
+    mbar_arrive_expect_tx(bars, static_cast<uint32_t>(pr->in_bytes));
+    bulk_load_1d(pr->in_addr, pr->in + static_cast<long long>(next_img) * pr->in_bytes, static_cast<uint32_t>(pr->in_bytes), bars);
   }
+}
+__device__ __forceinline__ void housekeeping(Cx& c, const FusedArgs& a, const Rt& rt, bool prefetch_image) {
+  housekeeping_out(c.smem_base + a.bars_off, rt.pc, prefetch_image ? rt.next_img : -1);
 }
 
 // border cells of a padded output buffer <- the tensor's zero point (run by the workers while the MMAs are in flight)
@@ -600,10 +615,9 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   if (c.tid == 0) {
     for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
     fence_mbar_init();
-    *c.producer(a) = Producer{0u, 0, 0, 0};
   }
   if (c.warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
-  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 96);           // parameter block table (<= kFusedMaxPhases entries)
+  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 128);          // parameter block table (<= kFusedMaxPhases entries)
   for (int i = c.tid; i < a.nphases; i += kFusedThreads) pb[i] = make_int2(a.phases[i].param_off, a.phases[i].param_bytes);
   tc_fence_before();
   __syncthreads();
@@ -612,10 +626,13 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   c.my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int nback = a.nphases - a.split;
   c.total_pc = static_cast<uint32_t>(c.my_images * a.split + ((c.my_images + 1) >> 1) * nback);
-  if (c.lead && c.my_images > 0) {
-    mbar_arrive_expect_tx(c.in_full(a), static_cast<uint32_t>(a.in_bytes));
-    bulk_load_1d(c.smem_base + a.in_off, a.in + static_cast<long long>(blockIdx.x) * a.in_bytes, static_cast<uint32_t>(a.in_bytes), c.in_full(a));
-    refill(c, a, 0u);
+  if (c.lead) {
+    Producer pr{};
+    pr.total_pc = c.total_pc; pr.my_images = c.my_images; pr.split = a.split; pr.nphases = a.nphases;
+    pr.slots_addr = c.smem_base + a.slot_off; pr.slot_bytes = a.slot_bytes;
+    pr.in_addr = c.smem_base + a.in_off; pr.in_bytes = a.in_bytes; pr.params = a.params; pr.in = a.in;
+    *c.producer(a) = pr;
+    if (c.my_images > 0) housekeeping_out(c.smem_base + a.bars_off, 0u, static_cast<int>(blockIdx.x));   // first image + first blocks
   }
 }
 __device__ __forceinline__ void cta_teardown(const Cx& c) {

@@ -79,12 +79,16 @@ static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity
     if (clock64() - t0 > (1ll << 32)) return false;
   }
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;                 // the common case: already complete
+// (the retry path is out of line: mbar_wait is inlined at ~80 sites of the fused kernel)
+static __device__ __noinline__ bool mbar_wait_retry(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
   for (int i = 0; i < 16; ++i)
     if (mbar_try_wait_suspend(bar, parity, 4000u)) return true;
   return mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;                 // the common case: already complete
+  return mbar_wait_retry(bar, parity);
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) { return mbar_wait(smem_u32(bar), parity); }
 
