@@ -1,24 +1,8 @@
-mkdir -p gpurun_out/r2p
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_second_model.py -m gpu -x -q > gpurun_out/r2p/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2p/pytest.log
-tail -3 gpurun_out/r2p/pytest.log
-for i in 1 2; do
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r2p/bench$i.json 2> gpurun_out/r2p/bench$i.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2p/bench$i.json')); print('value', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'serial', d['serial']['value'], 'launch', d['roofline']['launch_ms'], '1img', d['e2e']['single_image_call_us'])"
-done
-python - <<'PY'
-import sys, time, torch
-sys.path.insert(0, "tests")
-import pkg
-yf = pkg.load()
-net = yf.Network(chunk_images=8192)
-x = torch.randint(-128, 128, (8192, 56, 56, 3), dtype=torch.int8, device="cuda"); y = torch.empty((8192, 7, 7, 18), dtype=torch.int8, device="cuda")
-st = torch.cuda.Stream(); net.set_stream(st.cuda_stream)
-for _ in range(3): net.enqueue(x, y, 8192)
-net.sync()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(st)
-for _ in range(20): net.enqueue(x, y, 8192)
-e1.record(st); e1.synchronize()
-print("8192/launch: %.3f M img/s" % (8192 * 20 / e0.elapsed_time(e1) / 1e3))
-PY
+mkdir -p gpurun_out/r2q
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:yoloface_fused -s 2 -c 1 -o gpurun_out/r2q/fused_v10_b8192 -f python tools/run_once.py 8192 fused 3 > gpurun_out/r2q/ncu8192.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:yoloface_fused -s 2 -c 1 -o gpurun_out/r2q/fused_v10_b256 -f python tools/run_once.py 256 fused 3 > gpurun_out/r2q/ncu256.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2q/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extra > gpurun_out/r2q/ncu_bench.log 2>&1
+YF_B200_LIB=stm32h7-yolo_b200/libyoloface_b200_trace.so timeout 120 python tools/fused_trace.py 8192 > gpurun_out/r2q/trace8192.log 2>&1
+YF_B200_LIB=stm32h7-yolo_b200/libyoloface_b200_trace.so timeout 120 python tools/fused_trace.py 256 > gpurun_out/r2q/trace256.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2q/smoke.log 2>&1; cat gpurun_out/r2q/smoke.log | tail -2
+ls -la gpurun_out/r2q
