@@ -57,7 +57,7 @@ class Det(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("images", C.c_uint64), ("last_run_device_ms", C.c_float),
                 ("device", C.c_int32), ("sm_count", C.c_int32), ("chunk_images", C.c_uint32), ("steps", C.c_int32),
-                ("fused", C.c_int32), ("fused_smem_bytes", C.c_int32)]
+                ("fused", C.c_int32), ("fused_smem_bytes", C.c_int32), ("fused_latency", C.c_int32), ("latency_launches", C.c_uint32)]
 
 
 class StepInfo(C.Structure):
@@ -73,7 +73,7 @@ EXPORTS = [
     "ai_network_data_params_get", "yf_b200_set_input_size", "yf_b200_run", "yf_b200_decode", "yf_b200_detect",
     "yf_b200_preprocess_rgb565", "yf_b200_set_decode_params", "yf_b200_set_observer", "yf_b200_get_tensor", "yf_b200_tensor_shape",
     "yf_b200_get_stats", "yf_b200_step_count", "yf_b200_step_info_get", "yf_b200_set_step_profiling",
-    "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_enqueue_batches", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_debug_raise", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json",
+    "yf_b200_fused_trace", "yf_b200_submit", "yf_b200_wait", "yf_b200_set_stream", "yf_b200_enqueue", "yf_b200_enqueue_batches", "yf_b200_sync", "yf_b200_host_alloc", "yf_b200_host_free", "yf_b200_last_error_text", "yf_b200_debug_raise", "yf_b200_plan_json", "yf_b200_plan_blob", "yf_b200_fused_json", "yf_b200_fused_json_ex",
 ]
 
 _lib = None
@@ -158,6 +158,8 @@ def lib():
     L.yf_b200_plan_json.argtypes = [i32, i32, vp, C.c_char_p, C.c_uint64]
     L.yf_b200_fused_json.restype = C.c_int64
     L.yf_b200_fused_json.argtypes = [i32, i32, vp, C.c_char_p, C.c_uint64]
+    L.yf_b200_fused_json_ex.restype = C.c_int64
+    L.yf_b200_fused_json_ex.argtypes = [i32, i32, vp, i32, C.c_char_p, C.c_uint64]
     L.yf_b200_plan_blob.restype = C.c_int64
     L.yf_b200_plan_blob.argtypes = [i32, i32, vp, i32, vp, C.c_uint64]
     _lib = L
@@ -215,17 +217,18 @@ def plan(height=56, width=56, blob=None):
 EPI_DTYPE = np.dtype([("add64", "<i8"), ("mult", "<i4"), ("c2", "<i4"), ("e", "<i4"), ("ls", "<i4"), ("sgn_mask", "<i4"), ("acc_bound", "<i4")])
 
 
-def fused_program(height=56, width=56, blob=None):
-    """Fused single-kernel program (smem map, phases, parameter blob, EpiCh table); no GPU needed."""
+def fused_program(height=56, width=56, blob=None, threads=256):
+    """Fused single-kernel program (smem map, phases, parameter blob, EpiCh table); no GPU needed.
+    threads: CTA shape the program is laid out for (256 throughput, 512 latency)."""
     L = lib()
     bp = C.create_string_buffer(blob, len(blob)) if blob is not None else None
-    n = L.yf_b200_fused_json(height, width, bp, None, 0)
+    n = L.yf_b200_fused_json_ex(height, width, bp, threads, None, 0)
     if n < 0:
         raise RuntimeError(L.yf_b200_last_error_text().decode())
     buf = C.create_string_buffer(n)
-    L.yf_b200_fused_json(height, width, bp, buf, n)
+    L.yf_b200_fused_json_ex(height, width, bp, threads, buf, n)
     prog = json.loads(buf.value.decode())
-    for key, what in (("params", 3), ("epi", 4)):
+    for key, what in (("params", 5 if threads == 512 else 3), ("epi", 4)):
         k = L.yf_b200_plan_blob(height, width, bp, what, None, 0)
         raw = C.create_string_buffer(max(int(k), 1))
         L.yf_b200_plan_blob(height, width, bp, what, raw, k)

@@ -74,11 +74,18 @@ struct PlanDev {
   uint8_t* d_fparams = nullptr;
   FusedPhase* d_fphases = nullptr;      // this plan's phase descriptors (global memory: nothing is shared between plans)
   bool fused_spec = false;              // the plan is the one the specialised kernel was generated from
+  // the same plan laid out for the latency shape (512-thread CTAs, one per SM): launches of at most one image per SM
+  // that run alone.  Exists only where the specialised latency kernel does (deployed model at its own resolution).
+  FusedProgram fprog_lat;
+  uint8_t* d_fparams_lat = nullptr;
+  FusedPhase* d_fphases_lat = nullptr;
+  bool fused_lat = false;
   ~PlanDev() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (int l = 1; l < kLayerLanes; ++l) cudaFree(d_arena_l[l]);
     cudaFree(d_epi); cudaFree(d_epif);
     cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams); cudaFree(d_fphases);
+    cudaFree(d_fparams_lat); cudaFree(d_fphases_lat);
     for (int i = 0; i < kRing; ++i) { cudaFree(r_in[i]); cudaFree(r_head[i]); }
     for (int i = 0; i < kRing; ++i) { if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]); if (ev_comp[i]) cudaEventDestroy(ev_comp[i]); if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]); }
   }
@@ -140,6 +147,7 @@ struct Network {
   uint32_t last_run_n = 0;
   ai_buffer rep_in{}, rep_out{};        // I/O descriptors handed out by ai_network_get_report
   uint64_t launches = 0, images = 0;
+  uint32_t lat_launches = 0;            // fused launches that took the latency shape
   float last_ms = 0.f;
   // Multi-GPU context (yf_b200_config.device_mask / YF_B200_DEVICES): members[0] is this object, the others are
   // contexts on the other GPUs owned by it and driven by workers[i]; a member's `owner` points back here.
@@ -325,7 +333,18 @@ PlanDev* get_plan(Network* n, int H, int W) {
     if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fphases, pd->fprog.phases.data(), dbytes, cudaMemcpyHostToDevice, n->stream), "upload fused descriptors")) return nullptr;
     static const bool spec_off = [] { const char* e = std::getenv("YF_B200_FUSED_SPEC"); return e && !std::atoi(e); }();
     pd->fused_spec = !spec_off && fused_spec_matches(pd->fprog);
-    if (!cuda_ok(n, fused_init(pd->fprog.smem_bytes, pd->fused_spec ? pd->fprog.smem_bytes_spec : 0), "fused kernel attributes")) return nullptr;
+    if (!cuda_ok(n, fused_init(pd->fprog, pd->fused_spec), "fused kernel attributes")) return nullptr;
+    const char* lat_env = std::getenv("YF_B200_FUSED_LAT");      // diagnostics / tests: 0 keeps every launch on the throughput shape
+    const bool lat_off = lat_env && !std::atoi(lat_env);
+    if (pd->fused_spec && !lat_off && build_fused(pd->fplan, &pd->fprog_lat, kFusedLatThreads) && pd->fprog_lat.ok && fused_spec_matches(pd->fprog_lat)) {
+      const FusedProgram& FL = pd->fprog_lat;
+      if (!cuda_ok(n, cudaMalloc(&pd->d_fparams_lat, FL.params.size()), "cudaMalloc fused params", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+      if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fparams_lat, FL.params.data(), FL.params.size(), cudaMemcpyHostToDevice, n->stream), "upload fused params")) return nullptr;
+      if (!cuda_ok(n, cudaMalloc(&pd->d_fphases_lat, dbytes), "cudaMalloc fused descriptors", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+      if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fphases_lat, FL.phases.data(), dbytes, cudaMemcpyHostToDevice, n->stream), "upload fused descriptors")) return nullptr;
+      if (!cuda_ok(n, fused_init(FL, true), "fused kernel attributes")) return nullptr;
+      pd->fused_lat = true;
+    }
   } else {
     pd->fprog.ok = false;
     if (pd->fprog.why.empty()) pd->fprog.why = ferr;
@@ -455,8 +474,12 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
     L.d_in = d_in; L.d_out = d_head; L.d_params = pd->d_fparams; L.d_phases = pd->d_fphases; L.n_img = static_cast<int>(nb);
     L.sm_count = n->sm_count; L.d_err = n->d_err; L.stream = st; L.d_trace = n->trace_on ? n->d_trace : nullptr;
     L.use_spec = pd->fused_spec; L.overlapped = overlapped;
-    if (!cuda_ok(n, launch_fused(pd->fprog, L), "fused kernel")) return false;
+    // a launch that runs alone with at most one image per SM: the latency shape (twice the warps on each image)
+    const bool lat = pd->fused_lat && !overlapped && static_cast<int>(nb) <= n->sm_count;
+    if (lat) { L.d_params = pd->d_fparams_lat; L.d_phases = pd->d_fphases_lat; }
+    if (!cuda_ok(n, launch_fused(lat ? pd->fprog_lat : pd->fprog, L), "fused kernel")) return false;
     ++n->launches;
+    if (lat) ++n->lat_launches;
     return true;
   }
   if (!prepare_layer_lane(n, pd, lane)) return false;
@@ -543,7 +566,8 @@ bool ring_prepare(Network* n, PlanDev* pd) {
   return true;
 }
 // queue one chunk (nb <= cap) from host memory; returns without waiting.  out may be NULL (heads stay in the slot).
-bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_host, uint32_t nb, int8_t** slot_heads) {
+// alone: nothing else is queued around this chunk (a blocking call that fits one piece) -> the launch may take the latency shape
+bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_host, uint32_t nb, int8_t** slot_heads, bool alone = false) {
   if (!ring_prepare(n, pd)) return false;
   const int s = static_cast<int>(pd->seq++ % PlanDev::kRing);
   const size_t in_sz = static_cast<size_t>(pd->plan.H) * pd->plan.W * 3, out_sz = head_bytes(pd);
@@ -552,7 +576,7 @@ bool ring_submit(Network* n, PlanDev* pd, const int8_t* in_host, int8_t* out_hos
   cudaEventRecord(pd->ev_h2d[s], n->s_h2d);
   cudaStream_t ks = uses_fused(n, pd) ? n->lane[n->lane_seq++ % n->lanes] : n->stream;
   cudaStreamWaitEvent(ks, pd->ev_h2d[s], 0);
-  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb, ks, true)) return false;
+  if (!run_steps(n, pd, pd->r_in[s], pd->r_head[s], nb, ks, !alone)) return false;
   cudaEventRecord(pd->ev_comp[s], ks);
   cudaStreamWaitEvent(n->s_d2h, pd->ev_comp[s], 0);
   if (out_host && !cuda_ok(n, cudaMemcpyAsync(out_host, pd->r_head[s], nb * out_sz, cudaMemcpyDeviceToHost, n->s_d2h), "D2H output", AI_ERROR_INVALID_OUTPUT, AI_ERROR_CODE_INVALID_PTR)) return false;
@@ -621,7 +645,7 @@ int32_t run_images(Network* n, const void* in, void* out, uint32_t count, bool k
     if (uses_fused(n, pd) && count >= 512) piece = std::min<uint32_t>(pd->cap, std::max<uint32_t>(256, ((count + 3) / 4 + 15) & ~15u));
     for (uint32_t done = 0; done < count; done += piece) {
       const uint32_t nb = std::min<uint32_t>(piece, count - done);
-      if (!ring_submit(n, pd, static_cast<const int8_t*>(in) + done * in_sz, static_cast<int8_t*>(out) + done * out_sz, nb, nullptr)) {
+      if (!ring_submit(n, pd, static_cast<const int8_t*>(in) + done * in_sz, static_cast<int8_t*>(out) + done * out_sz, nb, nullptr, count <= piece)) {
         ring_drain(n, pd);                                  // copies into the caller's buffers must not stay pending
         return -1;
       }
@@ -1437,6 +1461,9 @@ AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* st) {
   st->steps = it == n->plans.end() ? 0 : static_cast<int32_t>(it->second->plan.steps.size());
   st->fused = (it != n->plans.end() && !n->observer && !n->step_profiling && n->mode != 1 && it->second->fprog.ok) ? 1 : 0;
   st->fused_smem_bytes = it == n->plans.end() ? 0 : it->second->fprog.smem_bytes;
+  st->fused_latency = (st->fused && it->second->fused_lat) ? 1 : 0;
+  st->latency_launches = n->lat_launches;
+  for (size_t i = 1; i < n->members.size(); ++i) st->latency_launches += n->members[i]->lat_launches;
   return 0;
 }
 
@@ -1563,26 +1590,29 @@ AI_API_ENTRY int64_t yf_b200_plan_json(int32_t H, int32_t W, const void* blob, c
   return static_cast<int64_t>(j.size() + 1);
 }
 
-static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedProgram* F) {
+static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedProgram* F, int threads = kFusedWorkerThreads) {
   TflModel model;
   if (!host_model(&model)) return false;
   size_t need = 0; st_blob_layout(model, &need);
   std::string perr;
   const bool st = std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS"));
   if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr, 16, st)) { set_text("plan: " + perr); return false; }
-  build_fused(*P, F);
+  build_fused(*P, F, threads);
   if (!F->ok) { set_text("fused: " + F->why); return false; }
   return true;
 }
 
 AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, char* dst, uint64_t cap) {
+  return yf_b200_fused_json_ex(H, W, blob, kFusedWorkerThreads, dst, cap);
+}
+AI_API_ENTRY int64_t yf_b200_fused_json_ex(int32_t H, int32_t W, const void* blob, int32_t threads, char* dst, uint64_t cap) {
   Plan P; FusedProgram F;
-  if (!host_fused(H, W, blob, &P, &F)) return -1;
+  if (!host_fused(H, W, blob, &P, &F, threads)) return -1;
   std::string j = "{";
   auto kv = [&](const char* k, long long v, bool comma = true) { j += std::string("\"") + k + "\":" + std::to_string(v) + (comma ? "," : ""); };
   kv("in_off", F.in_off); kv("in_bytes", F.in_bytes); kv("arena_off", F.arena_off); kv("arena_bytes", F.arena_bytes);
   kv("slot_off", F.slot_off); kv("slot_bytes", F.slot_bytes); kv("smem_bytes", F.smem_bytes); kv("head_bytes", F.head_bytes);
-  kv("warpgroups", kFusedWarpgroups); kv("tmem_cols", kFusedTmemCols); kv("param_slots", kFusedParamSlots); kv("desc_off", F.desc_off);
+  kv("threads", F.threads); kv("warpgroups", F.threads / 128); kv("tmem_cols", F.tmem_cols); kv("param_slots", kFusedParamSlots); kv("desc_off", F.desc_off);
   kv("in_pf_phase", F.in_pf_phase); kv("split", F.split); kv("smem_bytes_spec", F.smem_bytes_spec); kv("spec", fused_spec_matches(F) ? 1 : 0);
   j += "\"phases\":[";
   for (size_t i = 0; i < F.phases.size(); ++i) {
@@ -1609,7 +1639,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
 
 AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t H, int32_t W, const void* blob, int32_t what, void* dst, uint64_t cap) {
   Plan P; FusedProgram F;
-  if (what >= 3 ? !host_fused(H, W, blob, &P, &F) : !host_plan(H, W, blob, &P)) return -1;
+  if (what >= 3 ? !host_fused(H, W, blob, &P, &F, what == 5 ? kFusedLatThreads : kFusedWorkerThreads) : !host_plan(H, W, blob, &P)) return -1;
   const void* src; size_t n;
   switch (what) {
     case 0: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
@@ -1617,6 +1647,7 @@ AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t H, int32_t W, const void* blob, i
     case 2: src = P.wblob.data(); n = P.wblob.size(); break;
     case 3: src = F.params.data(); n = F.params.size(); break;
     case 4: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
+    case 5: src = F.params.data(); n = F.params.size(); break;
     default: return -1;
   }
   if (dst && cap) std::memcpy(dst, src, std::min<size_t>(cap, n));

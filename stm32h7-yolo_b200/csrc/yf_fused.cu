@@ -49,6 +49,8 @@ struct FusedArgs {
   int* err;
   long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first images
   int trace_phase;            // phase whose inner stamps (trace[96..127]) are recorded
+  int2 pb[kFusedMaxPhases];   // {param_off, param_bytes} per phase: in the kernel's parameter space, so that a CTA's first
+                              // bulk copies do not wait for a global-memory load of the table
 };
 #ifdef YF_TRACE
 #define YF_STAMP(tp, i) do { if (tp) (tp)[i] = clock64(); } while (0)
@@ -56,9 +58,16 @@ struct FusedArgs {
 #define YF_STAMP(tp, i) do { } while (0)
 #endif
 
-constexpr int kFusedThreads = kFusedWorkerThreads;       // 8 warps; the last one doubles as MMA issuer / prefetcher
+// CTA shapes (yf_plan.h): NT = 256 threads, three CTAs per SM (throughput) or NT = 512 threads, one CTA per SM (latency).
+// The last warp doubles as MMA issuer / prefetcher.  Every routine below that deals work to threads takes NT.
 constexpr int kFusedCtasPerSm = 3;
-constexpr int kCtrlWarp = kFusedCtrlWarp;                // TMEM lane quarter 3 of warpgroup 1
+template <int NT> struct Shape {
+  static_assert(NT == kFusedWorkerThreads || NT == kFusedLatThreads, "CTA shape");
+  static constexpr int threads = NT, warps = NT / 32, wgs = NT / 128, ctrl_warp = NT / 32 - 1;
+  static constexpr int ctas_per_sm = NT == kFusedWorkerThreads ? kFusedCtasPerSm : 1;
+  static constexpr int tmem_cols = NT == kFusedWorkerThreads ? kFusedTmemCols : kFusedLatTmemCols;
+  static constexpr int stages = 2 * wgs;                 // first conv: A stages (two rounds of one tile per warpgroup)
+};
 
 // UMMA smem descriptor: template low word (LBO) + start address; high word: SBO = 128 B, version 1, no swizzle
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo_tmpl, uint32_t saddr) {
@@ -111,8 +120,14 @@ struct Rt {
   int next_img;                                // front phases: next image of this CTA (input prefetch), or -1
 };
 
+// (everything but the first probe is out of line: the kernel waits at ~80 places)
+static __device__ __noinline__ bool wait_bar_slow(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_wait_retry(bar, parity)) return true;
+  atomicCAS(err, 0, code);
+  return false;
+}
 __device__ __forceinline__ void wait_bar(Cx& c, const FusedArgs& a, uint32_t bar, uint32_t parity, int code) {
-  if (c.ok && !mbar_wait(bar, parity)) { atomicCAS(a.err, 0, code); c.ok = false; }
+  if (c.ok && !mbar_try_wait(bar, parity)) c.ok = wait_bar_slow(bar, parity, a.err, code);
 }
 // phase order of one CTA: front(image 0), front(image 1), back(pair), front(image 2), ...
 __device__ __forceinline__ void advance_phase(int& p, int& k, int split, int nph, int my_images) {
@@ -151,10 +166,11 @@ __device__ __forceinline__ void housekeeping(Cx& c, const FusedArgs& a, const Rt
 }
 
 // border cells of a padded output buffer <- the tensor's zero point (run by the workers while the MMAs are in flight)
+template <int NT>
 __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem, int tid) {
   const int WP = ph.out_wp, H = ph.Hout, ncell = 2 * WP + 2 * H;
   const uint32_t z = static_cast<uint32_t>(ph.out_zp & 0xff) * 0x01010101u;
-  for (int i = tid; i < ncell * ph.nw; i += kFusedThreads) {
+  for (int i = tid; i < ncell * ph.nw; i += NT) {
     const int c = small_div(i, ph.rcp_ncell), k = i - c * ncell;
     int cell;
     if (k < WP) cell = k;
@@ -166,8 +182,10 @@ __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem,
 }
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
+// what a unit needs of the running state: where this image's rows go
+struct UnitCtx { int out_shift, img_a, img_b, head_bytes; int8_t* out; };
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
-                                          int row, int g, int rows, const Rt& rt, const FusedArgs& a) {
+                                          int row, int g, int rows, const UnitCtx& rt) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   tmem_ld_wait();
@@ -194,7 +212,7 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
       if (row >= ph.row_b0) { img = rt.img_b; r = row - ph.row_b0; }
       else if (row >= ph.rows_a) return;                     // separator rows
     }
-    uint16_t* o = reinterpret_cast<uint16_t*>(a.out + static_cast<long long>(img) * a.head_bytes + r * ph.cout + g * 16);
+    uint16_t* o = reinterpret_cast<uint16_t*>(rt.out + static_cast<long long>(img) * rt.head_bytes + r * ph.cout + g * 16);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (2 * j < nreal) o[j] = static_cast<uint16_t>((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
@@ -217,24 +235,30 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
 // (tiles t0 .. t0+nt-1 are the group whose accumulators sit in TMEM, tile t at column (t - t0) * npad)
 // tcol0: TMEM column of the group's first tile (0 for the 1x1 layers, whose groups reuse the columns; the first conv
 // keeps every tile in its own columns)
+template <int NT>
 __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt, const FusedArgs& a,
                                               int tcol0 = 0) {
+  constexpr int kWgs = Shape<NT>::wgs;
+  const UnitCtx u{rt.out_shift, rt.img_a, rt.img_b, a.head_bytes, a.out};
+  auto unit = [&](uint32_t taddr, int row, int g) {
+    conv_unit(ph, c.smem, slot + ph.lut_off, reinterpret_cast<const EpiChF*>(slot + ph.epi_off), taddr, row, g, rows, u);
+  };
   const int q = c.warp & 3, chunks = ph.chunks_out;
-  const uint8_t* lut = slot + ph.lut_off;
-  const EpiChF* epi = reinterpret_cast<const EpiChF*>(slot + ph.epi_off);
   const uint32_t tq = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tcol0);
-  if (nt >= kFusedWarpgroups) {
-    // several tiles: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
-    for (int t = c.warp >> 2; t < nt; t += kFusedWarpgroups) {
+  if (nt >= kWgs) {
+    // at least a tile per warpgroup: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
+    for (int t = c.warp >> 2; t < nt; t += kWgs) {
       const int row0 = (t0 + t) * 128 + q * 32;
       if (row0 >= rows) continue;                            // this warp's 32 rows are all padding
-      for (int g = 0; g < chunks; ++g) conv_unit(ph, c.smem, lut, epi, tq + t * ph.npad + g * 16, row0 + c.lane, g, rows, rt, a);
+      for (int g = 0; g < chunks; ++g) unit(tq + t * ph.npad + g * 16, row0 + c.lane, g);
     }
   } else {
-    // a single tile: split its chunks across the warpgroups
-    const int row0 = t0 * 128 + q * 32;
-    if (row0 < rows)
-      for (int g = c.warp >> 2; g < chunks; g += kFusedWarpgroups) conv_unit(ph, c.smem, lut, epi, tq + g * 16, row0 + c.lane, g, rows, rt, a);
+    // fewer tiles than warpgroups: deal the (tile, chunk) units round-robin (fused_has_rows() states the same rule)
+    for (int u = c.warp >> 2, t = 0, g = c.warp >> 2; u < nt * chunks; u += kWgs, g += kWgs) {
+      while (g >= chunks) { g -= chunks; ++t; }
+      const int row0 = (t0 + t) * 128 + q * 32;
+      if (row0 < rows) unit(tq + t * ph.npad + g * 16, row0 + c.lane, g);
+    }
   }
 }
 
@@ -421,12 +445,12 @@ __device__ __forceinline__ void pool_phase_loops(const FusedPhase& ph, uint8_t* 
 // MAX_POOL_2D (+ QUANTIZE table), windows 8 and 4 at stride 2 (the two pools of yoloface): separable, lines in registers.
 // Pass 1: one thread per (input row, 4-channel word, segment of output columns) -> row maxima (biased) in the scratch;
 // pass 2: one thread per (output column, word, segment of output rows) -> table -> chunk-planar output.
-template <int K>
+template <int K, int NT>
 __device__ __forceinline__ void pool_phase_lines(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
   const int nw = ph.nw, Hin = ph.Hin, Win = ph.Win, Hout = ph.Hout, Wout = ph.Wout;
   const int sws = ph.scratch_ws;
   {
-    const int lines = Hin * nw, segs = max(1, min(kFusedThreads / lines, (Wout + K / 2 - 1) / (K / 2)));
+    const int lines = Hin * nw, segs = max(1, min(NT / lines, (Wout + K / 2 - 1) / (K / 2)));
     const int seg_len = (Wout + segs - 1) / segs;
     int t = tid, seg = 0;
     while (t >= lines && seg < segs) { t -= lines; ++seg; }
@@ -440,7 +464,7 @@ __device__ __forceinline__ void pool_phase_lines(const FusedPhase& ph, uint8_t* 
   }
   __syncthreads();
   {
-    const int lines = Wout * nw, segs = max(1, min(kFusedThreads / lines, (Hout + K / 2 - 1) / (K / 2)));
+    const int lines = Wout * nw, segs = max(1, min(NT / lines, (Hout + K / 2 - 1) / (K / 2)));
     const int seg_len = (Hout + segs - 1) / segs;
     int t = tid, seg = 0;
     while (t >= lines && seg < segs) { t -= lines; ++seg; }
@@ -463,20 +487,23 @@ __device__ __forceinline__ void pool_phase_lines(const FusedPhase& ph, uint8_t* 
   }
 }
 
+template <int NT>
 __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int out_shift) {
   // (the line form needs rows * words <= threads for pass 1 and a window / stride it is instantiated for)
-  if (ph.stride == 2 && ph.ksize == 8 && ph.Hin * ph.nw <= kFusedThreads && ph.Wout * ph.nw <= kFusedThreads) pool_phase_lines<8>(ph, smem, slot, tid, out_shift);
-  else if (ph.stride == 2 && ph.ksize == 4 && ph.Hin * ph.nw <= kFusedThreads && ph.Wout * ph.nw <= kFusedThreads) pool_phase_lines<4>(ph, smem, slot, tid, out_shift);
+  if (ph.stride == 2 && ph.ksize == 8 && ph.Hin * ph.nw <= NT && ph.Wout * ph.nw <= NT) pool_phase_lines<8, NT>(ph, smem, slot, tid, out_shift);
+  else if (ph.stride == 2 && ph.ksize == 4 && ph.Hin * ph.nw <= NT && ph.Wout * ph.nw <= NT) pool_phase_lines<4, NT>(ph, smem, slot, tid, out_shift);
   else pool_phase_loops(ph, smem, slot, tid, out_shift);
 }
 
-// first conv: every thread builds one A row (3 x 16-byte chunks) of tile 2r + (tid >> 7)
+// first conv: every thread builds one A row (3 x 16-byte chunks) of tile wgs * r + (tid >> 7)
+template <int NT>
 __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem, int tid, int r) {
+  constexpr int kWgs = Shape<NT>::wgs, kStages = Shape<NT>::stages;
   const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
   const int row_bytes = ph.Win * 3, rt = tid & 127, hf = tid >> 7;
   const uint8_t* image = smem + ph.in_off;
-  uint8_t* stage = smem + ph.scratch_off + ((2 * r + hf) & 3) * 6144;
-  const int rr = (2 * r + hf) * 128 + rt;
+  uint8_t* stage = smem + ph.scratch_off + ((kWgs * r + hf) % kStages) * 6144;
+  const int rr = (kWgs * r + hf) * 128 + rt;
   if (rr >= ph.rows_out) return;
   const int oy = small_div(rr, ph.rcp_wout), ox = rr - oy * ph.Wout;
 #pragma unroll
@@ -499,7 +526,9 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
 // ---- one phase ------------------------------------------------------------------------------------------------------
 // `ph` is a shared-memory descriptor (generic kernel) or a bundle of compile-time constants (specialised kernel);
 // p = its index; everything that varies between executions is in rt.
+template <int NT>
 __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& c, const FusedArgs& a, const Rt& rt, long long* tp) {
+  constexpr int kWgs = Shape<NT>::wgs, kStages = Shape<NT>::stages, kCtrlWarp = Shape<NT>::ctrl_warp;
   uint8_t* const smem = c.smem;
   const int tid = c.tid, warp = c.warp;
   const int kind = ph.kind, ntiles = ph.ntiles, tpg = ph.tpg;
@@ -509,19 +538,21 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
   const uint32_t par_bar = c.par_full(a) + 8 * s_idx, par_parity = (rt.pc / kFusedParamSlots) & 1;
   const uint8_t* slot = smem + a.slot_off + s_idx * a.slot_bytes;
   const bool pf_here = p == a.in_pf_phase;
+  YF_STAMP(tp, 5);
   if (kind == STEP_CONV1X1) {
     uint32_t grp = (ph.pair && !rt.pair_b) ? ph.grp_warps_single : ph.grp_warps;
     const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off, sA = c.smem_base + ph.in_off;
-    const bool ctrl_busy = fused_has_rows(kCtrlWarp, 0, min(tpg, ntiles), rows, ph.chunks_out);
+    const bool ctrl_busy = fused_has_rows(kCtrlWarp, 0, min(tpg, ntiles), rows, ph.chunks_out, kWgs);
     for (int t0 = 0; t0 < ntiles; t0 += tpg, grp >>= 8) {
       const int nt = min(tpg, ntiles - t0);
       // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 14x14 layers)
       // never touch TMEM: they go straight to the end-of-phase barrier
-      const bool has_rows = fused_has_rows(warp, t0, nt, rows, ph.chunks_out);
+      const bool has_rows = fused_has_rows(warp, t0, nt, rows, ph.chunks_out, kWgs);
       const int meet = static_cast<int>(grp & 0xffu) * 32;   // threads at the release barrier: row owners + control warp
-      if (t0 == 0 && ph.out_wp && !c.ctrl) fill_border(ph, smem, tid);
+      if (t0 == 0 && ph.out_wp && !c.ctrl) fill_border<NT>(ph, smem, tid);
       if (c.ctrl) {                                          // every tile of the group, one commit
         if (t0 == 0) wait_bar(c, a, par_bar, par_parity, 302);   // the weights
+        if (t0 == 0) YF_STAMP(tp, 1);
         tc_fence_after();
         const bool el = elect_one();
         for (int t = 0; t < nt; ++t)
@@ -530,48 +561,55 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
                            mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16), static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
         if (el) mma_commit(c.mma_done(a));
         __syncwarp();
-        if (t0 == 0 && ph.out_wp) fill_border(ph, smem, tid);
+        if (t0 == 0) YF_STAMP(tp, 2);
+        if (t0 == 0 && ph.out_wp) fill_border<NT>(ph, smem, tid);
         // the control warp alone polls the accumulator barrier and then releases the row owners through a
         // hardware barrier, where waiting costs no issue slots
         wait_bar(c, a, c.mma_done(a), c.use0 & 1, 301);
+        if (t0 == 0) YF_STAMP(tp, 3);
         tc_fence_before();
         if (has_rows) epi_bar_sync(meet); else epi_bar_arrive(meet);
         if (c.lead && t0 == 0 && !ctrl_busy) housekeeping(c, a, rt, pf_here);
+        if (t0 == 0) YF_STAMP(tp, 4);
         __syncwarp();
       } else if (has_rows) {
+        if (t0 == 0) YF_STAMP(tp, 6);
         if (t0 == 0) wait_bar(c, a, par_bar, par_parity, 302);   // table and requant constants
+        if (t0 == 0) YF_STAMP(tp, 2);
         epi_bar_sync(meet);
+        if (t0 == 0) YF_STAMP(tp, 3);
       }
       ++c.use0;
       if (has_rows) {
         tc_fence_after();
-        conv_epilogue(ph, c, slot, t0, nt, rows, rt, a);
+        conv_epilogue<NT>(ph, c, slot, t0, nt, rows, rt, a);
         tc_fence_before();
+        if (t0 == 0) YF_STAMP(tp, 4);
       }
       if (t0 + tpg < ntiles) __syncthreads();                // the next group overwrites these TMEM columns
     }
     if (c.lead && ctrl_busy) housekeeping(c, a, rt, pf_here);
   } else if (kind == STEP_CONV_IM2COL) {
     const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off;
-    if (ph.out_wp) fill_border(ph, smem, tid);
+    if (ph.out_wp) fill_border<NT>(ph, smem, tid);
     wait_bar(c, a, par_bar, par_parity, 302);
     wait_bar(c, a, c.in_full(a), c.in_uses & 1, 303); ++c.in_uses;
-    // Software pipeline over rounds of two tiles: build the A rows of round r, issue its MMAs, then requantise the
-    // tiles of round r-1 while those MMAs run (one tile per warpgroup).  Waiting for round r-1's accumulators also
-    // frees the A stages round r+1 will overwrite (stage = tile & 3).
-    const int rounds = (ntiles + 1) >> 1;
+    // Software pipeline over rounds of one tile per warpgroup: build the A rows of round r, issue its MMAs, then
+    // requantise the tiles of round r-1 while those MMAs run.  Waiting for round r-1's accumulators also frees the A
+    // stages round r+1 will overwrite (stage = tile % (2 * warpgroups)).
+    const int rounds = (ntiles + kWgs - 1) / kWgs;
     for (int r = 0; r <= rounds; ++r) {
       if (r < rounds) {
-        im2col_build(ph, smem, tid, r);
+        im2col_build<NT>(ph, smem, tid, r);
         fence_proxy_async_smem();
         __syncthreads();
         if (c.ctrl) {
           tc_fence_after();
           const bool el = elect_one();
-          for (int h = 0; h < 2; ++h) {
-            const int tt = 2 * r + h;
+          for (int h = 0; h < kWgs; ++h) {
+            const int tt = kWgs * r + h;
             if (tt >= ntiles) break;
-            const uint32_t sS = c.smem_base + ph.scratch_off + (tt & 3) * 6144;
+            const uint32_t sS = c.smem_base + ph.scratch_off + (tt % kStages) * 6144;
             for (int k = 0; k < 2; ++k)
               if (el) mma_i8(c.tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
                              static_cast<uint32_t>(ph.idesc), k > 0 ? 1u : 0u);
@@ -584,15 +622,16 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
         const int rp = r - 1;
         if (rp & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 304); ++c.use0; }
         tc_fence_after();
-        conv_epilogue(ph, c, slot, 2 * rp, min(2, ntiles - 2 * rp), rows, rt, a, 2 * rp * ph.npad);
+        conv_epilogue<NT>(ph, c, slot, kWgs * rp, min(kWgs, ntiles - kWgs * rp), rows, rt, a, kWgs * rp * ph.npad);
         tc_fence_before();
       }
     }
     if (c.lead) housekeeping(c, a, rt, pf_here);
   } else {
     wait_bar(c, a, par_bar, par_parity, 302);
+    YF_STAMP(tp, 2);
     if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, (ph.pair && !rt.pair_b) ? ph.rows_a : ph.rows_out, rt.out_shift, tp);
-    else if (kind == STEP_MAXPOOL) pool_phase(ph, smem, slot, tid, rt.out_shift);
+    else if (kind == STEP_MAXPOOL) pool_phase<NT>(ph, smem, slot, tid, rt.out_shift);
     if (c.lead && c.producer(a)->pc_next <= rt.pc + 1) housekeeping(c, a, rt, pf_here);   // only when the next phase's block is not even requested yet
   }
   fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
@@ -606,7 +645,9 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
 }
 
 // ---- prologue / epilogue shared by the two kernels ---------------------------------------------------------------
+template <int NT>
 __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* smem) {
+  constexpr int kCtrlWarp = Shape<NT>::ctrl_warp;
   c.smem = smem; c.smem_base = smem_u32(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots));
   c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
@@ -616,9 +657,9 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
     for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
     fence_mbar_init();
   }
-  if (c.warp == 0) tmem_alloc(tmem_slot, kFusedTmemCols);
+  if (c.warp == 0) tmem_alloc(tmem_slot, Shape<NT>::tmem_cols);
   int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 128);          // parameter block table (<= kFusedMaxPhases entries)
-  for (int i = c.tid; i < a.nphases; i += kFusedThreads) pb[i] = make_int2(a.phases[i].param_off, a.phases[i].param_bytes);
+  for (int i = c.tid; i < a.nphases; i += NT) pb[i] = a.pb[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -635,10 +676,11 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
     if (c.my_images > 0) housekeeping_out(c.smem_base + a.bars_off, 0u, static_cast<int>(blockIdx.x));   // first image + first blocks
   }
 }
+template <int NT>
 __device__ __forceinline__ void cta_teardown(const Cx& c) {
   tc_fence_before();
   __syncthreads();
-  if (c.warp == 0) tmem_dealloc(c.tmem_base, kFusedTmemCols);
+  if (c.warp == 0) tmem_dealloc(c.tmem_base, Shape<NT>::tmem_cols);
 }
 // the image-dependent part of Rt for front phases of the CTA's k-th image / for the back phases that follow it
 __device__ __forceinline__ void rt_front(Rt& rt, const FusedArgs& a, int k, int my_images) {
@@ -657,13 +699,15 @@ __device__ __forceinline__ void rt_back(Rt& rt, const FusedArgs& a, int k) {
 #define YF_TRACE_PHASE(p)                                                                                      \
   const bool tr = a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u;                                     \
   if (tr) a.trace[rt.pc] = clock64();                                                                          \
-  long long* const tp = (tr && (p) == a.trace_phase && rt.pc < static_cast<uint32_t>(a.nphases)) ? a.trace + 96 : nullptr;
+  long long* const tp = (a.trace && blockIdx.x == 0 && (p) == a.trace_phase && rt.pc < static_cast<uint32_t>(a.nphases))                 \
+                            ? (c.tid == 0 ? a.trace + 96 : c.lead ? a.trace + 112 : nullptr) : nullptr;   /* thread 0 | control thread */
 #else
 #define YF_TRACE_PHASE(p) long long* const tp = nullptr;
 #endif
 
 // ---- generic kernel: descriptors in shared memory ----------------------------------------------------------------
-__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(kFusedWorkerThreads, kFusedCtasPerSm) yoloface_fused_kernel(const FusedArgs a) {
+  constexpr int kFusedThreads = kFusedWorkerThreads;
   extern __shared__ __align__(1024) uint8_t smem[];
   Cx c;
   {                                                           // phase descriptors: global -> smem, read with LDS from here on
@@ -671,7 +715,7 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
     uint4* dst = reinterpret_cast<uint4*>(smem + a.desc_off);
     for (int i = threadIdx.x; i < a.nphases * static_cast<int>(sizeof(FusedPhase) / 16); i += kFusedThreads) dst[i] = src[i];
   }
-  cta_setup(c, a, smem);
+  cta_setup<kFusedThreads>(c, a, smem);
   const FusedPhase* s_ph = reinterpret_cast<const FusedPhase*>(smem + a.desc_off);
   const int nph = a.nphases, split = a.split;
   Rt rt; rt.pc = 0u;
@@ -682,82 +726,89 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused
     if (p == split) rt_back(rt, a, k);
     if (p < split) rt.out_shift = (k & 1) ? s_ph[p].out_pair_shift : 0;
     YF_TRACE_PHASE(p)
-    do_phase(s_ph[p], p, c, a, rt, tp);
+    do_phase<kFusedThreads>(s_ph[p], p, c, a, rt, tp);
     advance_phase(p, k, split, nph, c.my_images);
   }
 #ifdef YF_TRACE
   if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
 #endif
-  cta_teardown(c);
+  cta_teardown<kFusedThreads>(c);
 }
 
-// ---- specialised kernel: descriptors compiled in --------------------------------------------------------------------
-// yf_fused_spec.inc (generated): kSpecNumPhases, kSpecSplit, kSpecWords[][72] (host-side identity check) and
-// template <int P> FusedPhase spec_phase() returning phase P as a bundle of constants.
+// ---- specialised kernels: descriptors compiled in -------------------------------------------------------------------
+// yf_fused_spec.inc (generated), for V = 0 (throughput shape) and V = 1 (latency shape): kSpecNumPhases<V>, kSpecSplit<V>,
+// kSpecWords<V>[][72] (host-side identity check) and template <int V, int P> FusedPhase spec_phase() returning phase P
+// as a bundle of constants.
 #include "yf_fused_spec.inc"
 
-template <int P>
+template <int NT, int V, int P>
 __device__ __forceinline__ void spec_step(Cx& c, const FusedArgs& a, Rt& rt, int k) {
-  const FusedPhase ph = spec_phase<P>();
-  if (P < kSpecSplit) rt.out_shift = (k & 1) ? ph.out_pair_shift : 0;
+  const FusedPhase ph = spec_phase<V, P>();
+  if (P < SpecProgram<V>::split) rt.out_shift = (k & 1) ? ph.out_pair_shift : 0;
   YF_TRACE_PHASE(P)
-  do_phase(ph, P, c, a, rt, tp);
+  do_phase<NT>(ph, P, c, a, rt, tp);
   ++rt.pc;
 }
-template <int P0, int P1>
+template <int NT, int V, int P0, int P1>
 __device__ __forceinline__ void spec_range(Cx& c, const FusedArgs& a, Rt& rt, int k) {
   if constexpr (P0 < P1) {
-    spec_step<P0>(c, a, rt, k);
-    spec_range<P0 + 1, P1>(c, a, rt, k);
+    spec_step<NT, V, P0>(c, a, rt, k);
+    spec_range<NT, V, P0 + 1, P1>(c, a, rt, k);
   }
 }
 
-__global__ void __launch_bounds__(kFusedThreads, kFusedCtasPerSm) yoloface_fused_spec_kernel(const FusedArgs a) {
+template <int NT, int V>
+__global__ void __launch_bounds__(NT, Shape<NT>::ctas_per_sm) yoloface_fused_spec_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Cx c;
-  cta_setup(c, a, smem);
+  cta_setup<NT>(c, a, smem);
   Rt rt; rt.pc = 0u;
 #pragma unroll 1
   for (int k = 0; k < c.my_images; ++k) {
     rt_front(rt, a, k, c.my_images);
-    spec_range<0, kSpecSplit>(c, a, rt, k);
+    spec_range<NT, V, 0, SpecProgram<V>::split>(c, a, rt, k);
     if ((k & 1) || k == c.my_images - 1) {
       rt_back(rt, a, k);
-      spec_range<kSpecSplit, kSpecNumPhases>(c, a, rt, k);
+      spec_range<NT, V, SpecProgram<V>::split, SpecProgram<V>::num_phases>(c, a, rt, k);
     }
   }
 #ifdef YF_TRACE
   if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
 #endif
-  cta_teardown(c);
+  cta_teardown<NT>(c);
 }
 
-// does the specialised kernel implement exactly this program?
+// does a specialised kernel implement exactly this program (for the CTA shape it was laid out for)?
+template <int V>
+static bool spec_matches(const FusedProgram& F) {
+  if (static_cast<int>(F.phases.size()) != SpecProgram<V>::num_phases || F.split != SpecProgram<V>::split) return false;
+  static_assert(sizeof(FusedPhase) == sizeof(SpecProgram<V>::words[0]), "generated table and FusedPhase disagree");
+  return std::memcmp(F.phases.data(), SpecProgram<V>::words, sizeof(FusedPhase) * SpecProgram<V>::num_phases) == 0;
+}
 bool fused_spec_matches(const FusedProgram& F) {
-  if (static_cast<int>(F.phases.size()) != kSpecNumPhases || F.split != kSpecSplit) return false;
-  static_assert(sizeof(FusedPhase) == sizeof(kSpecWords[0]), "generated table and FusedPhase disagree");
-  return std::memcmp(F.phases.data(), kSpecWords, sizeof(FusedPhase) * kSpecNumPhases) == 0;
+  return F.threads == kFusedLatThreads ? spec_matches<1>(F) : F.threads == kFusedWorkerThreads ? spec_matches<0>(F) : false;
 }
 
-cudaError_t fused_init(int smem_bytes, int smem_bytes_spec) {
+cudaError_t fused_init(const FusedProgram& F, bool use_spec) {
   // The attribute belongs to the function (per device), not to a plan: several plans / contexts share it, so it only
   // ever grows -- a later, smaller plan must not take the larger ones' shared memory away.
   const char* e = getenv("YF_B200_FUSED_PAD");
   const int pad = e ? atoi(e) : 0;
   int dev = 0;
   cudaGetDevice(&dev);
-  static int granted[64] = {}, granted_spec[64] = {};
-  if (smem_bytes + pad > granted[dev & 63]) {
-    const cudaError_t r = cudaFuncSetAttribute(yoloface_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes + pad);
-    if (r != cudaSuccess) return r;
-    granted[dev & 63] = smem_bytes + pad;
-  }
-  if (smem_bytes_spec > 0 && smem_bytes_spec + pad > granted_spec[dev & 63]) {
-    const cudaError_t r = cudaFuncSetAttribute(yoloface_fused_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_spec + pad);
-    if (r != cudaSuccess) return r;
-    granted_spec[dev & 63] = smem_bytes_spec + pad;
-  }
-  return cudaSuccess;
+  static int granted[3][64] = {};                            // generic | specialised | specialised, latency shape
+  const bool lat = F.threads == kFusedLatThreads;
+  if (lat && !use_spec) return cudaErrorInvalidValue;        // the latency shape exists as a specialised kernel only
+  auto grow = [&](int which, const void* fn, int bytes) {
+    if (bytes + pad <= granted[which][dev & 63]) return cudaSuccess;
+    const cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + pad);
+    if (r == cudaSuccess) granted[which][dev & 63] = bytes + pad;
+    return r;
+  };
+  if (lat) return grow(2, reinterpret_cast<const void*>(&yoloface_fused_spec_kernel<kFusedLatThreads, 1>), F.smem_bytes_spec);
+  const cudaError_t r = grow(0, reinterpret_cast<const void*>(&yoloface_fused_kernel), F.smem_bytes);
+  if (r != cudaSuccess || !use_spec) return r;
+  return grow(1, reinterpret_cast<const void*>(&yoloface_fused_spec_kernel<kFusedWorkerThreads, 0>), F.smem_bytes_spec);
 }
 
 cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
@@ -768,11 +819,19 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   a.in_off = F.in_off; a.in_bytes = F.in_bytes; a.slot_off = F.slot_off; a.slot_bytes = F.slot_bytes; a.desc_off = F.desc_off;
   a.head_bytes = F.head_bytes; a.err = L.d_err; a.trace = L.d_trace; a.in_pf_phase = F.in_pf_phase;
   { const char* e = getenv("YF_B200_TRACE_PHASE"); a.trace_phase = e ? atoi(e) : 1; }
+  for (int i = 0; i < a.nphases; ++i) a.pb[i] = make_int2(F.phases[i].param_off, F.phases[i].param_bytes);
   // YF_B200_FUSED_PAD (diagnostics): extra dynamic shared memory per CTA, to measure the kernel at lower residency
   static const int pad = [] { const char* e = getenv("YF_B200_FUSED_PAD"); return e ? atoi(e) : 0; }();
   const bool spec = L.use_spec;
   a.bars_off = spec ? F.desc_off : F.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127);
   const int smem = (spec ? F.smem_bytes_spec : F.smem_bytes) + pad;
+  if (F.threads == kFusedLatThreads) {
+    // latency shape: one image per CTA, one CTA per SM; the caller only picks it for launches that fit one wave
+    if (!spec) return cudaErrorInvalidValue;
+    const int grid = L.n_img < L.sm_count ? L.n_img : L.sm_count;
+    yoloface_fused_spec_kernel<kFusedLatThreads, 1><<<grid, kFusedLatThreads, smem, L.stream>>>(a);
+    return cudaGetLastError();
+  }
   const int per_sm = smem <= 75 * 1024 ? kFusedCtasPerSm : smem <= 113 * 1024 ? 2 : 1;
   const int slots = L.sm_count * per_sm;
   // Pairing: with other launches queued behind this one (`overlapped`) the resident-CTA slots stay full whatever the
@@ -781,8 +840,8 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   static const int pair_env = [] { const char* e = getenv("YF_B200_PAIR"); return e ? atoi(e) : -1; }();   // diagnostics: 0 never, 1 always
   int grid = L.n_img < slots ? L.n_img : slots;
   if ((pair_env < 0 ? L.overlapped : pair_env != 0) && F.split < a.nphases) { const int pairs = (L.n_img + 1) / 2; grid = pairs < slots ? pairs : slots; }
-  if (spec) yoloface_fused_spec_kernel<<<grid, kFusedThreads, smem, L.stream>>>(a);
-  else yoloface_fused_kernel<<<grid, kFusedThreads, smem, L.stream>>>(a);
+  if (spec) yoloface_fused_spec_kernel<kFusedWorkerThreads, 0><<<grid, kFusedWorkerThreads, smem, L.stream>>>(a);
+  else yoloface_fused_kernel<<<grid, kFusedWorkerThreads, smem, L.stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -110,7 +110,7 @@ struct FusedLaunch {
   bool overlapped;                       // other launches are queued around this one (pair the images even when few)
 };
 bool fused_spec_matches(const FusedProgram& F);
-cudaError_t fused_init(int smem_bytes, int smem_bytes_spec);
+cudaError_t fused_init(const FusedProgram& F, bool use_spec);   // shared-memory attributes of the kernel(s) F runs on
 cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L);
 
 }  // namespace yf

@@ -588,8 +588,12 @@ bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blo
 // ------------------------------------------------------------------------------------------
 // Fused program: shared-memory placement by liveness + per-phase parameter blocks
 // ------------------------------------------------------------------------------------------
-bool build_fused(const Plan& P, FusedProgram* F) {
+bool build_fused(const Plan& P, FusedProgram* F, int threads) {
   *F = FusedProgram{};
+  if (threads != kFusedWorkerThreads && threads != kFusedLatThreads) { F->ok = false; F->why = "unsupported CTA shape"; return false; }
+  const int wgs = threads / 128, ctrl_warp = threads / 32 - 1;
+  const int tmem_cols = threads == kFusedLatThreads ? kFusedLatTmemCols : kFusedTmemCols;
+  F->threads = threads; F->tmem_cols = tmem_cols;
   auto no = [&](const std::string& w) { F->ok = false; F->why = w; return false; };
   const int ns = static_cast<int>(P.steps.size());
   if (ns > kFusedMaxPhases) return no("too many steps");
@@ -672,9 +676,9 @@ bool build_fused(const Plan& P, FusedProgram* F) {
   std::vector<int> scratch_size(ns, 0);
   for (int i = 0; i < ns; ++i) {
     const Step& s = P.steps[i];
-    if (s.kind == STEP_CONV_IM2COL) scratch_size[i] = 4 * 6144 + 2048;
+    if (s.kind == STEP_CONV_IM2COL) scratch_size[i] = 2 * wgs * 6144 + 2048;   // A stages: two rounds of one tile per warpgroup
     if (s.kind == STEP_MAXPOOL) scratch_size[i] = ((s.Cout + 3) / 4) * plane_stride(s.Hin * s.Wout, (s.Cout + 3) / 4);
-    if (s.kind == STEP_CONV_IM2COL && ((s.Hout * s.Wout + 127) / 128) * s.Npad > kFusedTmemCols)
+    if (s.kind == STEP_CONV_IM2COL && ((s.Hout * s.Wout + 127) / 128) * s.Npad > tmem_cols)
       return no("accumulator tiles of the first conv exceed TMEM");
   }
   // first-fit placement in birth order (scratch of phase i is born with the buffers written at i).  Buffers that
@@ -766,9 +770,9 @@ bool build_fused(const Plan& P, FusedProgram* F) {
     ph.npad = s.Npad;
     ph.ntiles = (ph.rows_out + 127) / 128;
     ph.nw = (s.Cout + 3) / 4;
-    ph.per = kFusedWorkerThreads / ph.nw;
+    ph.per = threads / ph.nw;
     ph.dy = ph.per / ph.Wout; ph.dx = ph.per % ph.Wout;
-    ph.tpg = s.Npad ? std::max(1, std::min(ph.ntiles, kFusedTmemCols / s.Npad)) : 0;
+    ph.tpg = s.Npad ? std::max(1, std::min(ph.ntiles, tmem_cols / s.Npad)) : 0;
     if (ph.tpg && ph.ntiles > ph.tpg) {              // balance the groups (7 tiles: 4 + 3, not 4 + 3 -> same; 9: 3 x 3)
       const int groups = (ph.ntiles + ph.tpg - 1) / ph.tpg;
       ph.tpg = (ph.ntiles + groups - 1) / groups;
@@ -780,8 +784,8 @@ bool build_fused(const Plan& P, FusedProgram* F) {
         uint32_t v = 0;
         for (int t0 = 0, g = 0; t0 < ph.ntiles; t0 += ph.tpg, ++g) {
           const int nt = std::min(ph.tpg, ph.ntiles - t0);
-          int n = fused_has_rows(kFusedCtrlWarp, t0, nt, rows, ph.chunks_out) ? 0 : 1;
-          for (int w = 0; w < 4 * kFusedWarpgroups; ++w) n += fused_has_rows(w, t0, nt, rows, ph.chunks_out) ? 1 : 0;
+          int n = fused_has_rows(ctrl_warp, t0, nt, rows, ph.chunks_out, wgs) ? 0 : 1;
+          for (int w = 0; w < 4 * wgs; ++w) n += fused_has_rows(w, t0, nt, rows, ph.chunks_out, wgs) ? 1 : 0;
           v |= static_cast<uint32_t>(n) << (8 * g);
         }
         return v;
@@ -798,7 +802,7 @@ bool build_fused(const Plan& P, FusedProgram* F) {
         *out = m; return true;
       };
       const int ncell = ph.out_wp ? 2 * ph.out_wp + 2 * ph.Hout : 0;
-      const int xmax = std::max({kFusedWorkerThreads, ph.ntiles * 128, ph.Hin * ph.Wout + kFusedWorkerThreads, ncell * ph.nw + kFusedWorkerThreads, ph.rows_out});
+      const int xmax = std::max({threads, ph.ntiles * 128, ph.Hin * ph.Wout + threads, ncell * ph.nw + threads, ph.rows_out});
       if (xmax >= 4096 || !rcp(ph.nw, xmax, &ph.rcp_nw) || !rcp(ph.Wout, xmax, &ph.rcp_wout) || !rcp(ncell, xmax, &ph.rcp_ncell) || !rcp(ph.per, xmax, &ph.rcp_per))
         return no("index range of step " + s.name + " exceeds the kernel's mul-shift division");
     }

@@ -222,24 +222,39 @@ struct FusedProgram {
   int smem_bytes = 0;                   // generic kernel (phase descriptors in shared memory)
   int smem_bytes_spec = 0;              // specialised kernel (descriptors compiled in): barriers sit at desc_off
   int head_bytes = 0;           // bytes per image of the dense head
+  int threads = 0;              // CTA shape this program was laid out for (kFusedWorkerThreads / kFusedLatThreads)
+  int tmem_cols = 0;            // TMEM columns the CTA allocates
 };
 constexpr int kFusedMaxPhases = 32;
-constexpr int kFusedWarpgroups = 2;   // warps = 4 * kFusedWarpgroups (a warp reads the TMEM lane quarter warp % 4)
+// Two shapes of the fused kernel's CTA.  THROUGHPUT: 256 threads (two warpgroups), 128 TMEM columns, three CTAs per SM --
+// the shape every batch larger than the GPU's SM count runs.  LATENCY: 512 threads (four warpgroups), all 512 TMEM
+// columns, one CTA per SM and 128 registers per thread -- the same phases with their work spread over twice the warps,
+// for launches of at most one image per SM (a single image: the reference's own use, stm32/Core/Src/main.c:285-291).
+// warps = threads / 32; a warp reads the TMEM lane quarter warp % 4; the LAST warp issues the MMAs / bulk copies.
+constexpr int kFusedWarpgroups = 2;
 constexpr int kFusedWorkerThreads = kFusedWarpgroups * 128;
+constexpr int kFusedLatThreads = 512;
 constexpr int kFusedParamSlots = 3;
-constexpr int kFusedTmemCols = 128;     // per CTA (three CTAs share an SM's 512 columns); larger layers run in tile groups
-constexpr int kFusedCtrlWarp = 4 * kFusedWarpgroups - 1;   // issues the MMAs / bulk copies (lane quarter 3 of the last warpgroup)
+constexpr int kFusedTmemCols = 128;     // throughput shape, per CTA (three CTAs share an SM's 512 columns); larger layers run in tile groups
+constexpr int kFusedLatTmemCols = 512;  // latency shape
+constexpr int kFusedCtrlWarp = 4 * kFusedWarpgroups - 1;   // throughput shape: lane quarter 3 of the last warpgroup
 
-// Does `warp` own accumulator rows of the tile group [t0, t0 + nt) of a conv phase?  A warp reads TMEM lane
-// quarter warp % 4; with several tiles in the group a warpgroup takes whole tiles (first: t0 + warp / 4), with a
-// single tile the warpgroups split its 16-channel chunks.  Shared by the kernel and the host (barrier counts).
+// Does `warp` own accumulator rows of the tile group [t0, t0 + nt) of a conv phase run by `wgs` warpgroups?  A warp
+// reads TMEM lane quarter warp % 4.  With at least as many tiles in the group as warpgroups, a warpgroup takes whole
+// tiles (t0 + wg, t0 + wg + wgs, ...); with fewer, the (tile, 16-channel chunk) units u = t * chunks + g are dealt to
+// the warpgroups round-robin (u = wg, wg + wgs, ...).  Shared by the kernel and the host (barrier counts).
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline bool fused_has_rows(int warp, int t0, int nt, int rows_out, int chunks) {
+inline bool fused_has_rows(int warp, int t0, int nt, int rows_out, int chunks, int wgs) {
   const int wg = warp >> 2, q = warp & 3;
-  return nt >= kFusedWarpgroups ? (t0 + wg) * 128 + q * 32 < rows_out : (t0 * 128 + q * 32 < rows_out && wg < chunks);
+  if (nt >= wgs) return (t0 + wg) * 128 + q * 32 < rows_out;
+  for (int u = wg, t = 0, g = wg; u < nt * chunks; u += wgs, g += wgs) {
+    while (g >= chunks) { g -= chunks; ++t; }
+    if ((t0 + t) * 128 + q * 32 < rows_out) return true;
+  }
+  return false;
 }
-bool build_fused(const Plan& plan, FusedProgram* prog);
+bool build_fused(const Plan& plan, FusedProgram* prog, int threads = kFusedWorkerThreads);
 
 }  // namespace yf

@@ -72,7 +72,7 @@ def _phase(F, ph, smem, rng, params, epi_all, heads, shift, pair_b):
         rows_dw = ph["rows_out"] if (not pair or pair_b) else ph["rows_a"]         # rows the depthwise phases produce
         lut = slot[ph["lut_off"]:ph["lut_off"] + 256].view(np.int8) if ph["has_lut"] else None
         if ph["scratch_off"] >= 0:      # the kernel scribbles here during this phase: must not alias anything live
-            size = 4 * 6144 + 2048 if kind == 0 else ph["nw"] * ph["scratch_ws"]
+            size = 2 * F["warpgroups"] * 6144 + 2048 if kind == 0 else ph["nw"] * ph["scratch_ws"]
             assert kind == 0 or ph["scratch_ws"] >= ph["Hin"] * ph["Wout"] * 4
             smem[ph["scratch_off"]:ph["scratch_off"] + size] = rng.integers(0, 256, size, dtype=np.uint8)
         if kind in (0, 1):

@@ -112,6 +112,32 @@ def test_many_images_per_cta(yf, oracle, golden, n):
         big.close()
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 147, 148, 149, 300])
+def test_fused_cta_shapes_agree(yf, oracle, golden, monkeypatch, n):
+    """A launch that runs alone with at most one image per SM takes the latency shape (512-thread CTAs, one per SM);
+    everything else the throughput shape (256 threads, three per SM).  Same heads either way, and the shape taken is
+    the one the rule states."""
+    x = real_batch(golden, n, 7000 + n)
+    want = oracle.run_batch(x, threads=os.cpu_count())
+    a = yf.Network(chunk_images=512, mode="fused")
+    try:
+        st = a.stats()
+        assert st["fused_latency"] == 1
+        assert np.array_equal(a.run(x), want)
+        took = a.stats()["latency_launches"]
+        assert took == (1 if n <= st["sm_count"] else 0)
+    finally:
+        a.close()
+    monkeypatch.setenv("YF_B200_FUSED_LAT", "0")
+    b = yf.Network(chunk_images=512, mode="fused")
+    try:
+        assert b.stats()["fused_latency"] == 0
+        assert np.array_equal(b.run(x), want)
+        assert b.stats()["latency_launches"] == 0
+    finally:
+        b.close()
+
+
 def test_large_batch_properties(net, oracle, golden):
     """Full-size check through size-independent properties: a 16,384-image batch built by tiling
     64 distinct images must give the tiled 64 heads (batch independence), and a permutation of the

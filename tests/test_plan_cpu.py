@@ -142,6 +142,49 @@ def test_fused_program_reproduces_oracle(yf, oracle, golden):
     assert np.array_equal(ha.reshape(7, 7, 18), oracle.run(vector_a())) and np.array_equal(hb.reshape(7, 7, 18), oracle.run(vector_b()))
 
 
+def _has_rows(warp, t0, nt, rows, chunks, wgs):
+    """yf_plan.h fused_has_rows(), restated."""
+    wg, q = warp >> 2, warp & 3
+    if nt >= wgs:
+        return (t0 + wg) * 128 + q * 32 < rows
+    return any((t0 + u // chunks) * 128 + q * 32 < rows for u in range(wg, nt * chunks, wgs))
+
+
+@pytest.mark.parametrize("threads", [256, 512])
+def test_fused_program_cta_shapes(yf, oracle, golden, threads):
+    """Both CTA shapes of the fused kernel (256 threads: throughput; 512 threads, all of TMEM: latency) come from the
+    same planner: the emulated program gives the oracle's head, every (tile, chunk) unit of every conv phase has
+    exactly one owning warpgroup, and the barrier counts equal the warps that own rows plus the control warp."""
+    from fused_emulator import run_fused
+    F = yf.fused_program(56, 56, threads=threads)
+    wgs = threads // 128
+    assert F["threads"] == threads and F["warpgroups"] == wgs and F["tmem_cols"] == (128 if threads == 256 else 512)
+    assert F["spec"] == 1                          # a specialised kernel exists for each shape
+    assert len(F["phases"]) == 26 and F["split"] == 14
+    img = golden["images"][11]
+    assert np.array_equal(run_fused(F, img, 3).reshape(7, 7, 18), oracle.run(img))
+    ctrl = 4 * wgs - 1
+    for ph in F["phases"]:
+        if ph["kind"] != 1:
+            continue
+        for rows, counts in ((ph["rows_out"], ph["grp_warps"]), (ph["rows_single"], ph["grp_warps_single"])):
+            for g, t0 in enumerate(range(0, ph["ntiles"], ph["tpg"])):
+                nt = min(ph["tpg"], ph["ntiles"] - t0)
+                owners = [w for w in range(4 * wgs) if _has_rows(w, t0, nt, rows, ph["chunks_out"], wgs)]
+                assert ((counts >> (8 * g)) & 0xff) == len(owners) + (0 if ctrl in owners else 1)
+                # every unit with real rows is reached by exactly one warpgroup (per lane quarter)
+                for t in range(nt):
+                    for q in range(4):
+                        if (t0 + t) * 128 + q * 32 >= rows:
+                            continue
+                        for c in range(ph["chunks_out"]):
+                            if nt >= wgs:
+                                own = [wg for wg in range(wgs) if t in range(wg, nt, wgs)]
+                            else:
+                                own = [wg for wg in range(wgs) if (t * ph["chunks_out"] + c) in range(wg, nt * ph["chunks_out"], wgs)]
+                            assert len(own) == 1 and (4 * own[0] + q) in owners
+
+
 @pytest.mark.parametrize("hw", [(8, 8), (8, 16), (24, 16), (32, 32), (40, 56), (56, 64), (64, 64), (16, 128)])
 def test_fused_program_other_resolutions(yf, oracle, hw):
     """The allocator, the word-plane skew, the tile groups and the mul-shift divisions all depend on the shape:

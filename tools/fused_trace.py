@@ -55,4 +55,20 @@ for i, (p, k) in enumerate(seq[:79]):
     per_kind[tag] = per_kind.get(tag, 0) + d
     print("  img %d %s %-14s kind %d rows %4d cout %2d  %7d cyc  %5.1f%%" % (k, tag, s["name"], s["kind"], F["phases"][p]["rows_out"], F["phases"][p]["cout"], d, 100.0 * d / max(tot, 1)))
 print("total %d cycles; %s" % (tot, per_kind))
+# inner stamps of single phases (thread 0's view), one extra launch per phase: YF_B200_TRACE_INNER=3,5,8
+inner = [int(v) for v in os.environ.get("YF_B200_TRACE_INNER", "").split(",") if v]
+names = {0: "dw:start", 1: "dw:setup done", 2: "params landed", 3: "accumulators released", 4: "epilogue done", 5: "entry", 6: "before params wait",
+         8: "dw:loop done", 10: "before end barrier", 11: "after end barrier"}
+lead_names = {5: "entry", 1: "params landed", 2: "MMAs committed", 3: "accumulators ready", 4: "released + housekeeping", 10: "before end barrier", 11: "after end barrier"}
+for p in inner:
+    os.environ["YF_B200_TRACE_PHASE"] = str(p)
+    net.fused_trace(True)
+    net.enqueue(x, y, n); net.sync()
+    st = net.fused_trace(False, read=True)
+    t0 = st[p]
+    evs = sorted((st[96 + i] - t0, names[i]) for i in names if st[96 + i] >= t0 and st[96 + i] <= st[p + 1] + 100)
+    print("  phase %2d %-12s (%d cyc): " % (p, steps[p]["name"], st[p + 1] - st[p]) + "; ".join("%s +%d" % (nm, d) for d, nm in evs))
+    evs = sorted((st[112 + i] - t0, lead_names[i]) for i in lead_names if st[112 + i] >= t0 and st[112 + i] <= st[p + 1] + 100)
+    if evs:
+        print("           control thread: " + "; ".join("%s +%d" % (nm, d) for d, nm in evs))
 net.close()
