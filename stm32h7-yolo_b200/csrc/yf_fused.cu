@@ -49,6 +49,7 @@ struct FusedArgs {
   int* err;
   long long* trace;           // optional: CTA 0 / thread 0 records clock64() at every phase boundary of its first images
   int trace_phase;            // phase whose inner stamps (trace[96..127]) are recorded
+  uint32_t* done; uint32_t done_seq;   // optional (host-mapped): CTA b stores done_seq to done[b] once its heads are written
   int2 pb[kFusedMaxPhases];   // {param_off, param_bytes} per phase: in the kernel's parameter space, so that a CTA's first
                               // bulk copies do not wait for a global-memory load of the table
 };
@@ -247,6 +248,7 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c,
   const uint32_t tq = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tcol0);
   if (nt >= kWgs) {
     // at least a tile per warpgroup: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
+#pragma unroll 1
     for (int t = c.warp >> 2; t < nt; t += kWgs) {
       const int row0 = (t0 + t) * 128 + q * 32;
       if (row0 >= rows) continue;                            // this warp's 32 rows are all padding
@@ -598,6 +600,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
     // requantise the tiles of round r-1 while those MMAs run.  Waiting for round r-1's accumulators also frees the A
     // stages round r+1 will overwrite (stage = tile % (2 * warpgroups)).
     const int rounds = (ntiles + kWgs - 1) / kWgs;
+#pragma unroll 1
     for (int r = 0; r <= rounds; ++r) {
       if (r < rounds) {
         im2col_build<NT>(ph, smem, tid, r);
@@ -677,9 +680,12 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   }
 }
 template <int NT>
-__device__ __forceinline__ void cta_teardown(const Cx& c) {
+__device__ __forceinline__ void cta_teardown(const Cx& c, const FusedArgs& a) {
   tc_fence_before();
   __syncthreads();
+  // Completion word for a host that polls instead of synchronising the stream (blocking calls of a few images): the
+  // barrier orders every thread's head stores before this thread, the system-scope fence before the flag.
+  if (a.done && c.tid == 0) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(a.done + blockIdx.x) = a.done_seq; }
   if (c.warp == 0) tmem_dealloc(c.tmem_base, Shape<NT>::tmem_cols);
 }
 // the image-dependent part of Rt for front phases of the CTA's k-th image / for the back phases that follow it
@@ -732,7 +738,7 @@ __global__ void __launch_bounds__(kFusedWorkerThreads, kFusedCtasPerSm) yoloface
 #ifdef YF_TRACE
   if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
 #endif
-  cta_teardown<kFusedThreads>(c);
+  cta_teardown<kFusedThreads>(c, a);
 }
 
 // ---- specialised kernels: descriptors compiled in -------------------------------------------------------------------
@@ -775,7 +781,7 @@ __global__ void __launch_bounds__(NT, Shape<NT>::ctas_per_sm) yoloface_fused_spe
 #ifdef YF_TRACE
   if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
 #endif
-  cta_teardown<NT>(c);
+  cta_teardown<NT>(c, a);
 }
 
 // does a specialised kernel implement exactly this program (for the CTA shape it was laid out for)?
@@ -820,6 +826,7 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   a.head_bytes = F.head_bytes; a.err = L.d_err; a.trace = L.d_trace; a.in_pf_phase = F.in_pf_phase;
   { const char* e = getenv("YF_B200_TRACE_PHASE"); a.trace_phase = e ? atoi(e) : 1; }
   for (int i = 0; i < a.nphases; ++i) a.pb[i] = make_int2(F.phases[i].param_off, F.phases[i].param_bytes);
+  a.done = L.d_done; a.done_seq = L.done_seq;
   // YF_B200_FUSED_PAD (diagnostics): extra dynamic shared memory per CTA, to measure the kernel at lower residency
   static const int pad = [] { const char* e = getenv("YF_B200_FUSED_PAD"); return e ? atoi(e) : 0; }();
   const bool spec = L.use_spec;
@@ -829,6 +836,7 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
     // latency shape: one image per CTA, one CTA per SM; the caller only picks it for launches that fit one wave
     if (!spec) return cudaErrorInvalidValue;
     const int grid = L.n_img < L.sm_count ? L.n_img : L.sm_count;
+    if (L.grid_out) *L.grid_out = grid;
     yoloface_fused_spec_kernel<kFusedLatThreads, 1><<<grid, kFusedLatThreads, smem, L.stream>>>(a);
     return cudaGetLastError();
   }
@@ -840,6 +848,7 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   static const int pair_env = [] { const char* e = getenv("YF_B200_PAIR"); return e ? atoi(e) : -1; }();   // diagnostics: 0 never, 1 always
   int grid = L.n_img < slots ? L.n_img : slots;
   if ((pair_env < 0 ? L.overlapped : pair_env != 0) && F.split < a.nphases) { const int pairs = (L.n_img + 1) / 2; grid = pairs < slots ? pairs : slots; }
+  if (L.grid_out) *L.grid_out = grid;
   if (spec) yoloface_fused_spec_kernel<kFusedWorkerThreads, 0><<<grid, kFusedWorkerThreads, smem, L.stream>>>(a);
   else yoloface_fused_kernel<<<grid, kFusedWorkerThreads, smem, L.stream>>>(a);
   return cudaGetLastError();

@@ -108,6 +108,8 @@ struct FusedLaunch {
   long long* d_trace;
   bool use_spec;                         // the plan equals the compiled-in program: run the specialised kernel
   bool overlapped;                       // other launches are queued around this one (pair the images even when few)
+  uint32_t* d_done; uint32_t done_seq;   // optional completion words (host-mapped memory), one per CTA: see cta_teardown()
+  int* grid_out;                         // optional: CTAs launched
 };
 bool fused_spec_matches(const FusedProgram& F);
 cudaError_t fused_init(const FusedProgram& F, bool use_spec);   // shared-memory attributes of the kernel(s) F runs on
