@@ -835,7 +835,9 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   if (F.threads == kFusedLatThreads) {
     // latency shape: one image per CTA, one CTA per SM; the caller only picks it for launches that fit one wave
     if (!spec) return cudaErrorInvalidValue;
-    const int grid = L.n_img < L.sm_count ? L.n_img : L.sm_count;
+    static const int grid_env = [] { const char* e = getenv("YF_B200_LAT_GRID"); return e ? atoi(e) : 0; }();   // diagnostics: several images per CTA
+    int grid = L.n_img < L.sm_count ? L.n_img : L.sm_count;
+    if (grid_env > 0 && grid_env < grid) grid = grid_env;
     if (L.grid_out) *L.grid_out = grid;
     yoloface_fused_spec_kernel<kFusedLatThreads, 1><<<grid, kFusedLatThreads, smem, L.stream>>>(a);
     return cudaGetLastError();

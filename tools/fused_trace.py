@@ -30,6 +30,8 @@ nph, split = len(steps), F["split"]
 # stamps clock64() at the start of its first 80 phases and once at the end
 slots = 148 * 3
 grid = min(n, slots)
+if int(os.environ.get("YF_B200_LAT_GRID", "0")) > 0 and n <= 148:
+    grid = min(grid, int(os.environ["YF_B200_LAT_GRID"]))
 my_images = (n + grid - 1) // grid
 seq, p, k = [], 0, 0
 while k < my_images and len(seq) < 79:
