@@ -1657,6 +1657,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json_ex(int32_t H, int32_t W, const void* blo
     kv("in_ws", p.in_ws); kv("out_ws", p.out_ws); kv("scratch_ws", p.scratch_ws); kv("tpg", p.tpg); kv("ntiles", p.ntiles);
     kv("pair", p.pair); kv("sep_y", p.sep_y); kv("rows_a", p.rows_a); kv("row_b0", p.row_b0); kv("rows_single", p.rows_single);
     kv("out_pair_shift", p.out_pair_shift); kv("grp_warps", p.grp_warps); kv("grp_warps_single", p.grp_warps_single);
+    kv("own0", p.own[0]); kv("own1", p.own[1]); kv("own_single0", p.own_single[0]); kv("own_single1", p.own_single[1]);
     j += "\"add\":[" + std::to_string(p.add.enabled) + "," + std::to_string(p.add.zp1) + "," + std::to_string(p.add.zp2) + "," + std::to_string(p.add.zp_out) + "," +
          std::to_string(p.add.m1) + "," + std::to_string(p.add.m2) + "," + std::to_string(p.add.mo) + "," + std::to_string(p.add.s1) + "," +
          std::to_string(p.add.s2) + "," + std::to_string(p.add.so) + "]";

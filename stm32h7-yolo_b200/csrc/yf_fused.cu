@@ -542,14 +542,18 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
   const bool pf_here = p == a.in_pf_phase;
   YF_STAMP(tp, 5);
   if (kind == STEP_CONV1X1) {
-    uint32_t grp = (ph.pair && !rt.pair_b) ? ph.grp_warps_single : ph.grp_warps;
+    const bool single = ph.pair && !rt.pair_b;
+    uint32_t grp = single ? ph.grp_warps_single : ph.grp_warps;
+    const uint32_t own0 = single ? ph.own_single[0] : ph.own[0], own1 = single ? ph.own_single[1] : ph.own[1];
     const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off, sA = c.smem_base + ph.in_off;
-    const bool ctrl_busy = fused_has_rows(kCtrlWarp, 0, min(tpg, ntiles), rows, ph.chunks_out, kWgs);
-    for (int t0 = 0; t0 < ntiles; t0 += tpg, grp >>= 8) {
+    const bool ctrl_busy = (own0 >> kCtrlWarp) & 1u;          // the control warp owns rows of the first group
+    for (int t0 = 0, g = 0; t0 < ntiles; t0 += tpg, grp >>= 8, ++g) {
       const int nt = min(tpg, ntiles - t0);
       // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 14x14 layers)
-      // never touch TMEM: they go straight to the end-of-phase barrier
-      const bool has_rows = fused_has_rows(warp, t0, nt, rows, ph.chunks_out, kWgs);
+      // never touch TMEM: they go straight to the end-of-phase barrier (fused_has_rows(), evaluated by the planner)
+      const uint32_t owners = (((g & 2) ? own1 : own0) >> (16 * (g & 1))) & 0xffffu;
+      constexpr uint32_t kAllWarps = (1u << Shape<NT>::warps) - 1u;
+      const bool has_rows = owners == kAllWarps || ((owners >> warp) & 1u);   // (a compile-time mask of all warps folds the test away)
       const int meet = static_cast<int>(grp & 0xffu) * 32;   // threads at the release barrier: row owners + control warp
       if (t0 == 0 && ph.out_wp && !c.ctrl) fill_border<NT>(ph, smem, tid);
       if (c.ctrl) {                                          // every tile of the group, one commit

@@ -780,18 +780,20 @@ bool build_fused(const Plan& P, FusedProgram* F, int threads) {
     ph.scratch_ws = s.kind == STEP_MAXPOOL ? plane_stride(s.Hin * s.Wout, ph.nw) : 0;
     if (s.kind == STEP_CONV1X1) {
       if ((ph.ntiles + ph.tpg - 1) / ph.tpg > 4) return no("more than four tile groups in step " + s.name);
-      auto meet_counts = [&](int rows) {
+      auto meet_counts = [&](int rows, uint32_t (&own)[2]) {
         uint32_t v = 0;
+        own[0] = own[1] = 0;
         for (int t0 = 0, g = 0; t0 < ph.ntiles; t0 += ph.tpg, ++g) {
           const int nt = std::min(ph.tpg, ph.ntiles - t0);
           int n = fused_has_rows(ctrl_warp, t0, nt, rows, ph.chunks_out, wgs) ? 0 : 1;
-          for (int w = 0; w < 4 * wgs; ++w) n += fused_has_rows(w, t0, nt, rows, ph.chunks_out, wgs) ? 1 : 0;
+          for (int w = 0; w < 4 * wgs; ++w)
+            if (fused_has_rows(w, t0, nt, rows, ph.chunks_out, wgs)) { ++n; own[g >> 1] |= 1u << (16 * (g & 1) + w); }
           v |= static_cast<uint32_t>(n) << (8 * g);
         }
         return v;
       };
-      ph.grp_warps = meet_counts(ph.rows_out);
-      ph.grp_warps_single = meet_counts(ph.rows_single);
+      ph.grp_warps = meet_counts(ph.rows_out, ph.own);
+      ph.grp_warps_single = meet_counts(ph.rows_single, ph.own_single);
     }
     {
       // reciprocal multipliers; every quotient the kernel forms has x < 4096

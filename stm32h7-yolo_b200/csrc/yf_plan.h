@@ -201,9 +201,13 @@ struct alignas(16) FusedPhase {
   uint32_t grp_warps_single;    // grp_warps for rows_single
   // front phases whose output crosses into the back phases: byte offset added to out_off for the pair's second image
   int32_t out_pair_shift;
+  // conv: 16-bit masks of the warps that own accumulator rows of tile group g (fused_has_rows() per warp, evaluated on
+  // the host so that the kernel tests one bit): group g in bits [16 * (g & 1), +16) of own[g >> 1]; *_single: for rows_single
+  uint32_t own[2], own_single[2];
   int32_t pad_[2];
 };
-static_assert(sizeof(FusedPhase) == 72 * 4, "FusedPhase: 72 32-bit words, no holes (copied with 16-byte loads, compared word-wise with the generated table)");
+static_assert(sizeof(FusedPhase) == 76 * 4, "FusedPhase: 72 32-bit words, no holes (copied with 16-byte loads, compared word-wise with the generated table)");
+static_assert(sizeof(FusedPhase) % 16 == 0, "FusedPhase is copied with 16-byte loads");
 
 struct FusedProgram {
   bool ok = false;              // false: this resolution/model cannot run fused (use the layered path)

@@ -167,11 +167,13 @@ def test_fused_program_cta_shapes(yf, oracle, golden, threads):
     for ph in F["phases"]:
         if ph["kind"] != 1:
             continue
-        for rows, counts in ((ph["rows_out"], ph["grp_warps"]), (ph["rows_single"], ph["grp_warps_single"])):
+        for rows, counts, key in ((ph["rows_out"], ph["grp_warps"], "own"), (ph["rows_single"], ph["grp_warps_single"], "own_single")):
             for g, t0 in enumerate(range(0, ph["ntiles"], ph["tpg"])):
                 nt = min(ph["tpg"], ph["ntiles"] - t0)
                 owners = [w for w in range(4 * wgs) if _has_rows(w, t0, nt, rows, ph["chunks_out"], wgs)]
                 assert ((counts >> (8 * g)) & 0xff) == len(owners) + (0 if ctrl in owners else 1)
+                mask = (ph[key + str(g >> 1)] >> (16 * (g & 1))) & 0xffff
+                assert mask == sum(1 << w for w in owners)        # the kernel tests these bits instead of re-deriving them
                 # every unit with real rows is reached by exactly one warpgroup (per lane quarter)
                 for t in range(nt):
                     for q in range(4):
