@@ -454,8 +454,7 @@ __device__ __forceinline__ void pool_phase_lines(const FusedPhase& ph, uint8_t* 
   {
     const int lines = Hin * nw, segs = max(1, min(NT / lines, (Wout + K / 2 - 1) / (K / 2)));
     const int seg_len = (Wout + segs - 1) / segs;
-    int t = tid, seg = 0;
-    while (t >= lines && seg < segs) { t -= lines; ++seg; }
+    const int seg = tid / lines, t = tid - seg * lines;         // (a multiply-shift in the specialised kernel: lines is a constant)
     if (seg < segs) {
       const int y = small_div(t, ph.rcp_nw), wd = t - y * nw;
       const uint8_t* in = smem + ph.in_off + wd * ph.in_ws + ((y + 1) * ph.in_wp + 1) * 4;   // cell (y, 0) of the bordered buffer
@@ -468,8 +467,7 @@ __device__ __forceinline__ void pool_phase_lines(const FusedPhase& ph, uint8_t* 
   {
     const int lines = Wout * nw, segs = max(1, min(NT / lines, (Hout + K / 2 - 1) / (K / 2)));
     const int seg_len = (Hout + segs - 1) / segs;
-    int t = tid, seg = 0;
-    while (t >= lines && seg < segs) { t -= lines; ++seg; }
+    const int seg = tid / lines, t = tid - seg * lines;         // (a multiply-shift in the specialised kernel: lines is a constant)
     if (seg < segs) {
       const int ox = small_div(t, ph.rcp_nw), wd = t - ox * nw;
       const uint8_t* in = smem + ph.scratch_off + wd * sws + ox * 4;
