@@ -24,8 +24,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-NCU_B256 = "r02_fused_v10_b256_ncu_summary.txt"      # `ncu --set full` summaries of the current kernel (tools/ncu_summary.py)
-NCU_B8192 = "r02_fused_v10_b8192_ncu_summary.txt"
+NCU_B256 = "r02_fused_v11_b256_ncu_summary.txt"
+NCU_B8192 = "r02_fused_v11_b8192_ncu_summary.txt"
 BATCH = 256
 RING = 64                       # distinct input batches: 64 x 2.4 MB = 154 MB > 126 MB of L2
 IN_BYTES, OUT_BYTES = 56 * 56 * 3, 7 * 7 * 18

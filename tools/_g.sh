@@ -1,8 +1,9 @@
-mkdir -p gpurun_out/r3f
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "shapes or ragged or single_image or golden or many or resol" > gpurun_out/r3f/pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r3f/pytest.log
-tail -3 gpurun_out/r3f/pytest.log
-for i in 1 2; do
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r3f/bench$i.json 2> gpurun_out/r3f/bench$i.err
+mkdir -p gpurun_out/r3j
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 --no-cpu > gpurun_out/r3j/bench_n8.json 2> gpurun_out/r3j/bench_n8.err; echo "bench8 rc $?"
 python -c "
-import json; d=json.load(open('gpurun_out/r3f/bench$i.json')); print('value', d['value'], 'e2e', d['e2e']['value'], 'sustained', d['e2e']['sustained_aggregate']['value'], 'serial', d['serial']['value'], d['e2e']['single_image']['blocking_call_us']['median'], d['e2e']['single_image']['device_resident_launch_us'])"
-done
+import json; d=json.load(open('gpurun_out/r3j/bench_n8.json')); print('N=8 value', d['value'], 'e2e', d['e2e']['value'], 'sustained', d['e2e']['sustained_aggregate']['value'], d['e2e']['bounds']['box_fed_images_per_s'], d.get('config3',{}).get('images_per_s'))"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/r3j/bench_n4.json 2> gpurun_out/r3j/bench_n4.err; echo "bench4 rc $?"
+python -c "
+import json; d=json.load(open('gpurun_out/r3j/bench_n4.json')); print('N=4 value', d['value'], 'e2e', d['e2e']['value'], 'sustained', d['e2e']['sustained_aggregate']['value'], d['e2e']['bounds']['box_fed_images_per_s'])"
+timeout 300 python tools/one_handle_probe.py > gpurun_out/r3j/one_handle.log 2>&1; cat gpurun_out/r3j/one_handle.log
+timeout 300 python -m pytest tests/test_multi_gpu_handle.py -m gpu -x -q 2>&1 | tail -2
