@@ -138,6 +138,24 @@ def test_fused_cta_shapes_agree(yf, oracle, golden, monkeypatch, n):
         b.close()
 
 
+def test_small_blocking_calls_poll_completion_words(yf, oracle, golden):
+    """Blocking calls of a few images return when the CTAs' completion words (mapped memory) carry this call's sequence
+    number, not when the stream is idle: stale words of an earlier context (the staging buffer is recycled by the
+    allocator), interleaved contexts and changing image counts must never let a call return early."""
+    x = real_batch(golden, 8, 4242)
+    want = oracle.run_batch(x, threads=os.cpu_count())
+    for round_ in range(3):
+        a = yf.Network(chunk_images=64, mode="fused")
+        b = yf.Network(chunk_images=64, mode="fused")
+        try:
+            for i in range(40):
+                n = 1 + (i * 5 + round_) % 8
+                net_ = a if i % 3 else b
+                assert np.array_equal(net_.run(x[:n]), want[:n]), (round_, i, n)
+        finally:
+            a.close(); b.close()
+
+
 def test_large_batch_properties(net, oracle, golden):
     """Full-size check through size-independent properties: a 16,384-image batch built by tiling
     64 distinct images must give the tiled 64 heads (batch independence), and a permutation of the
