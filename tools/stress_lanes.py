@@ -25,10 +25,20 @@ stream = torch.cuda.Stream()
 bad = 0
 for r in range(rounds):
     k = int(rng.integers(1, 12))
-    sizes = [int(rng.choice([1, 3, 17, 64, 200, 256, 300, 700])) for _ in range(k)]
+    sizes = [int(rng.choice([1, 2, 3, 8, 9, 17, 64, 147, 148, 149, 200, 256, 300, 700])) for _ in range(k)]
     starts = [int(rng.integers(0, 4096 - s)) for s in sizes]
-    mode = r % 3
-    if mode == 0:                                  # device-resident batches over the lanes
+    mode = r % 4
+    if mode == 3:                                  # device-resident launches one after the other (latency shape for <= 148 images)
+        net.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            d_in = [torch.from_numpy(pool[a:a + s]).cuda() for a, s in zip(starts, sizes)]
+            d_out = [torch.full((s, 7, 7, 18), 77, dtype=torch.int8, device="cuda") for s in sizes]
+            stream.synchronize()
+            for x, y, s in zip(d_in, d_out, sizes):
+                net.enqueue(x, y, s)
+        net.sync(); net.set_stream(None)
+        got = [t.cpu().numpy() for t in d_out]
+    elif mode == 0:                                  # device-resident batches over the lanes
         net.set_stream(stream.cuda_stream)
         with torch.cuda.stream(stream):
             d_in = [torch.from_numpy(pool[a:a + s]).cuda() for a, s in zip(starts, sizes)]
@@ -51,6 +61,7 @@ for r in range(rounds):
         if not np.array_equal(g, ref[a:a + s]):
             bad += 1
             print("MISMATCH round %d mode %d size %d" % (r, mode, s))
-print("stress: %d rounds, %d mismatches, launches %d" % (rounds, bad, net.stats()["kernel_launches"]))
+st = net.stats()
+print("stress: %d rounds, %d mismatches, launches %d (%d in the latency shape)" % (rounds, bad, st["kernel_launches"], st["latency_launches"]))
 net.close()
 sys.exit(1 if bad else 0)
