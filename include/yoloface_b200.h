@@ -127,6 +127,8 @@ typedef struct yf_b200_stats_ {
   int32_t fused_smem_bytes;   /* dynamic shared memory of the fused kernel */
   int32_t fused_latency;      /* 1: launches of at most one image per SM that run alone use the latency shape (512-thread CTAs) */
   uint32_t latency_launches;  /* how many launches took that shape since create */
+  int32_t cluster_images;     /* > 0: launches of at most this many images that run alone give every image a CLUSTER of 4 such CTAs */
+  uint32_t cluster_launches;  /* how many launches did */
 } yf_b200_stats;
 AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* stats);
 
@@ -162,7 +164,8 @@ AI_API_ENTRY int64_t yf_b200_plan_json(int32_t height, int32_t width, const void
  * blob, 4: its EpiCh table.  <0 if this input size cannot run fused. */
 AI_API_ENTRY int64_t yf_b200_fused_json(int32_t height, int32_t width, const void* blob, char* dst, uint64_t cap);
 /* the same program laid out for a CTA of `threads` threads: 256 = throughput shape (what yf_b200_fused_json describes),
- * 512 = latency shape (launches of at most one image per SM; plan_blob what = 5 is its parameter blob). */
+ * 512 = latency shape (launches of at most one image per SM; plan_blob what = 5 is its parameter blob),
+ * 4512 = cluster shape (512-thread CTAs in clusters of 4 per image; plan_blob what = 6). */
 AI_API_ENTRY int64_t yf_b200_fused_json_ex(int32_t height, int32_t width, const void* blob, int32_t threads, char* dst, uint64_t cap);
 AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t height, int32_t width, const void* blob, int32_t what, void* dst, uint64_t cap);
 

@@ -57,7 +57,8 @@ class Det(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("images", C.c_uint64), ("last_run_device_ms", C.c_float),
                 ("device", C.c_int32), ("sm_count", C.c_int32), ("chunk_images", C.c_uint32), ("steps", C.c_int32),
-                ("fused", C.c_int32), ("fused_smem_bytes", C.c_int32), ("fused_latency", C.c_int32), ("latency_launches", C.c_uint32)]
+                ("fused", C.c_int32), ("fused_smem_bytes", C.c_int32), ("fused_latency", C.c_int32), ("latency_launches", C.c_uint32),
+                ("cluster_images", C.c_int32), ("cluster_launches", C.c_uint32)]
 
 
 class StepInfo(C.Structure):
@@ -219,7 +220,7 @@ EPI_DTYPE = np.dtype([("add64", "<i8"), ("mult", "<i4"), ("c2", "<i4"), ("e", "<
 
 def fused_program(height=56, width=56, blob=None, threads=256):
     """Fused single-kernel program (smem map, phases, parameter blob, EpiCh table); no GPU needed.
-    threads: CTA shape the program is laid out for (256 throughput, 512 latency)."""
+    threads: CTA shape the program is laid out for (256 throughput, 512 latency, 4512 latency with clusters of 4)."""
     L = lib()
     bp = C.create_string_buffer(blob, len(blob)) if blob is not None else None
     n = L.yf_b200_fused_json_ex(height, width, bp, threads, None, 0)
@@ -228,7 +229,7 @@ def fused_program(height=56, width=56, blob=None, threads=256):
     buf = C.create_string_buffer(n)
     L.yf_b200_fused_json_ex(height, width, bp, threads, buf, n)
     prog = json.loads(buf.value.decode())
-    for key, what in (("params", 5 if threads == 512 else 3), ("epi", 4)):
+    for key, what in (("params", {512: 5, 4512: 6}.get(threads, 3)), ("epi", 4)):
         k = L.yf_b200_plan_blob(height, width, bp, what, None, 0)
         raw = C.create_string_buffer(max(int(k), 1))
         L.yf_b200_plan_blob(height, width, bp, what, raw, k)

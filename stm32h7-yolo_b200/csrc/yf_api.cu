@@ -81,12 +81,18 @@ struct PlanDev {
   uint8_t* d_fparams_lat = nullptr;
   FusedPhase* d_fphases_lat = nullptr;
   bool fused_lat = false;
+  // and for the cluster shape (the front phases of one image shared by a cluster of CTAs over distributed shared memory):
+  // launches of so few images that every image can have a cluster of its own
+  FusedProgram fprog_cl;
+  uint8_t* d_fparams_cl = nullptr;
+  FusedPhase* d_fphases_cl = nullptr;
+  int cluster_images = 0;               // images one launch of the cluster shape can take (0: shape unavailable)
   ~PlanDev() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (int l = 1; l < kLayerLanes; ++l) cudaFree(d_arena_l[l]);
     cudaFree(d_epi); cudaFree(d_epif);
     cudaFree(d_wblob); cudaFree(d_luts); cudaFree(d_arena); cudaFree(d_in); cudaFree(d_head); cudaFree(d_fparams); cudaFree(d_fphases);
-    cudaFree(d_fparams_lat); cudaFree(d_fphases_lat);
+    cudaFree(d_fparams_lat); cudaFree(d_fphases_lat); cudaFree(d_fparams_cl); cudaFree(d_fphases_cl);
     for (int i = 0; i < kRing; ++i) { cudaFree(r_in[i]); cudaFree(r_head[i]); }
     for (int i = 0; i < kRing; ++i) { if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]); if (ev_comp[i]) cudaEventDestroy(ev_comp[i]); if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]); }
   }
@@ -152,6 +158,7 @@ struct Network {
   ai_buffer rep_in{}, rep_out{};        // I/O descriptors handed out by ai_network_get_report
   uint64_t launches = 0, images = 0;
   uint32_t lat_launches = 0;            // fused launches that took the latency shape
+  uint32_t cl_launches = 0;             // ... of which with a cluster per image
   float last_ms = 0.f;
   // Multi-GPU context (yf_b200_config.device_mask / YF_B200_DEVICES): members[0] is this object, the others are
   // contexts on the other GPUs owned by it and driven by workers[i]; a member's `owner` points back here.
@@ -349,6 +356,20 @@ PlanDev* get_plan(Network* n, int H, int W) {
       if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fphases_lat, FL.phases.data(), dbytes, cudaMemcpyHostToDevice, n->stream), "upload fused descriptors")) return nullptr;
       if (!cuda_ok(n, fused_init(FL, true), "fused kernel attributes")) return nullptr;
       pd->fused_lat = true;
+      // The cluster shape is OPT-IN (YF_B200_FUSED_CLUSTER=1): measured on B200 it is slower than the plain latency shape
+      // (one image 49 vs 42 us): a cluster barrier plus the remote stores cost ~1.2 k cycles per shared phase, more than
+      // sharing the phase's work over four SMs saves.
+      const char* cl_env = std::getenv("YF_B200_FUSED_CLUSTER");
+      if (cl_env && std::atoi(cl_env) && build_fused(pd->fplan, &pd->fprog_cl, kFusedLatThreads, kFusedMaxCluster) && pd->fprog_cl.ok &&
+          fused_spec_matches(pd->fprog_cl)) {
+        const FusedProgram& FC = pd->fprog_cl;
+        if (!cuda_ok(n, cudaMalloc(&pd->d_fparams_cl, FC.params.size()), "cudaMalloc fused params", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+        if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fparams_cl, FC.params.data(), FC.params.size(), cudaMemcpyHostToDevice, n->stream), "upload fused params")) return nullptr;
+        if (!cuda_ok(n, cudaMalloc(&pd->d_fphases_cl, dbytes), "cudaMalloc fused descriptors", al, AI_ERROR_CODE_NETWORK_WEIGHTS)) return nullptr;
+        if (!cuda_ok(n, cudaMemcpyAsync(pd->d_fphases_cl, FC.phases.data(), dbytes, cudaMemcpyHostToDevice, n->stream), "upload fused descriptors")) return nullptr;
+        if (!cuda_ok(n, fused_init(FC, true), "fused kernel attributes")) return nullptr;
+        pd->cluster_images = fused_max_clusters(FC);
+      }
     }
   } else {
     pd->fprog.ok = false;
@@ -482,10 +503,14 @@ bool run_steps(Network* n, PlanDev* pd, const int8_t* d_in, int8_t* d_head, uint
     L.d_done = n->done_words; L.done_seq = n->done_seq; L.grid_out = &n->done_grid;
     // a launch that runs alone with at most one image per SM: the latency shape (twice the warps on each image)
     const bool lat = pd->fused_lat && !overlapped && static_cast<int>(nb) <= n->sm_count;
-    if (lat) { L.d_params = pd->d_fparams_lat; L.d_phases = pd->d_fphases_lat; }
-    if (!cuda_ok(n, launch_fused(lat ? pd->fprog_lat : pd->fprog, L), "fused kernel")) return false;
+    // ... and with so few images that each can have a cluster of CTAs: the cluster shape
+    const bool cl = lat && static_cast<int>(nb) <= pd->cluster_images;
+    if (cl) { L.d_params = pd->d_fparams_cl; L.d_phases = pd->d_fphases_cl; }
+    else if (lat) { L.d_params = pd->d_fparams_lat; L.d_phases = pd->d_fphases_lat; }
+    if (!cuda_ok(n, launch_fused(cl ? pd->fprog_cl : lat ? pd->fprog_lat : pd->fprog, L), "fused kernel")) return false;
     ++n->launches;
     if (lat) ++n->lat_launches;
+    if (cl) ++n->cl_launches;
     return true;
   }
   if (!prepare_layer_lane(n, pd, lane)) return false;
@@ -1492,8 +1517,9 @@ AI_API_ENTRY int32_t yf_b200_get_stats(ai_handle network, yf_b200_stats* st) {
   st->fused = (it != n->plans.end() && !n->observer && !n->step_profiling && n->mode != 1 && it->second->fprog.ok) ? 1 : 0;
   st->fused_smem_bytes = it == n->plans.end() ? 0 : it->second->fprog.smem_bytes;
   st->fused_latency = (st->fused && it->second->fused_lat) ? 1 : 0;
-  st->latency_launches = n->lat_launches;
-  for (size_t i = 1; i < n->members.size(); ++i) st->latency_launches += n->members[i]->lat_launches;
+  st->latency_launches = n->lat_launches; st->cluster_launches = n->cl_launches;
+  st->cluster_images = (st->fused_latency && it != n->plans.end()) ? it->second->cluster_images : 0;
+  for (size_t i = 1; i < n->members.size(); ++i) { st->latency_launches += n->members[i]->lat_launches; st->cluster_launches += n->members[i]->cl_launches; }
   return 0;
 }
 
@@ -1620,14 +1646,14 @@ AI_API_ENTRY int64_t yf_b200_plan_json(int32_t H, int32_t W, const void* blob, c
   return static_cast<int64_t>(j.size() + 1);
 }
 
-static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedProgram* F, int threads = kFusedWorkerThreads) {
+static bool host_fused(int32_t H, int32_t W, const void* blob, Plan* P, FusedProgram* F, int threads = kFusedWorkerThreads, int cluster = 1) {
   TflModel model;
   if (!host_model(&model)) return false;
   size_t need = 0; st_blob_layout(model, &need);
   std::string perr;
   const bool st = std::getenv("YF_B200_ST_ACTIVATIONS") && std::atoi(std::getenv("YF_B200_ST_ACTIVATIONS"));
   if (!build_plan(model, H, W, static_cast<const uint8_t*>(blob), blob ? need : 0, P, &perr, 16, st)) { set_text("plan: " + perr); return false; }
-  build_fused(*P, F, threads);
+  build_fused(*P, F, threads, cluster);
   if (!F->ok) { set_text("fused: " + F->why); return false; }
   return true;
 }
@@ -1636,13 +1662,16 @@ AI_API_ENTRY int64_t yf_b200_fused_json(int32_t H, int32_t W, const void* blob, 
   return yf_b200_fused_json_ex(H, W, blob, kFusedWorkerThreads, dst, cap);
 }
 AI_API_ENTRY int64_t yf_b200_fused_json_ex(int32_t H, int32_t W, const void* blob, int32_t threads, char* dst, uint64_t cap) {
+  // threads: 256 | 512, plus 1000 x the cluster size for the cluster shape (4512 = 512-thread CTAs in clusters of 4)
+  const int cluster = threads >= 1000 ? threads / 1000 : 1;
+  threads %= 1000;
   Plan P; FusedProgram F;
-  if (!host_fused(H, W, blob, &P, &F, threads)) return -1;
+  if (!host_fused(H, W, blob, &P, &F, threads, cluster)) return -1;
   std::string j = "{";
   auto kv = [&](const char* k, long long v, bool comma = true) { j += std::string("\"") + k + "\":" + std::to_string(v) + (comma ? "," : ""); };
   kv("in_off", F.in_off); kv("in_bytes", F.in_bytes); kv("arena_off", F.arena_off); kv("arena_bytes", F.arena_bytes);
   kv("slot_off", F.slot_off); kv("slot_bytes", F.slot_bytes); kv("smem_bytes", F.smem_bytes); kv("head_bytes", F.head_bytes);
-  kv("threads", F.threads); kv("warpgroups", F.threads / 128); kv("tmem_cols", F.tmem_cols); kv("param_slots", kFusedParamSlots); kv("desc_off", F.desc_off);
+  kv("threads", F.threads); kv("cluster", F.cluster); kv("warpgroups", F.threads / 128); kv("tmem_cols", F.tmem_cols); kv("param_slots", kFusedParamSlots); kv("desc_off", F.desc_off);
   kv("in_pf_phase", F.in_pf_phase); kv("split", F.split); kv("smem_bytes_spec", F.smem_bytes_spec); kv("spec", fused_spec_matches(F) ? 1 : 0);
   j += "\"phases\":[";
   for (size_t i = 0; i < F.phases.size(); ++i) {
@@ -1653,7 +1682,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json_ex(int32_t H, int32_t W, const void* blo
     kv("out_off", p.out_off); kv("out_cs", p.out_cs); kv("add_off", p.add_off); kv("add_cs", p.add_cs); kv("nk", p.nk); kv("npad", p.npad);
     kv("cout", p.cout); kv("chunks_out", p.chunks_out); kv("epi_base", p.epi_base); kv("has_lut", p.has_lut); kv("in_zp", p.in_zp);
     kv("to_global", p.to_global); kv("param_off", p.param_off); kv("param_bytes", p.param_bytes); kv("w_off", p.w_off); kv("lut_off", p.lut_off);
-    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("epi_off", p.epi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw); kv("in_wp", p.in_wp); kv("out_wp", p.out_wp); kv("out_zp", p.out_zp);
+    kv("dw_off", p.dw_off); kv("dwepi_off", p.dwepi_off); kv("epi_off", p.epi_off); kv("scratch_off", p.scratch_off); kv("nw", p.nw); kv("per", p.per); kv("in_wp", p.in_wp); kv("out_wp", p.out_wp); kv("out_zp", p.out_zp);
     kv("in_ws", p.in_ws); kv("out_ws", p.out_ws); kv("scratch_ws", p.scratch_ws); kv("tpg", p.tpg); kv("ntiles", p.ntiles);
     kv("pair", p.pair); kv("sep_y", p.sep_y); kv("rows_a", p.rows_a); kv("row_b0", p.row_b0); kv("rows_single", p.rows_single);
     kv("out_pair_shift", p.out_pair_shift); kv("grp_warps", p.grp_warps); kv("grp_warps_single", p.grp_warps_single);
@@ -1670,7 +1699,7 @@ AI_API_ENTRY int64_t yf_b200_fused_json_ex(int32_t H, int32_t W, const void* blo
 
 AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t H, int32_t W, const void* blob, int32_t what, void* dst, uint64_t cap) {
   Plan P; FusedProgram F;
-  if (what >= 3 ? !host_fused(H, W, blob, &P, &F, what == 5 ? kFusedLatThreads : kFusedWorkerThreads) : !host_plan(H, W, blob, &P)) return -1;
+  if (what >= 3 ? !host_fused(H, W, blob, &P, &F, what >= 5 ? kFusedLatThreads : kFusedWorkerThreads, what == 6 ? kFusedMaxCluster : 1) : !host_plan(H, W, blob, &P)) return -1;
   const void* src; size_t n;
   switch (what) {
     case 0: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
@@ -1678,7 +1707,7 @@ AI_API_ENTRY int64_t yf_b200_plan_blob(int32_t H, int32_t W, const void* blob, i
     case 2: src = P.wblob.data(); n = P.wblob.size(); break;
     case 3: src = F.params.data(); n = F.params.size(); break;
     case 4: src = P.epi.data(); n = P.epi.size() * sizeof(EpiCh); break;
-    case 5: src = F.params.data(); n = F.params.size(); break;
+    case 5: case 6: src = F.params.data(); n = F.params.size(); break;
     default: return -1;
   }
   if (dst && cap) std::memcpy(dst, src, std::min<size_t>(cap, n));

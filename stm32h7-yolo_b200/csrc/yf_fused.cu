@@ -100,6 +100,7 @@ struct Cx {
   uint8_t* smem;
   uint32_t smem_base, tmem_base;
   int tid, warp, lane;
+  int rank;                                    // CTA's rank in its cluster (0 without clusters)
   bool ctrl, lead, ok;
   uint32_t use0, use1, in_uses;                // completed waits on mma_done[0/1], in_full
   uint32_t total_pc;
@@ -184,7 +185,30 @@ __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem,
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
 // what a unit needs of the running state: where this image's rows go
-struct UnitCtx { int out_shift, img_a, img_b, head_bytes; int8_t* out; };
+struct UnitCtx { int out_shift, img_a, img_b, head_bytes; int8_t* out; int rank; };
+
+// Stores of a phase whose work a cluster of C CTAs shares: every CTA keeps the whole tensor, so a result goes to the
+// same location of all of them (the others through distributed shared memory).  C == 1: a plain store.
+template <int C>
+__device__ __forceinline__ void st_all_u32(uint8_t* p, uint32_t v, int rank) {
+  *reinterpret_cast<uint32_t*>(p) = v;
+  if constexpr (C > 1) {
+    const uint32_t la = smem_u32(p);
+#pragma unroll
+    for (int d = 1; d < C; ++d) st_cluster_u32(mapa_shared(la, static_cast<uint32_t>((rank + d) & (C - 1))), v);
+  }
+}
+template <int C>
+__device__ __forceinline__ void st_all_v4(uint8_t* p, uint4 v, int rank) {
+  *reinterpret_cast<uint4*>(p) = v;
+  if constexpr (C > 1) {
+    const uint32_t la = smem_u32(p);
+#pragma unroll
+    for (int d = 1; d < C; ++d) st_cluster_v4(mapa_shared(la, static_cast<uint32_t>((rank + d) & (C - 1))), v);
+  }
+}
+// C > 1: this phase is shared by a cluster (front phases of the cluster shape): results go to every CTA
+template <int C>
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
                                           int row, int g, int rows, const UnitCtx& rt) {
   uint32_t v[16];
@@ -226,9 +250,9 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
     uint8_t* o = smem + ph.out_off + g * 4 * ph.out_ws + ((y + 1) * ph.out_wp + (row - y * ph.Wout) + 1) * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (j < nwords) *reinterpret_cast<uint32_t*>(o + j * ph.out_ws) = w[j];
+      if (j < nwords) st_all_u32<C>(o + j * ph.out_ws, w[j], rt.rank);
   } else {
-    *reinterpret_cast<uint4*>(smem + ph.out_off + rt.out_shift + g * ph.out_cs + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    st_all_v4<C>(smem + ph.out_off + rt.out_shift + g * ph.out_cs + row * 16, make_uint4(w[0], w[1], w[2], w[3]), rt.rank);
   }
 }
 
@@ -236,29 +260,33 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
 // (tiles t0 .. t0+nt-1 are the group whose accumulators sit in TMEM, tile t at column (t - t0) * npad)
 // tcol0: TMEM column of the group's first tile (0 for the 1x1 layers, whose groups reuse the columns; the first conv
 // keeps every tile in its own columns)
-template <int NT>
+// C > 1: the phase is shared by a cluster of C CTAs (results stored to all of them).  DEAL: the units are dealt over the
+// whole cluster's warpgroups (1x1 layers: every CTA holds every tile's accumulators); otherwise over this CTA's own
+// (first conv: the CTA's tiles are t0, t0 + tstride, ... and only they are in its TMEM, at tcol0 + t * npad).
+template <int NT, int C = 1, bool DEAL = false>
 __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt, const FusedArgs& a,
-                                              int tcol0 = 0) {
-  constexpr int kWgs = Shape<NT>::wgs;
-  const UnitCtx u{rt.out_shift, rt.img_a, rt.img_b, a.head_bytes, a.out};
+                                              int tcol0 = 0, int tstride = 1) {
+  constexpr int kWgs = DEAL ? Shape<NT>::wgs * C : Shape<NT>::wgs;
+  const int wgi = DEAL ? (c.warp >> 2) * C + c.rank : (c.warp >> 2);
+  const UnitCtx u{rt.out_shift, rt.img_a, rt.img_b, a.head_bytes, a.out, c.rank};
   auto unit = [&](uint32_t taddr, int row, int g) {
-    conv_unit(ph, c.smem, slot + ph.lut_off, reinterpret_cast<const EpiChF*>(slot + ph.epi_off), taddr, row, g, rows, u);
+    conv_unit<C>(ph, c.smem, slot + ph.lut_off, reinterpret_cast<const EpiChF*>(slot + ph.epi_off), taddr, row, g, rows, u);
   };
   const int q = c.warp & 3, chunks = ph.chunks_out;
   const uint32_t tq = c.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(tcol0);
   if (nt >= kWgs) {
     // at least a tile per warpgroup: a warpgroup takes whole tiles (all chunks), so 16-channel and tail chunks are shared evenly
 #pragma unroll 1
-    for (int t = c.warp >> 2; t < nt; t += kWgs) {
-      const int row0 = (t0 + t) * 128 + q * 32;
+    for (int t = wgi; t < nt; t += kWgs) {
+      const int row0 = (t0 + t * tstride) * 128 + q * 32;
       if (row0 >= rows) continue;                            // this warp's 32 rows are all padding
       for (int g = 0; g < chunks; ++g) unit(tq + t * ph.npad + g * 16, row0 + c.lane, g);
     }
   } else {
     // fewer tiles than warpgroups: deal the (tile, chunk) units round-robin (fused_has_rows() states the same rule)
-    for (int u = c.warp >> 2, t = 0, g = c.warp >> 2; u < nt * chunks; u += kWgs, g += kWgs) {
+    for (int u = wgi, t = 0, g = wgi; u < nt * chunks; u += kWgs, g += kWgs) {
       while (g >= chunks) { g -= chunks; ++t; }
-      const int row0 = (t0 + t) * 128 + q * 32;
+      const int row0 = (t0 + t * tstride) * 128 + q * 32;
       if (row0 < rows) unit(tq + t * ph.npad + g * 16, row0 + c.lane, g);
     }
   }
@@ -266,18 +294,22 @@ __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c,
 
 // DEPTHWISE_CONV_2D 3x3
 // requantise the four channels of one word and store it
+template <int C>
 __device__ __forceinline__ void dw_store(const int32_t (&acc)[4], const int32_t (&k_bias)[4], const int32_t (&k_mult)[4], const int32_t (&k_c2p)[4],
-                                         const int32_t (&k_e)[4], bool has_lut, const uint8_t* lut, uint8_t* o) {
+                                         const int32_t (&k_e)[4], bool has_lut, const uint8_t* lut, uint8_t* o, int rank) {
   uint32_t ow = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int32_t idx = requant_idx(acc[j], k_bias[j], k_mult[j], k_c2p[j], k_e[j]);
     ow |= static_cast<uint32_t>(has_lut ? static_cast<int32_t>(lut[idx]) : (idx ^ 0x80)) << (8 * j);
   }
-  *reinterpret_cast<uint32_t*>(o) = ow;
+  st_all_u32<C>(o, ow, rank);
 }
 
-__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int rows, int out_shift, long long* tp) {
+// (C > 1: the pixels are dealt over the threads of a cluster -- `tid` is then the virtual thread rank * threads + tid,
+//  ph.per counts the cluster's threads -- and every word is stored to all CTAs)
+template <int C = 1>
+__device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, const uint8_t* slot, int tid, int rows, int out_shift, long long* tp, int rank = 0) {
   const int nw = ph.nw, per = ph.per;
   YF_STAMP(tp, 0);
   if (tid >= per * nw) return;
@@ -342,8 +374,8 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
         bcc[3] = __dp4a(static_cast<int>(xb[kx]), static_cast<int>(w.w), bcc[3]);
       }
     }
-    dw_store(acc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o);
-    dw_store(bcc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o + dO);
+    dw_store<C>(acc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o, rank);
+    dw_store<C>(bcc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o + dO, rank);
     o += 2 * dO; p = q + dP; ox = oxq + dx;
     if (ox >= Wout) { ox -= Wout; p += dWrap; }
   }
@@ -360,7 +392,7 @@ __device__ __forceinline__ void dw_phase(const FusedPhase& ph, uint8_t* smem, co
         acc[2] = __dp4a(static_cast<int>(x), static_cast<int>(w.z), acc[2]);
         acc[3] = __dp4a(static_cast<int>(x), static_cast<int>(w.w), acc[3]);
       }
-    dw_store(acc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o);
+    dw_store<C>(acc, k_bias, k_mult, k_c2p, k_e, has_lut, lut, o, rank);
   }
   YF_STAMP(tp, 8);
 }
@@ -496,14 +528,15 @@ __device__ __forceinline__ void pool_phase(const FusedPhase& ph, uint8_t* smem, 
 }
 
 // first conv: every thread builds one A row (3 x 16-byte chunks) of tile wgs * r + (tid >> 7)
-template <int NT>
-__device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem, int tid, int r) {
+// (C > 1: the CTA of rank `rank` builds the tiles rank, rank + C, ...; its local tile lt = wgs * r + (tid >> 7))
+template <int NT, int C = 1>
+__device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem, int tid, int r, int rank = 0) {
   constexpr int kWgs = Shape<NT>::wgs, kStages = Shape<NT>::stages;
   const uint32_t zpw = static_cast<uint32_t>(ph.in_zp & 0xff) * 0x01010101u;
   const int row_bytes = ph.Win * 3, rt = tid & 127, hf = tid >> 7;
   const uint8_t* image = smem + ph.in_off;
   uint8_t* stage = smem + ph.scratch_off + ((kWgs * r + hf) % kStages) * 6144;
-  const int rr = (kWgs * r + hf) * 128 + rt;
+  const int rr = (rank + (kWgs * r + hf) * C) * 128 + rt;
   if (rr >= ph.rows_out) return;
   const int oy = small_div(rr, ph.rcp_wout), ox = rr - oy * ph.Wout;
 #pragma unroll
@@ -526,7 +559,8 @@ __device__ __forceinline__ void im2col_build(const FusedPhase& ph, uint8_t* smem
 // ---- one phase ------------------------------------------------------------------------------------------------------
 // `ph` is a shared-memory descriptor (generic kernel) or a bundle of compile-time constants (specialised kernel);
 // p = its index; everything that varies between executions is in rt.
-template <int NT>
+// CF > 1: this phase is shared by a cluster of CF CTAs (front phases of the cluster shape, see build_fused)
+template <int NT, int CF = 1>
 __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& c, const FusedArgs& a, const Rt& rt, long long* tp) {
   constexpr int kWgs = Shape<NT>::wgs, kStages = Shape<NT>::stages, kCtrlWarp = Shape<NT>::ctrl_warp;
   uint8_t* const smem = c.smem;
@@ -544,8 +578,11 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
     uint32_t grp = single ? ph.grp_warps_single : ph.grp_warps;
     const uint32_t own0 = single ? ph.own_single[0] : ph.own[0], own1 = single ? ph.own_single[1] : ph.own[1];
     const uint32_t sW = c.smem_base + a.slot_off + s_idx * a.slot_bytes + ph.w_off, sA = c.smem_base + ph.in_off;
-    const bool ctrl_busy = (own0 >> kCtrlWarp) & 1u;          // the control warp owns rows of the first group
-    for (int t0 = 0, g = 0; t0 < ntiles; t0 += tpg, grp >>= 8, ++g) {
+    const uint32_t own_first = (CF > 1 && (c.rank & 2)) ? own1 : own0;       // masks of the first group (cluster shape: of this rank)
+    const int own_shift = (CF > 1 ? 16 * (c.rank & 1) : 0) + kCtrlWarp;
+    const bool ctrl_busy = ((own_first >> own_shift) & 1u) != 0u;            // the control warp owns rows of the first group
+    if (CF > 1) grp >>= 8 * c.rank;                         // cluster shape: one tile group, counts and masks indexed by rank
+    for (int t0 = 0, g = (CF > 1 ? c.rank : 0); t0 < ntiles; t0 += tpg, grp >>= 8, ++g) {
       const int nt = min(tpg, ntiles - t0);
       // warps whose TMEM lane quarter holds no pixel rows of this group (most warps of the 14x14 layers)
       // never touch TMEM: they go straight to the end-of-phase barrier (fused_has_rows(), evaluated by the planner)
@@ -586,7 +623,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
       ++c.use0;
       if (has_rows) {
         tc_fence_after();
-        conv_epilogue<NT>(ph, c, slot, t0, nt, rows, rt, a);
+        conv_epilogue<NT, CF, (CF > 1)>(ph, c, slot, t0, nt, rows, rt, a);
         tc_fence_before();
         if (t0 == 0) YF_STAMP(tp, 4);
       }
@@ -601,11 +638,12 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
     // Software pipeline over rounds of one tile per warpgroup: build the A rows of round r, issue its MMAs, then
     // requantise the tiles of round r-1 while those MMAs run.  Waiting for round r-1's accumulators also frees the A
     // stages round r+1 will overwrite (stage = tile % (2 * warpgroups)).
-    const int rounds = (ntiles + kWgs - 1) / kWgs;
+    const int nloc = CF > 1 ? (ntiles - c.rank + CF - 1) / CF : ntiles;     // this CTA's tiles: rank, rank + CF, ...
+    const int rounds = (nloc + kWgs - 1) / kWgs;
 #pragma unroll 1
     for (int r = 0; r <= rounds; ++r) {
       if (r < rounds) {
-        im2col_build<NT>(ph, smem, tid, r);
+        im2col_build<NT, CF>(ph, smem, tid, r, c.rank);
         fence_proxy_async_smem();
         __syncthreads();
         if (c.ctrl) {
@@ -613,7 +651,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
           const bool el = elect_one();
           for (int h = 0; h < kWgs; ++h) {
             const int tt = kWgs * r + h;
-            if (tt >= ntiles) break;
+            if (tt >= nloc) break;
             const uint32_t sS = c.smem_base + ph.scratch_off + (tt % kStages) * 6144;
             for (int k = 0; k < 2; ++k)
               if (el) mma_i8(c.tmem_base + tt * ph.npad, mk_desc(ph.adesc_lo, sS + k * 4096), mk_desc(ph.bdesc_lo, sW + k * 2 * ph.npad * 16),
@@ -627,7 +665,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
         const int rp = r - 1;
         if (rp & 1) { wait_bar(c, a, c.mma_done(a) + 8, c.use1 & 1, 304); ++c.use1; } else { wait_bar(c, a, c.mma_done(a), c.use0 & 1, 304); ++c.use0; }
         tc_fence_after();
-        conv_epilogue<NT>(ph, c, slot, kWgs * rp, min(kWgs, ntiles - kWgs * rp), rows, rt, a, kWgs * rp * ph.npad);
+        conv_epilogue<NT, CF, false>(ph, c, slot, (CF > 1 ? c.rank : 0) + kWgs * rp * CF, min(kWgs, nloc - kWgs * rp), rows, rt, a, kWgs * rp * ph.npad, CF);
         tc_fence_before();
       }
     }
@@ -635,25 +673,32 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
   } else {
     wait_bar(c, a, par_bar, par_parity, 302);
     YF_STAMP(tp, 2);
-    if (kind == STEP_DW) dw_phase(ph, smem, slot, tid, (ph.pair && !rt.pair_b) ? ph.rows_a : ph.rows_out, rt.out_shift, tp);
+    if (kind == STEP_DW) dw_phase<CF>(ph, smem, slot, CF > 1 ? c.rank * NT + tid : tid, (ph.pair && !rt.pair_b) ? ph.rows_a : ph.rows_out, rt.out_shift, tp, c.rank);
     else if (kind == STEP_MAXPOOL) pool_phase<NT>(ph, smem, slot, tid, rt.out_shift);
     if (c.lead && c.producer(a)->pc_next <= rt.pc + 1) housekeeping(c, a, rt, pf_here);   // only when the next phase's block is not even requested yet
   }
-  fence_proxy_async_smem();            // this phase's st.shared -> visible to the next phase's MMAs / bulk copies
+  // this phase's st.shared -> visible to the next phase's MMAs / bulk copies; a shared phase ends with the CLUSTER's
+  // barrier (also the replicated pool phases: a faster CTA's next phase stores into buffers this one may still read)
+  if (CF > 1) fence_proxy_async_all(); else fence_proxy_async_smem();
 #ifdef YF_TRACE
   if (tp) tp[10] = clock64();
 #endif
-  __syncthreads();
+  if (CF > 1) cluster_sync_all(); else __syncthreads();
 #ifdef YF_TRACE
   if (tp) tp[11] = clock64();
 #endif
 }
 
 // ---- prologue / epilogue shared by the two kernels ---------------------------------------------------------------
-template <int NT>
+// image stream of this CTA (cluster shape: of its cluster) and the number of streams in the grid
+template <int C> __device__ __forceinline__ int img_stream() { return static_cast<int>(blockIdx.x) / C; }
+template <int C> __device__ __forceinline__ int img_streams() { return static_cast<int>(gridDim.x) / C; }
+
+template <int NT, int C = 1>
 __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* smem) {
   constexpr int kCtrlWarp = Shape<NT>::ctrl_warp;
   c.smem = smem; c.smem_base = smem_u32(smem);
+  c.rank = C > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.bars_off + 8 * (3 + kFusedParamSlots));
   c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
   c.ctrl = c.warp == kCtrlWarp; c.lead = c.tid == kCtrlWarp * 32; c.ok = true;
@@ -669,8 +714,8 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   __syncthreads();
   tc_fence_after();
   c.tmem_base = *tmem_slot;
-  c.my_images = (a.n_img - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int nback = a.nphases - a.split;
+  c.my_images = (a.n_img - img_stream<C>() + img_streams<C>() - 1) / img_streams<C>();
+  const int nback = (C > 1 && c.rank != 0) ? 0 : a.nphases - a.split;    // cluster shape: rank 0 alone runs the back phases
   c.total_pc = static_cast<uint32_t>(c.my_images * a.split + ((c.my_images + 1) >> 1) * nback);
   if (c.lead) {
     Producer pr{};
@@ -678,29 +723,32 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
     pr.slots_addr = c.smem_base + a.slot_off; pr.slot_bytes = a.slot_bytes;
     pr.in_addr = c.smem_base + a.in_off; pr.in_bytes = a.in_bytes; pr.params = a.params; pr.in = a.in;
     *c.producer(a) = pr;
-    if (c.my_images > 0) housekeeping_out(c.smem_base + a.bars_off, 0u, static_cast<int>(blockIdx.x));   // first image + first blocks
+    if (c.my_images > 0) housekeeping_out(c.smem_base + a.bars_off, 0u, img_stream<C>());   // first image + first blocks
   }
+  if (C > 1) cluster_sync_all();        // every CTA of the cluster runs before any of them stores into another's shared memory
 }
-template <int NT>
+template <int NT, int C = 1>
 __device__ __forceinline__ void cta_teardown(const Cx& c, const FusedArgs& a) {
   tc_fence_before();
   __syncthreads();
   // Completion word for a host that polls instead of synchronising the stream (blocking calls of a few images): the
   // barrier orders every thread's head stores before this thread, the system-scope fence before the flag.
-  if (a.done && c.tid == 0) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(a.done + blockIdx.x) = a.done_seq; }
+  if (a.done && c.tid == 0 && c.rank == 0) { __threadfence_system(); *reinterpret_cast<volatile uint32_t*>(a.done + img_stream<C>()) = a.done_seq; }
   if (c.warp == 0) tmem_dealloc(c.tmem_base, Shape<NT>::tmem_cols);
 }
 // the image-dependent part of Rt for front phases of the CTA's k-th image / for the back phases that follow it
+template <int C = 1>
 __device__ __forceinline__ void rt_front(Rt& rt, const FusedArgs& a, int k, int my_images) {
-  const int img = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+  const int img = img_stream<C>() + k * img_streams<C>();
   rt.pair_b = false; rt.img_a = img; rt.img_b = img;
-  rt.next_img = (k + 1 < my_images) ? img + static_cast<int>(gridDim.x) : -1;
+  rt.next_img = (k + 1 < my_images) ? img + img_streams<C>() : -1;
 }
+template <int C = 1>
 __device__ __forceinline__ void rt_back(Rt& rt, const FusedArgs& a, int k) {
-  const int img = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+  const int img = img_stream<C>() + k * img_streams<C>();
   rt.pair_b = (k & 1) != 0; rt.out_shift = 0; rt.next_img = -1;
   rt.img_b = img;                                                        // only used when pair_b
-  rt.img_a = rt.pair_b ? img - static_cast<int>(gridDim.x) : img;
+  rt.img_a = rt.pair_b ? img - img_streams<C>() : img;
 }
 
 #ifdef YF_TRACE
@@ -749,12 +797,14 @@ __global__ void __launch_bounds__(kFusedWorkerThreads, kFusedCtasPerSm) yoloface
 // as a bundle of constants.
 #include "yf_fused_spec.inc"
 
+// C = SpecProgram<V>::cluster CTAs share the front phases of an image (1: none); the back phases are never shared
 template <int NT, int V, int P>
 __device__ __forceinline__ void spec_step(Cx& c, const FusedArgs& a, Rt& rt, int k) {
   const FusedPhase ph = spec_phase<V, P>();
+  constexpr int CF = P < SpecProgram<V>::split ? SpecProgram<V>::cluster : 1;
   if (P < SpecProgram<V>::split) rt.out_shift = (k & 1) ? ph.out_pair_shift : 0;
   YF_TRACE_PHASE(P)
-  do_phase<NT>(ph, P, c, a, rt, tp);
+  do_phase<NT, CF>(ph, P, c, a, rt, tp);
   ++rt.pc;
 }
 template <int NT, int V, int P0, int P1>
@@ -768,22 +818,23 @@ __device__ __forceinline__ void spec_range(Cx& c, const FusedArgs& a, Rt& rt, in
 template <int NT, int V>
 __global__ void __launch_bounds__(NT, Shape<NT>::ctas_per_sm) yoloface_fused_spec_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int C = SpecProgram<V>::cluster;
   Cx c;
-  cta_setup<NT>(c, a, smem);
+  cta_setup<NT, C>(c, a, smem);
   Rt rt; rt.pc = 0u;
 #pragma unroll 1
   for (int k = 0; k < c.my_images; ++k) {
-    rt_front(rt, a, k, c.my_images);
+    rt_front<C>(rt, a, k, c.my_images);
     spec_range<NT, V, 0, SpecProgram<V>::split>(c, a, rt, k);
-    if ((k & 1) || k == c.my_images - 1) {
-      rt_back(rt, a, k);
+    if (((k & 1) || k == c.my_images - 1) && (C == 1 || c.rank == 0)) {   // cluster shape: rank 0 holds everything the back phases need
+      rt_back<C>(rt, a, k);
       spec_range<NT, V, SpecProgram<V>::split, SpecProgram<V>::num_phases>(c, a, rt, k);
     }
   }
 #ifdef YF_TRACE
   if (a.trace && c.tid == 0 && blockIdx.x == 0 && rt.pc < 80u) a.trace[rt.pc] = clock64();
 #endif
-  cta_teardown<NT>(c, a);
+  cta_teardown<NT, C>(c, a);
 }
 
 // does a specialised kernel implement exactly this program (for the CTA shape it was laid out for)?
@@ -794,6 +845,8 @@ static bool spec_matches(const FusedProgram& F) {
   return std::memcmp(F.phases.data(), SpecProgram<V>::words, sizeof(FusedPhase) * SpecProgram<V>::num_phases) == 0;
 }
 bool fused_spec_matches(const FusedProgram& F) {
+  if (F.cluster == SpecProgram<2>::cluster && F.threads == kFusedLatThreads) return spec_matches<2>(F);
+  if (F.cluster != 1) return false;
   return F.threads == kFusedLatThreads ? spec_matches<1>(F) : F.threads == kFusedWorkerThreads ? spec_matches<0>(F) : false;
 }
 
@@ -804,8 +857,16 @@ cudaError_t fused_init(const FusedProgram& F, bool use_spec) {
   const int pad = e ? atoi(e) : 0;
   int dev = 0;
   cudaGetDevice(&dev);
-  static int granted[3][64] = {};                            // generic | specialised | specialised, latency shape
+  static int granted[4][64] = {};                            // generic | specialised | specialised, latency shape | ..., cluster
   const bool lat = F.threads == kFusedLatThreads;
+  if (lat && F.cluster > 1) {
+    if (!use_spec) return cudaErrorInvalidValue;
+    const void* fn = reinterpret_cast<const void*>(&yoloface_fused_spec_kernel<kFusedLatThreads, 2>);
+    if (F.smem_bytes_spec + pad <= granted[3][dev & 63]) return cudaSuccess;
+    const cudaError_t r = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, F.smem_bytes_spec + pad);
+    if (r == cudaSuccess) granted[3][dev & 63] = F.smem_bytes_spec + pad;
+    return r;
+  }
   if (lat && !use_spec) return cudaErrorInvalidValue;        // the latency shape exists as a specialised kernel only
   auto grow = [&](int which, const void* fn, int bytes) {
     if (bytes + pad <= granted[which][dev & 63]) return cudaSuccess;
@@ -817,6 +878,20 @@ cudaError_t fused_init(const FusedProgram& F, bool use_spec) {
   const cudaError_t r = grow(0, reinterpret_cast<const void*>(&yoloface_fused_kernel), F.smem_bytes);
   if (r != cudaSuccess || !use_spec) return r;
   return grow(1, reinterpret_cast<const void*>(&yoloface_fused_spec_kernel<kFusedWorkerThreads, 0>), F.smem_bytes_spec);
+}
+
+int fused_max_clusters(const FusedProgram& F) {
+  if (F.threads != kFusedLatThreads || F.cluster != SpecProgram<2>::cluster) return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(F.cluster)); cfg.blockDim = dim3(kFusedLatThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(F.smem_bytes_spec);
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = static_cast<unsigned>(F.cluster); attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, yoloface_fused_spec_kernel<kFusedLatThreads, 2>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
@@ -834,6 +909,19 @@ cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L) {
   const bool spec = L.use_spec;
   a.bars_off = spec ? F.desc_off : F.desc_off + ((a.nphases * static_cast<int>(sizeof(FusedPhase)) + 127) & ~127);
   const int smem = (spec ? F.smem_bytes_spec : F.smem_bytes) + pad;
+  if (F.threads == kFusedLatThreads && F.cluster > 1) {
+    // cluster shape: one image per cluster of F.cluster CTAs (one CTA per SM); the caller checked that the clusters fit
+    if (!spec || F.cluster != SpecProgram<2>::cluster) return cudaErrorInvalidValue;
+    if (L.grid_out) *L.grid_out = L.n_img;                   // completion words: one per image (cluster)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(L.n_img * F.cluster)); cfg.blockDim = dim3(kFusedLatThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem); cfg.stream = L.stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = static_cast<unsigned>(F.cluster); attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, yoloface_fused_spec_kernel<kFusedLatThreads, 2>, a);
+  }
   if (F.threads == kFusedLatThreads) {
     // latency shape: one image per CTA, one CTA per SM; the caller only picks it for launches that fit one wave
     if (!spec) return cudaErrorInvalidValue;

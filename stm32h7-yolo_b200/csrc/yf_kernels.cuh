@@ -114,5 +114,6 @@ struct FusedLaunch {
 bool fused_spec_matches(const FusedProgram& F);
 cudaError_t fused_init(const FusedProgram& F, bool use_spec);   // shared-memory attributes of the kernel(s) F runs on
 cudaError_t launch_fused(const FusedProgram& F, const FusedLaunch& L);
+int fused_max_clusters(const FusedProgram& F);   // images one launch of the cluster shape can run at once on the current device (0: none)
 
 }  // namespace yf

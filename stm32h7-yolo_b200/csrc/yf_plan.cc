@@ -588,9 +588,13 @@ bool build_plan(const TflModel& m, int H, int W, const uint8_t* blob, size_t blo
 // ------------------------------------------------------------------------------------------
 // Fused program: shared-memory placement by liveness + per-phase parameter blocks
 // ------------------------------------------------------------------------------------------
-bool build_fused(const Plan& P, FusedProgram* F, int threads) {
+bool build_fused(const Plan& P, FusedProgram* F, int threads, int cluster) {
   *F = FusedProgram{};
   if (threads != kFusedWorkerThreads && threads != kFusedLatThreads) { F->ok = false; F->why = "unsupported CTA shape"; return false; }
+  if (cluster < 1 || cluster > kFusedMaxCluster || (cluster & (cluster - 1)) || (cluster > 1 && threads != kFusedLatThreads)) {
+    F->ok = false; F->why = "unsupported cluster size"; return false;
+  }
+  F->cluster = cluster;
   const int wgs = threads / 128, ctrl_warp = threads / 32 - 1;
   const int tmem_cols = threads == kFusedLatThreads ? kFusedLatTmemCols : kFusedTmemCols;
   F->threads = threads; F->tmem_cols = tmem_cols;
@@ -770,7 +774,8 @@ bool build_fused(const Plan& P, FusedProgram* F, int threads) {
     ph.npad = s.Npad;
     ph.ntiles = (ph.rows_out + 127) / 128;
     ph.nw = (s.Cout + 3) / 4;
-    ph.per = threads / ph.nw;
+    const bool shared_front = cluster > 1 && !back;       // this phase's work is dealt over the whole cluster
+    ph.per = ((shared_front && s.kind == STEP_DW) ? cluster * threads : threads) / ph.nw;
     ph.dy = ph.per / ph.Wout; ph.dx = ph.per % ph.Wout;
     ph.tpg = s.Npad ? std::max(1, std::min(ph.ntiles, tmem_cols / s.Npad)) : 0;
     if (ph.tpg && ph.ntiles > ph.tpg) {              // balance the groups (7 tiles: 4 + 3, not 4 + 3 -> same; 9: 3 x 3)
@@ -794,6 +799,23 @@ bool build_fused(const Plan& P, FusedProgram* F, int threads) {
       };
       ph.grp_warps = meet_counts(ph.rows_out, ph.own);
       ph.grp_warps_single = meet_counts(ph.rows_single, ph.own_single);
+      if (shared_front) {
+        // one tile group; byte r / mask r = the warps of CTA rank r (virtual warpgroup wg * cluster + r of wgs * cluster)
+        if (ph.ntiles > ph.tpg) return no("cluster shape: step " + s.name + " needs more than one tile group");
+        ph.grp_warps = 0; ph.own[0] = ph.own[1] = 0;
+        for (int r = 0; r < cluster; ++r) {
+          int n = 1;                                     // the control warp always meets, as a row owner or only to release
+          for (int w = 0; w < 4 * wgs; ++w) {
+            const int vw = (((w >> 2) * cluster + r) << 2) | (w & 3);
+            if (fused_has_rows(vw, 0, ph.ntiles, ph.rows_out, ph.chunks_out, wgs * cluster)) {
+              if (w != ctrl_warp) ++n;
+              ph.own[r >> 1] |= 1u << (16 * (r & 1) + w);
+            }
+          }
+          ph.grp_warps |= static_cast<uint32_t>(n) << (8 * r);
+        }
+        ph.grp_warps_single = ph.grp_warps; ph.own_single[0] = ph.own[0]; ph.own_single[1] = ph.own[1];
+      }
     }
     {
       // reciprocal multipliers; every quotient the kernel forms has x < 4096
@@ -804,7 +826,7 @@ bool build_fused(const Plan& P, FusedProgram* F, int threads) {
         *out = m; return true;
       };
       const int ncell = ph.out_wp ? 2 * ph.out_wp + 2 * ph.Hout : 0;
-      const int xmax = std::max({threads, ph.ntiles * 128, ph.Hin * ph.Wout + threads, ncell * ph.nw + threads, ph.rows_out});
+      const int xmax = std::max({cluster * threads, ph.ntiles * 128, ph.Hin * ph.Wout + threads, ncell * ph.nw + threads, ph.rows_out});
       if (xmax >= 4096 || !rcp(ph.nw, xmax, &ph.rcp_nw) || !rcp(ph.Wout, xmax, &ph.rcp_wout) || !rcp(ncell, xmax, &ph.rcp_ncell) || !rcp(ph.per, xmax, &ph.rcp_per))
         return no("index range of step " + s.name + " exceeds the kernel's mul-shift division");
     }

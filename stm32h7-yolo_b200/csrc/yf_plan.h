@@ -228,6 +228,7 @@ struct FusedProgram {
   int head_bytes = 0;           // bytes per image of the dense head
   int threads = 0;              // CTA shape this program was laid out for (kFusedWorkerThreads / kFusedLatThreads)
   int tmem_cols = 0;            // TMEM columns the CTA allocates
+  int cluster = 1;              // CTAs sharing the front phases of one image (see build_fused)
 };
 constexpr int kFusedMaxPhases = 32;
 // Two shapes of the fused kernel's CTA.  THROUGHPUT: 256 threads (two warpgroups), 128 TMEM columns, three CTAs per SM --
@@ -259,6 +260,13 @@ inline bool fused_has_rows(int warp, int t0, int nt, int rows_out, int chunks, i
   }
   return false;
 }
-bool build_fused(const Plan& plan, FusedProgram* prog, int threads = kFusedWorkerThreads);
+// cluster > 1 (latency shape only): the front phases of ONE image are shared by a thread-block cluster of that many
+// CTAs.  Every CTA holds the whole image's activations; a front conv phase deals its (tile, chunk) units over the
+// cluster's warpgroups (virtual warpgroup = wg * cluster + rank), a front depthwise phase its pixels over the cluster's
+// threads (virtual thread = rank * threads + tid), and every result is stored to all CTAs (distributed shared memory),
+// so after the last front phase each CTA holds the complete 7x7 tensors and rank 0 alone runs the back phases.  Front
+// conv phases then form ONE tile group, and `own` / `grp_warps` are indexed by the CTA's rank instead of the group.
+constexpr int kFusedMaxCluster = 4;
+bool build_fused(const Plan& plan, FusedProgram* prog, int threads = kFusedWorkerThreads, int cluster = 1);
 
 }  // namespace yf

@@ -138,6 +138,27 @@ def test_fused_cta_shapes_agree(yf, oracle, golden, monkeypatch, n):
         b.close()
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 33])
+def test_fused_cluster_shape(yf, oracle, golden, monkeypatch, n):
+    """Opt-in third shape: a thread-block cluster of four 512-thread CTAs shares the front phases of ONE image (units and
+    pixels dealt over the cluster, results stored to every CTA through distributed shared memory, one cluster barrier per
+    phase); rank 0 runs the 7x7 layers.  Same heads; it is off by default because it measures slower."""
+    monkeypatch.setenv("YF_B200_FUSED_CLUSTER", "1")
+    x = real_batch(golden, n, 8100 + n)
+    want = oracle.run_batch(x, threads=os.cpu_count())
+    a = yf.Network(chunk_images=512, mode="fused")
+    try:
+        st = a.stats()
+        if st["cluster_images"] == 0:
+            pytest.skip("this device cannot co-schedule clusters of four of these CTAs")
+        for rep in range(3):
+            assert np.array_equal(a.run(x), want)
+        assert a.stats()["cluster_launches"] == (3 if n <= st["cluster_images"] else 0)
+        assert a.get_error() == (0, 0)
+    finally:
+        a.close()
+
+
 def test_small_blocking_calls_poll_completion_words(yf, oracle, golden):
     """Blocking calls of a few images return when the CTAs' completion words (mapped memory) carry this call's sequence
     number, not when the stream is idle: stale words of an earlier context (the staging buffer is recycled by the

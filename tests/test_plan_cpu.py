@@ -150,22 +150,46 @@ def _has_rows(warp, t0, nt, rows, chunks, wgs):
     return any((t0 + u // chunks) * 128 + q * 32 < rows for u in range(wg, nt * chunks, wgs))
 
 
-@pytest.mark.parametrize("threads", [256, 512])
+@pytest.mark.parametrize("threads", [256, 512, 4512])
 def test_fused_program_cta_shapes(yf, oracle, golden, threads):
-    """Both CTA shapes of the fused kernel (256 threads: throughput; 512 threads, all of TMEM: latency) come from the
-    same planner: the emulated program gives the oracle's head, every (tile, chunk) unit of every conv phase has
-    exactly one owning warpgroup, and the barrier counts equal the warps that own rows plus the control warp."""
+    """The CTA shapes of the fused kernel (256 threads: throughput; 512 threads, all of TMEM: latency; 4512: latency with
+    a cluster of 4 CTAs sharing an image's front phases) come from the same planner: the emulated program gives the
+    oracle's head, every (tile, chunk) unit of every conv phase has exactly one owning warpgroup (of one CTA), and the
+    barrier counts equal the warps that own rows plus the control warp."""
     from fused_emulator import run_fused
     F = yf.fused_program(56, 56, threads=threads)
-    wgs = threads // 128
-    assert F["threads"] == threads and F["warpgroups"] == wgs and F["tmem_cols"] == (128 if threads == 256 else 512)
+    cluster, nthreads = (threads // 1000 or 1), threads % 1000
+    wgs = nthreads // 128
+    assert F["threads"] == nthreads and F["cluster"] == cluster and F["warpgroups"] == wgs and F["tmem_cols"] == (128 if nthreads == 256 else 512)
     assert F["spec"] == 1                          # a specialised kernel exists for each shape
     assert len(F["phases"]) == 26 and F["split"] == 14
     img = golden["images"][11]
     assert np.array_equal(run_fused(F, img, 3).reshape(7, 7, 18), oracle.run(img))
     ctrl = 4 * wgs - 1
-    for ph in F["phases"]:
+    for pi, ph in enumerate(F["phases"]):
+        shared = cluster > 1 and pi < F["split"]    # front phases of the cluster shape are dealt over the whole cluster
+        if ph["kind"] == 2:
+            assert ph_per(ph) == (cluster if shared else 1) * nthreads // ph["nw"]
         if ph["kind"] != 1:
+            continue
+        if shared:
+            assert ph["ntiles"] <= ph["tpg"]        # one tile group; masks / counts are indexed by the CTA's rank
+            nt, chunks, rows, W = ph["ntiles"], ph["chunks_out"], ph["rows_out"], wgs * cluster
+            seen = {}
+            for r in range(cluster):
+                owners = [w for w in range(4 * wgs) if _has_rows((((w >> 2) * cluster + r) << 2) | (w & 3), 0, nt, rows, chunks, W)]
+                mask = (ph["own" + str(r >> 1)] >> (16 * (r & 1))) & 0xffff
+                assert mask == sum(1 << w for w in owners)
+                assert ((ph["grp_warps"] >> (8 * r)) & 0xff) == len([w for w in owners if w != ctrl]) + 1
+                for w in owners:
+                    seen[(r, w >> 2)] = True
+            for t in range(nt):                     # every unit with real rows: exactly one (rank, warpgroup)
+                for q in range(4):
+                    if t * 128 + q * 32 >= rows:
+                        continue
+                    for c in range(chunks):
+                        own = [v for v in range(W) if (t in range(v, nt, W) if nt >= W else (t * chunks + c) in range(v, nt * chunks, W))]
+                        assert len(own) == 1 and (own[0] % cluster, own[0] // cluster) in seen
             continue
         for rows, counts, key in ((ph["rows_out"], ph["grp_warps"], "own"), (ph["rows_single"], ph["grp_warps_single"], "own_single")):
             for g, t0 in enumerate(range(0, ph["ntiles"], ph["tpg"])):
@@ -185,6 +209,10 @@ def test_fused_program_cta_shapes(yf, oracle, golden, threads):
                             else:
                                 own = [wg for wg in range(wgs) if (t * ph["chunks_out"] + c) in range(wg, nt * ph["chunks_out"], wgs)]
                             assert len(own) == 1 and (4 * own[0] + q) in owners
+
+
+def ph_per(ph):
+    return ph["per"]
 
 
 @pytest.mark.parametrize("hw", [(8, 8), (8, 16), (24, 16), (32, 32), (40, 56), (56, 64), (64, 64), (16, 128)])
