@@ -1,6 +1,10 @@
 // yf_fused.cu -- the whole yoloface int8 network as ONE persistent sm_100a kernel.
 //
-// One CTA (256 threads, three CTAs per SM) takes its images through all 26 fused steps.
+// One CTA takes its images through all 26 fused steps.  CTA SHAPES, one body (template
+// <int NT>): throughput -- 256 threads, three CTAs per SM, every launch of more than one image per SM; latency -- 512
+// threads, one CTA per SM, all of TMEM, launches of at most one image per SM that run alone (one frame per call is the
+// reference's own use); and, opt-in, the latency shape in clusters of four CTAs per image (front phases shared over
+// distributed shared memory: measured slower).
 // Activations never leave the SM: MMA operands sit in shared memory in chunk-planar form [C/16][rows][16 B], which is
 // directly the canonical no-swizzle K-major UMMA operand layout, so every CONV_2D is  tcgen05.mma.kind::i8
 // (smem x smem -> TMEM)  on the data where the previous phase left it; tensors only the depthwise / pool phases read
