@@ -211,6 +211,24 @@ def test_fused_program_cta_shapes(yf, oracle, golden, threads):
                             assert len(own) == 1 and (4 * own[0] + q) in owners
 
 
+def test_fused_program_rejects_unknown_shapes(yf):
+    """CTAs of 256 or 512 threads; clusters (of 2 or 4) only of 512-thread CTAs.  A cluster of 2 can be laid out but has
+    no compiled kernel (spec == 0)."""
+    for threads in (128, 384, 1024, 8512, 4256, 3512):
+        with pytest.raises(RuntimeError):
+            yf.fused_program(56, 56, threads=threads)
+    assert yf.fused_program(56, 56, threads=2512)["spec"] == 0
+    # the cluster shape needs every front conv layer's tiles in ONE TMEM group: true for the deployed model, and the
+    # layout is the plain latency shape's apart from the dealing fields
+    a, b = yf.fused_program(56, 56, threads=512), yf.fused_program(56, 56, threads=4512)
+    assert a["arena_bytes"] == b["arena_bytes"] and a["smem_bytes_spec"] == b["smem_bytes_spec"]
+    assert np.array_equal(a["params"], b["params"])
+    for pa, pb in zip(a["phases"], b["phases"]):
+        for k in pa:
+            if k not in ("per", "grp_warps", "grp_warps_single", "own0", "own1", "own_single0", "own_single1"):
+                assert pa[k] == pb[k], k
+
+
 def ph_per(ph):
     return ph["per"]
 
