@@ -707,21 +707,17 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
   c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
   c.ctrl = c.warp == kCtrlWarp; c.lead = c.tid == kCtrlWarp * 32; c.ok = true;
   c.use0 = 0u; c.use1 = 0u; c.in_uses = 0u;
-  if (c.tid == 0) {
-    for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
-    fence_mbar_init();
-  }
-  if (c.warp == 0) tmem_alloc(tmem_slot, Shape<NT>::tmem_cols);
-  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 128);          // parameter block table (<= kFusedMaxPhases entries)
-  for (int i = c.tid; i < a.nphases; i += NT) pb[i] = a.pb[i];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  c.tmem_base = *tmem_slot;
   c.my_images = (a.n_img - img_stream<C>() + img_streams<C>() - 1) / img_streams<C>();
   const int nback = (C > 1 && c.rank != 0) ? 0 : a.nphases - a.split;    // cluster shape: rank 0 alone runs the back phases
   c.total_pc = static_cast<uint32_t>(c.my_images * a.split + ((c.my_images + 1) >> 1) * nback);
+  int2* pb = reinterpret_cast<int2*>(smem + a.bars_off + 128);          // parameter block table (<= kFusedMaxPhases entries)
   if (c.lead) {
+    // The control thread starts the first image and the first parameter blocks on their way BEFORE the CTA meets: the
+    // TMEM allocation and the barrier below then overlap the loads' latency instead of preceding it.
+    for (int i = 0; i < 3 + kFusedParamSlots; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + a.bars_off) + i, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();                                            // the bulk copies (async proxy) signal these barriers
+    for (int i = 0; i < kFusedParamSlots && i < a.nphases; ++i) pb[i] = a.pb[i];
     Producer pr{};
     pr.total_pc = c.total_pc; pr.my_images = c.my_images; pr.split = a.split; pr.nphases = a.nphases;
     pr.slots_addr = c.smem_base + a.slot_off; pr.slot_bytes = a.slot_bytes;
@@ -729,6 +725,12 @@ __device__ __forceinline__ void cta_setup(Cx& c, const FusedArgs& a, uint8_t* sm
     *c.producer(a) = pr;
     if (c.my_images > 0) housekeeping_out(c.smem_base + a.bars_off, 0u, img_stream<C>());   // first image + first blocks
   }
+  if (c.warp == 0) tmem_alloc(tmem_slot, Shape<NT>::tmem_cols);
+  for (int i = kFusedParamSlots + c.tid; i < a.nphases; i += NT) pb[i] = a.pb[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem_base = *tmem_slot;
   if (C > 1) cluster_sync_all();        // every CTA of the cluster runs before any of them stores into another's shared memory
 }
 template <int NT, int C = 1>
