@@ -189,7 +189,7 @@ __device__ __forceinline__ void fill_border(const FusedPhase& ph, uint8_t* smem,
 
 // One (tile, 16-channel chunk) unit of a conv epilogue for this lane's row.
 // what a unit needs of the running state: where this image's rows go
-struct UnitCtx { int out_shift, img_a, img_b, head_bytes; int8_t* out; int rank; };
+struct UnitCtx { int out_shift, img_a, img_b, head_bytes; int8_t* out; int rank; long long* tp; };
 
 // Stores of a phase whose work a cluster of C CTAs shares: every CTA keeps the whole tensor, so a result goes to the
 // same location of all of them (the others through distributed shared memory).  C == 1: a plain store.
@@ -216,8 +216,10 @@ template <int C>
 __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, const uint8_t* lut, const EpiChF* epi, uint32_t taddr,
                                           int row, int g, int rows, const UnitCtx& rt) {
   uint32_t v[16];
+  YF_STAMP(rt.tp, 12);
   tmem_ld16(taddr, v);
   tmem_ld_wait();
+  YF_STAMP(rt.tp, 13);
   if (row >= rows) return;
   const int nreal = ph.cout - g * 16;                        // real channels in this chunk (> 0)
   const int nwords = nreal >= 13 ? 4 : (nreal + 3) >> 2;     // warp-uniform
@@ -225,6 +227,7 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
   uint32_t w[4] = {0u, 0u, 0u, 0u};
   if (ph.has_lut) {
     requant_chunk<true>(v, ek, lut, nwords, w);
+    YF_STAMP(rt.tp, 14);
   } else {
     requant_chunk<false>(v, ek, lut, nwords, w);
     if (ph.add_off >= 0) {
@@ -269,10 +272,10 @@ __device__ __forceinline__ void conv_unit(const FusedPhase& ph, uint8_t* smem, c
 // (first conv: the CTA's tiles are t0, t0 + tstride, ... and only they are in its TMEM, at tcol0 + t * npad).
 template <int NT, int C = 1, bool DEAL = false>
 __device__ __forceinline__ void conv_epilogue(const FusedPhase& ph, const Cx& c, const uint8_t* slot, int t0, int nt, int rows, const Rt& rt, const FusedArgs& a,
-                                              int tcol0 = 0, int tstride = 1) {
+                                              int tcol0 = 0, int tstride = 1, long long* tp = nullptr) {
   constexpr int kWgs = DEAL ? Shape<NT>::wgs * C : Shape<NT>::wgs;
   const int wgi = DEAL ? (c.warp >> 2) * C + c.rank : (c.warp >> 2);
-  const UnitCtx u{rt.out_shift, rt.img_a, rt.img_b, a.head_bytes, a.out, c.rank};
+  const UnitCtx u{rt.out_shift, rt.img_a, rt.img_b, a.head_bytes, a.out, c.rank, tp};
   auto unit = [&](uint32_t taddr, int row, int g) {
     conv_unit<C>(ph, c.smem, slot + ph.lut_off, reinterpret_cast<const EpiChF*>(slot + ph.epi_off), taddr, row, g, rows, u);
   };
@@ -627,7 +630,7 @@ __device__ __forceinline__ void do_phase(const FusedPhase& ph, const int p, Cx& 
       ++c.use0;
       if (has_rows) {
         tc_fence_after();
-        conv_epilogue<NT, CF, (CF > 1)>(ph, c, slot, t0, nt, rows, rt, a);
+        conv_epilogue<NT, CF, (CF > 1)>(ph, c, slot, t0, nt, rows, rt, a, 0, 1, tp);
         tc_fence_before();
         if (t0 == 0) YF_STAMP(tp, 4);
       }

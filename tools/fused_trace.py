@@ -59,7 +59,7 @@ for i, (p, k) in enumerate(seq[:79]):
 print("total %d cycles; %s" % (tot, per_kind))
 # inner stamps of single phases (thread 0's view), one extra launch per phase: YF_B200_TRACE_INNER=3,5,8
 inner = [int(v) for v in os.environ.get("YF_B200_TRACE_INNER", "").split(",") if v]
-names = {0: "dw:start", 1: "dw:setup done", 2: "params landed", 3: "accumulators released", 4: "epilogue done", 5: "entry", 6: "before params wait",
+names = {12: "unit: before tcgen05.ld", 13: "unit: accumulators in registers", 14: "unit: requantised + table", 0: "dw:start", 1: "dw:setup done", 2: "params landed", 3: "accumulators released", 4: "epilogue done", 5: "entry", 6: "before params wait",
          8: "dw:loop done", 10: "before end barrier", 11: "after end barrier"}
 lead_names = {5: "entry", 1: "params landed", 2: "MMAs committed", 3: "accumulators ready", 4: "released + housekeeping", 10: "before end barrier", 11: "after end barrier"}
 for p in inner:
